@@ -1,0 +1,254 @@
+/*
+ * glrm_b200.h — C ABI of the B200-native GLRM proximal-gradient fitting engine.
+ *
+ * This is the drop-in boundary for ONE hot path of madeleineudell/LowRankModels.jl:
+ *     fit!(glrm::GLRM, params::ProxGradParams; ch, verbose)      src/algorithms/proxgrad.jl:34-220
+ * (threaded twin src/algorithms/proxgrad_multithread.jl:34-222).  The reference has no FFI; its
+ * extension point is Julia multiple dispatch on `T <: AbstractParams` (src/fit.jl:4,8-21), exactly
+ * how SparseProxGradParams plugs in (src/algorithms/sparse_proxgrad.jl:4-24).  A Julia maintainer
+ * adds `struct B200ProxGradParams <: AbstractParams` and a `fit!` method that `ccall`s the entry
+ * points below (the binding is shown in INTEGRATION.md and shipped, unexecuted, in
+ * lowrankmodels.jl_b200/julia/LowRankModelsB200.jl).
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns 0 on success or a negative
+ *     GLRMB200_E_* code; glrmb200_last_error() gives the thread-local message.
+ *   - the caller owns every host pointer; the library copies what it needs during the call and
+ *     never keeps a host pointer after returning.
+ *   - factor matrices are column-major Float64 exactly as Julia stores glrm.X (k x m) and
+ *     glrm.Y (k x d): element (r, c) at [c*k + r].
+ *   - all indices crossing the ABI are 0-based (the Julia shim subtracts 1).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     GLRMB200_E_NO_DEVICE.
+ */
+#ifndef GLRM_B200_H
+#define GLRM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLRMB200_VERSION 100          /* major*100 + minor */
+#define GLRMB200_LOSS_NPARAM 8        /* doubles per loss descriptor */
+#define GLRMB200_REG_NPARAM 4         /* doubles per regularizer descriptor */
+
+/* ---- status codes ------------------------------------------------------------------------- */
+enum {
+  GLRMB200_OK = 0,
+  GLRMB200_E_INVALID = -1,      /* bad argument / shape (reference: error(...) in src/glrm.jl:38-43) */
+  GLRMB200_E_UNSUPPORTED = -2,  /* loss / regularizer without a device implementation        */
+  GLRMB200_E_NO_DEVICE = -3,    /* no CUDA device: the engine never falls back to the CPU     */
+  GLRMB200_E_CUDA = -4,         /* CUDA runtime error (message has the call site)             */
+  GLRMB200_E_NCCL = -5,         /* NCCL error / libnccl not loadable                          */
+  GLRMB200_E_LABEL = -6,        /* label outside the loss's domain (reference: InexactError from
+                                   myBool, src/losses.jl:104; BoundsError for u[a])           */
+  GLRMB200_E_NAN = -7,          /* NaN among observed values (reference: src/glrm.jl:63-71)   */
+  GLRMB200_E_STATE = -8         /* call order (e.g. fit on a destroyed handle)                */
+};
+
+/* ---- loss codes (src/losses.jl) ----------------------------------------------------------- *
+ * loss_param[f*8 + ...]:  [0]=scale  [1]=p1  [2]=p2  [3]=bin_loss code  [4]=bin scale  [5]=bin p1
+ *   QUAD           losses.jl:138-146   -
+ *   L1             losses.jl:152-160   -
+ *   HUBER          losses.jl:166-177   p1=crossover
+ *   QUANTILE       losses.jl:186-201   p1=quantile
+ *   PERIODIC       losses.jl:209-218   p1=T
+ *   POISSON        losses.jl:231-241   -
+ *   ORDINAL_HINGE  losses.jl:247-292   p1=min p2=max
+ *   LOGISTIC       losses.jl:298-306   -            labels: 1 -> true; 0,-1 -> false (losses.jl:104)
+ *   WEIGHTED_HINGE losses.jl:317-341   p1=case_weight_ratio   (HingeLoss == ratio 1, losses.jl:324)
+ *   MULTINOMIAL    losses.jl:360-398   p2=max  (embedding dim = max)       labels 1..max
+ *   OVA            losses.jl:413-438   p2=max  [3..5]=bin loss             labels 1..max
+ *   BVS            losses.jl:450-475   p2=max  (embedding dim = max-1)     labels 1..max
+ *   ORDISTIC       losses.jl:490-519   p2=max
+ *   MULTINOMIAL_ORDINAL losses.jl:562-608  p2=max (embedding dim = max-1)
+ */
+enum {
+  GLRMB200_LOSS_QUAD = 1,
+  GLRMB200_LOSS_L1 = 2,
+  GLRMB200_LOSS_HUBER = 3,
+  GLRMB200_LOSS_QUANTILE = 4,
+  GLRMB200_LOSS_PERIODIC = 5,
+  GLRMB200_LOSS_POISSON = 6,
+  GLRMB200_LOSS_ORDINAL_HINGE = 7,
+  GLRMB200_LOSS_LOGISTIC = 8,
+  GLRMB200_LOSS_WEIGHTED_HINGE = 9,
+  GLRMB200_LOSS_MULTINOMIAL = 10,
+  GLRMB200_LOSS_OVA = 11,
+  GLRMB200_LOSS_BVS = 12,
+  GLRMB200_LOSS_ORDISTIC = 13,
+  GLRMB200_LOSS_MULTINOMIAL_ORDINAL = 14
+};
+
+/* ---- regularizer codes (src/regularizers.jl) ---------------------------------------------- *
+ * reg_code = base | wrapper flags;  reg_param[i*4 + ...]: [0]=scale / max_2norm / k
+ *   ZERO            regularizers.jl:91-97
+ *   QUAD            regularizers.jl:52-58     [0]=scale
+ *   QUAD_CONSTRAINT regularizers.jl:68-76     [0]=max_2norm
+ *   ONE             regularizers.jl:79-88     [0]=scale
+ *   NONNEG          regularizers.jl:101-114
+ *   NONNEG_ONE      regularizers.jl:118-138   [0]=scale (prox ignores it, as in the reference)
+ *   ONE_SPARSE      regularizers.jl:235-255
+ *   KSPARSE         regularizers.jl:258-291   [0]=k
+ *   UNIT_ONE_SPARSE regularizers.jl:295-318
+ *   SIMPLEX         regularizers.jl:323-348
+ * wrappers (the offset path, src/modify_glrm.jl:21-24):
+ *   LASTENTRY1            regularizers.jl:163-174   last factor entry pinned to 1
+ *   LASTENTRY_UNPENALIZED regularizers.jl:178-189   last factor entry skipped by the inner reg
+ */
+enum {
+  GLRMB200_REG_ZERO = 0,
+  GLRMB200_REG_QUAD = 1,
+  GLRMB200_REG_QUAD_CONSTRAINT = 2,
+  GLRMB200_REG_ONE = 3,
+  GLRMB200_REG_NONNEG = 4,
+  GLRMB200_REG_NONNEG_ONE = 5,
+  GLRMB200_REG_ONE_SPARSE = 6,
+  GLRMB200_REG_KSPARSE = 7,
+  GLRMB200_REG_UNIT_ONE_SPARSE = 8,
+  GLRMB200_REG_SIMPLEX = 9,
+  GLRMB200_REG_BASE_MASK = 0xff,
+  GLRMB200_REG_LASTENTRY1 = 0x100,
+  GLRMB200_REG_LASTENTRY_UNPENALIZED = 0x200
+};
+
+/* ---- the problem: what `GLRM(A, losses, rx, ry, k; ...)` holds (src/glrm.jl:12-22) ---------- *
+ * Observations replace glrm.observed_features / glrm.observed_examples (src/glrm.jl:9,17-18;
+ * built by sort_observations, src/modify_glrm.jl:5-18).  Both adjacency lists are passed because
+ * the reference keeps both and they may legitimately differ (order, duplicates, even content:
+ * src/cross_validate.jl:255-257).  Values of A are co-located with each list so the device
+ * never performs an A[e,f] lookup (src/algorithms/proxgrad.jl:125,168).
+ */
+typedef struct glrmb200_problem {
+  int64_t m;                 /* rows of A      (examples)                                      */
+  int64_t n;                 /* columns of A   (features)                                      */
+  int64_t k;                 /* rank                                                           */
+  int64_t d;                 /* sum of embedding dims == size(Y,2)   (losses.jl:72-93)         */
+
+  const int32_t* loss_code;  /* [n]                                                            */
+  const double*  loss_param; /* [n * GLRMB200_LOSS_NPARAM]                                     */
+
+  int64_t        rx_count;   /* 1 (one regularizer shared by all rows) or m                    */
+  const int32_t* rx_code;    /* [rx_count]                                                     */
+  const double*  rx_param;   /* [rx_count * GLRMB200_REG_NPARAM]                               */
+  int64_t        ry_count;   /* 1 or n                                                         */
+  const int32_t* ry_code;    /* [ry_count]                                                     */
+  const double*  ry_param;   /* [ry_count * GLRMB200_REG_NPARAM]                               */
+
+  int32_t obs_full;          /* 1: every entry observed (the UnitRange default,
+                                src/glrm.jl:33-34); `dense_A` is used, the lists are ignored   */
+  const double*  dense_A;    /* [m*n] column-major, as Julia stores A; labels as Float64       */
+
+  /* observed_features: for row e, entries row_ptr[e] .. row_ptr[e+1]-1 in list order           */
+  const int64_t* row_ptr;    /* [m+1]                                                          */
+  const int32_t* row_idx;    /* [nnz_rows] feature index f (0-based)                           */
+  const double*  row_val;    /* [nnz_rows] A[e,f]                                              */
+  /* observed_examples: for column f, entries col_ptr[f] .. col_ptr[f+1]-1 in list order        */
+  const int64_t* col_ptr;    /* [n+1]                                                          */
+  const int32_t* col_idx;    /* [nnz_cols] example index e (0-based)                           */
+  const double*  col_val;    /* [nnz_cols] A[e,f]                                              */
+} glrmb200_problem;
+
+/* ---- ProxGradParams (src/algorithms/proxgrad.jl:4-31), same seven fields -------------------- */
+typedef struct glrmb200_params {
+  double  stepsize;      /* initial step size                     (default 1.0)                */
+  int32_t max_iter;      /* outer iterations                      (default 100)                */
+  int32_t inner_iter_X;  /* prox-grad steps on X per outer iter   (default 1)                  */
+  int32_t inner_iter_Y;  /* prox-grad steps on Y per outer iter   (default 1)                  */
+  double  abs_tol;       /* stop if decrease < abs_tol * |Omega|  (default 1e-5)               */
+  double  rel_tol;       /* stop if decrease/obj < rel_tol        (default 1e-4)               */
+  double  min_stepsize;  /* line-search floor                     (default 0.01*stepsize)      */
+} glrmb200_params;
+
+/* per-fit device timings (CUDA events on the engine's own stream), all in milliseconds         */
+typedef struct glrmb200_profile {
+  double  setup_ms;        /* H2D of X,Y + initial objective                                   */
+  double  update_x_ms;     /* sum over iterations of the update-X launches                     */
+  double  update_y_ms;     /* sum over iterations of the update-Y launches                     */
+  double  reduce_ms;       /* objective reduction + D2H of the scalar                          */
+  double  comm_ms;         /* all-gathers (multi-GPU only)                                     */
+  double  loop_ms;         /* first update-X launch .. last iteration end                      */
+  int64_t x_launches;      /* kernels launched for X sweeps                                    */
+  int64_t y_launches;      /* kernels launched for Y sweeps                                    */
+  int64_t other_launches;  /* objective / reduction kernels                                    */
+  int64_t x_trials;        /* line-search trial passes summed over rows and iterations         */
+  int64_t y_trials;        /* line-search trial passes summed over columns and iterations      */
+  int32_t iterations;      /* outer iterations executed                                        */
+  int32_t reserved;
+} glrmb200_profile;
+
+typedef struct glrmb200_engine* glrmb200_handle;
+
+/* Library / device discovery. */
+int         glrmb200_version(void);
+const char* glrmb200_last_error(void);
+int         glrmb200_device_count(int32_t* count);          /* 0 devices => GLRMB200_E_NO_DEVICE */
+
+/* glrmb200_create: validate the problem (labels, NaN, shapes: src/glrm.jl:38-43,63-71),
+ * encode it for the device (int32 indices, k padded to a 32-byte multiple, degree-sorted
+ * schedules) and upload it to `device`.  Replaces the setup block src/algorithms/proxgrad.jl:38-105.
+ * rank/nranks describe the shard this handle owns (1-GPU: rank=0, nranks=1); with nranks>1 call
+ * glrmb200_comm_init before glrmb200_fit. */
+int glrmb200_create(glrmb200_handle* out, const glrmb200_problem* problem,
+                    int32_t device, int32_t rank, int32_t nranks);
+
+/* Multi-GPU plumbing (one process per GPU).  Rank 0 calls glrmb200_comm_unique_id and the host
+ * side (torch.distributed / Julia Distributed) broadcasts the 128 bytes; every rank then calls
+ * glrmb200_comm_init.  The data-path exchange is one all-gather of the freshly updated factor per
+ * half-iteration. */
+int glrmb200_comm_unique_id(uint8_t id[128]);
+int glrmb200_comm_init(glrmb200_handle h, const uint8_t id[128]);
+
+/* Row range [row_begin,row_end) and column range [col_begin,col_end) this handle updates
+ * (nnz-balanced contiguous shards; whole range when nranks==1). */
+int glrmb200_shard(glrmb200_handle h, int64_t* row_begin, int64_t* row_end,
+                   int64_t* col_begin, int64_t* col_end);
+
+/* glrmb200_fit: the whole outer loop of proxgrad.jl:107-217 on the device.
+ *   X [k*m], Y [k*d]   in/out, column-major (aliases of glrm.X / glrm.Y: mutated in place,
+ *                      proxgrad.jl:43,219; warm start = call again)
+ *   ch_objective[cap]  out: objective series exactly as the reference records it — entry 0 is the
+ *                      full objective (proxgrad.jl:76), later entries are sum(obj_by_col)
+ *                      = losses + ry only (proxgrad.jl:205)
+ *   ch_seconds[cap]    out: per-entry elapsed seconds (0 for entry 0), NOT cumulative; the shim
+ *                      feeds them to update_ch! (src/convergence.jl:16-27) which accumulates
+ *   n_recorded         out: entries written (<= max_iter+1; cap must be >= max_iter+1)
+ *   profile            optional (may be NULL) */
+int glrmb200_fit(glrmb200_handle h, const glrmb200_params* params,
+                 double* X, double* Y,
+                 double* ch_objective, double* ch_seconds, int32_t cap, int32_t* n_recorded,
+                 glrmb200_profile* profile);
+
+/* glrmb200_objective: objective(glrm, X, Y; include_regularization) of src/evaluate_fit.jl:57-83
+ * (loss summed over observed_examples, then calc_penalty :91-104), evaluated on observed entries
+ * only. */
+int glrmb200_objective(glrmb200_handle h, const double* X, const double* Y,
+                       int32_t include_regularization, double* out);
+
+/* Residency helpers for the callers that refit the same data (src/cross_validate.jl:141-240):
+ * rescale all regularizers (scale_regularizer!, src/glrm.jl:84-88) without re-uploading A. */
+int glrmb200_set_reg_scale(glrmb200_handle h, double newscale);
+
+/* Device-resident benchmarking hooks: keep factors on the device between calls so the timed
+ * region of bench.py's `value` leg contains no host<->device copies.
+ *   glrmb200_upload_factors  copies host X,Y to the device buffers
+ *   glrmb200_fit_resident    runs the loop on the resident factors (no X/Y copies; objective
+ *                            scalars still come back once per iteration)
+ *   glrmb200_download_factors copies the device factors to host X,Y */
+int glrmb200_upload_factors(glrmb200_handle h, const double* X, const double* Y);
+int glrmb200_fit_resident(glrmb200_handle h, const glrmb200_params* params,
+                          double* ch_objective, double* ch_seconds, int32_t cap,
+                          int32_t* n_recorded, glrmb200_profile* profile);
+int glrmb200_download_factors(glrmb200_handle h, double* X, double* Y);
+
+/* Step-size state (alpharow / alphacol, proxgrad.jl:69-70) for tests: n_row = m, n_col = n. */
+int glrmb200_get_stepsizes(glrmb200_handle h, double* alpharow, double* alphacol);
+
+int glrmb200_destroy(glrmb200_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLRM_B200_H */

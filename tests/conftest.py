@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def lrm():
+    import lowrankmodels_b200
+    return lowrankmodels_b200
+
+
+@pytest.fixture(scope="session")
+def orc():
+    import oracle_py
+    oracle_py.lib()
+    return oracle_py
