@@ -201,6 +201,10 @@ int glrmb200_create(glrmb200_handle* out, const glrmb200_problem* problem,
 int glrmb200_comm_unique_id(uint8_t id[128]);
 int glrmb200_comm_init(glrmb200_handle h, const uint8_t id[128]);
 
+/* Host-only shard planner (no device needed): contiguous ranges balanced by observation count.
+ * ptr = row_ptr / col_ptr ([count+1]) or NULL (balance by unit count); bounds receives nranks+1 entries. */
+int glrmb200_plan_shards(const int64_t* ptr, int64_t count, int32_t nranks, int64_t* bounds);
+
 /* Row range [row_begin,row_end) and column range [col_begin,col_end) this handle updates
  * (nnz-balanced contiguous shards; whole range when nranks==1). */
 int glrmb200_shard(glrmb200_handle h, int64_t* row_begin, int64_t* row_end,

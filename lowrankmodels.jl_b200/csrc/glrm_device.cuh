@@ -1,0 +1,593 @@
+// glrm_device.cuh — device side of the B200 GLRM prox-grad engine (sm_100a).
+//
+// One *unit* = one factor column (a row's x_e in the X sweep, a feature's y_f in the Y sweep).
+// The fused update kernel does, for its unit, everything the reference does between
+// proxgrad.jl:119-155 (X) / :163-200 (Y):
+//   gradient pass  : gather the opposite factor's columns at the observed entries, u = x.y,
+//                    loss + dloss/du (losses.jl), g += dloss * y, and the unit's current objective
+//                    (row_objective / col_objective, evaluate_fit.jl:24-55) in the same pass
+//   line search    : x_new = prox(x - (alpha/l) g, alpha/l) in registers (regularizers.jl), trial
+//                    objective by a second gather pass, accept iff new < old (strict), alpha*1.05 /
+//                    alpha*0.7 with the min_stepsize floor (proxgrad.jl:136-155)
+//   write-back     : the accepted column, alpha, and the unit's recorded objective.
+//
+// Thread mapping.  A *lane group* of G lanes owns one observed entry at a time; lane `lg` of the group
+// holds R double2 slices of the k-vector (elements 2*(lg+G*r), +1), so a group reads one factor column
+// with R coalesced 16-byte loads per lane and reduces the dot product with log2(G) shuffles.  A warp
+// holds 32/G groups; a unit is processed by W warps (W=1: one warp per unit, no block barrier;
+// W=8: one CTA per heavy unit, cross-warp reduction through shared memory in a fixed order).
+// Every reduction tree depends only on (G, R, W, degree): results are independent of which SM / GPU
+// the unit lands on.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/glrm_b200.h"
+
+namespace glrm {
+
+constexpr unsigned FULLMASK = 0xffffffffu;
+enum : int { FLAG_EVAL_ONLY = 1, FLAG_NO_REG = 2, FLAG_LOSS_BY_ENTRY = 4 };
+
+struct SweepArgs {
+  // observation lists of this side (shard-local), see glrm_b200.h
+  const int64_t* ptr;     // [units+1] rebased to the shard, or nullptr when fully observed
+  const int32_t* idx;     // opposite index per entry, or nullptr (fully observed: idx = position)
+  const double* val;      // A values aligned with the lists
+  int64_t full_len;       // list length when fully observed
+  int64_t unit_base;      // first unit of the shard (ptr is indexed by unit - unit_base)
+  const int32_t* order;   // schedule: unit ids, heaviest first
+  int64_t n_units;        // units this launch covers: order[0 .. n_units)
+  double* own;            // factor being updated   [units_total * kp]
+  const double* opp;      // factor being gathered  [opp_total * kp]
+  int32_t kp;             // padded rank (multiple of 4 doubles = 32 B)
+  int32_t k;              // rank
+  const int32_t* loss_code;   // [n] per feature
+  const double* loss_param;   // [n * 8]
+  double uparam[3];           // uniform loss parameters (scale, p1, p2) when LOSS != 0
+  const int32_t* reg_code;    // [1] or [units_total]
+  const double* reg_param;    // [1*4] or [units_total*4]
+  int32_t reg_uniform;
+  int32_t flags;
+  double* alpha;          // [units_total] step sizes (alpharow / alphacol, proxgrad.jl:69-70)
+  double min_stepsize;
+  double* obj_out;        // [units_total] recorded objective of the unit (obj_by_col, proxgrad.jl:178,190)
+  unsigned long long* trial_counter;  // total line-search trials (profile)
+};
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  return v;
+}
+template <int G>
+__device__ __forceinline__ int group_sum_i(int v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  return v;
+}
+// sum over the 32/G groups of a warp (every lane of a group holds the same value on entry)
+template <int G>
+__device__ __forceinline__ double cross_group_sum(double v) {
+#pragma unroll
+  for (int o = G; o < 32; o <<= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  return v;
+}
+__device__ __forceinline__ double jl_max0(double x) { return (x != x) ? x : (x > 0.0 ? x : 0.0); }   // max(x,0)
+__device__ __forceinline__ double jl_min0(double x) { return (x != x) ? x : (x < 0.0 ? x : 0.0); }   // min(x,0)
+__device__ __forceinline__ double jl_maxd(double a, double b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
+__device__ __forceinline__ double jl_mind(double a, double b) { return (a != a || b != b) ? NAN : (a < b ? a : b); }
+__device__ __forceinline__ double jl_sign(double x) { return (double)((x > 0.0) - (x < 0.0)); }
+
+// ------------------------------------------------------------------------------------------------
+// scalar losses (losses.jl:136-341): value and d/du in one call.  LOSS != 0 fixes the code at
+// compile time (uniform-loss problems); LOSS == 0 switches on `code` (warp-uniform in the Y sweep,
+// per-entry in the X sweep of heterogeneous problems).
+template <int LOSS, bool WANT_GRAD>
+__device__ __forceinline__ void loss_eval(int code, double s, double p1, double p2, double u, double a,
+                                          double& l, double& c) {
+  const int cd = LOSS ? LOSS : code;
+  c = 0.0;
+  switch (cd) {
+    case GLRMB200_LOSS_QUAD: {                       // losses.jl:144,146
+      const double d = u - a;
+      l = s * (d * d);
+      if (WANT_GRAD) c = 2.0 * d * s;
+    } break;
+    case GLRMB200_LOSS_L1: {                         // :158,160
+      const double d = u - a;
+      l = s * fabs(d);
+      if (WANT_GRAD) c = jl_sign(d) * s;
+    } break;
+    case GLRMB200_LOSS_HUBER: {                      // :173-177 (grad has no factor 2, as in the reference)
+      const double d = u - a, ad = fabs(d);
+      l = ad > p1 ? (ad - p1 + p1 * p1) * s : d * d * s;
+      if (WANT_GRAD) c = ad > p1 ? jl_sign(d) * s : d * s;
+    } break;
+    case GLRMB200_LOSS_QUANTILE: {                   // :193-201
+      const double diff = a - u;
+      l = diff > 0.0 ? s * p1 * diff : -s * (1.0 - p1) * diff;
+      if (WANT_GRAD) c = diff > 0.0 ? -s * p1 : s * (1.0 - p1);
+    } break;
+    case GLRMB200_LOSS_PERIODIC: {                   // :216,218
+      const double w = (a - u) * (2.0 * M_PI) / p1;
+      l = s * (1.0 - cos(w));
+      if (WANT_GRAD) c = -s * ((2.0 * M_PI) / p1) * sin(w);
+    } break;
+    case GLRMB200_LOSS_POISSON: {                    // :237-241
+      const double eu = exp(u);
+      l = s * (eu - a * u + (a == 0.0 ? 0.0 : a * (log(a) - 1.0)));
+      if (WANT_GRAD) c = s * (eu - a);
+    } break;
+    case GLRMB200_LOSS_ORDINAL_HINGE: {              // :258-292  (p1 = min, p2 = max)
+      double n, loss;
+      if (u > p2 - 1.0) {
+        n = jl_mind(floor(u), p2 - 1.0) - a;
+        loss = n * (n + 1.0) / 2.0 + (n + 1.0) * (u - p2 + 1.0);
+      } else if (u > a) {
+        n = jl_mind(floor(u), p2) - a;
+        loss = n * (n + 1.0) / 2.0 + (n + 1.0) * (u - floor(u));
+      } else if (u > p1 + 1.0) {
+        n = a - jl_maxd(ceil(u), p1 + 1.0);
+        loss = n * (n + 1.0) / 2.0 + (n + 1.0) * (ceil(u) - u);
+      } else {
+        n = a - jl_maxd(ceil(u), p1 + 1.0);
+        loss = n * (n + 1.0) / 2.0 + (n + 1.0) * (p1 + 1.0 - u);
+      }
+      l = s * loss;
+      if (WANT_GRAD) c = s * (u > a ? (jl_mind(ceil(u), p2) - a) : -(a - jl_maxd(floor(u), p1)));
+    } break;
+    case GLRMB200_LOSS_LOGISTIC: {                   // :304,306 (labels: 1 -> +1, 0/-1 -> -1, :104)
+      const double aa = (a == 1.0) ? 1.0 : -1.0;
+      const double e = exp(-aa * u);                 // exp(-(2a-1)u)
+      l = s * log(1.0 + e);
+      if (WANT_GRAD) c = -aa * s / (1.0 + exp(aa * u));
+    } break;
+    case GLRMB200_LOSS_WEIGHTED_HINGE: {             // :326-341 (p1 = case_weight_ratio)
+      const bool pos = (a == 1.0);
+      const double an = pos ? 1.0 : -1.0;
+      l = s * jl_max0(1.0 - an * u);
+      if (WANT_GRAD) c = (an * u >= 1.0) ? 0.0 : -an * s;
+      if (p1 != 1.0 && pos) { l *= p1; c *= p1; }
+    } break;
+    default: l = NAN; break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// regularizers on a k-vector distributed over a lane group (regularizers.jl:52-348).
+// Lane `lg` holds v[r] = elements (i0, i0+1), i0 = 2*(lg + G*r).  `kin` = number of elements the inner
+// regularizer sees (k, or k-1 under the offset wrappers lastentry1 / lastentry_unpenalized :163-189).
+struct ArgMax { double v; int i; };
+__device__ __forceinline__ bool am_better(double av, int ai, double bv, int bi) {   // Julia argmax: first max, NaN wins
+  const bool an = av != av, bn = bv != bv;
+  if (an || bn) return an && (!bn || ai < bi);
+  return av > bv || (av == bv && ai < bi);
+}
+template <int G>
+__device__ __forceinline__ ArgMax group_argmax(ArgMax m) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(FULLMASK, m.v, o);
+    const int oi = __shfl_xor_sync(FULLMASK, m.i, o);
+    if (am_better(ov, oi, m.v, m.i)) { m.v = ov; m.i = oi; }
+  }
+  return m;
+}
+
+template <int G, int R>
+__device__ __forceinline__ double reg_eval(int code, const double* __restrict__ rp, const double2 (&v)[R], int lg, int k) {
+  const int base = code & GLRMB200_REG_BASE_MASK;
+  const bool wrapped = code & (GLRMB200_REG_LASTENTRY1 | GLRMB200_REG_LASTENTRY_UNPENALIZED);
+  const int kin = wrapped ? k - 1 : k;
+  double s1 = 0.0, s2 = 0.0, sabs = 0.0;
+  int neg = 0, nz = 0, ones = 0, other = 0, badlast = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i0 = 2 * (lg + G * r);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const double e = h ? v[r].y : v[r].x;
+      const int i = i0 + h;
+      if (i < kin) {
+        s1 += e; s2 += e * e; sabs += fabs(e);
+        neg += (e < 0.0); nz += (e != 0.0); ones += (e == 1.0); other += (e != 0.0 && e != 1.0);
+      }
+      if ((code & GLRMB200_REG_LASTENTRY1) && i == k - 1 && e != 1.0) badlast = 1;   // :171
+    }
+  }
+  double res;
+  switch (base) {
+    case GLRMB200_REG_ZERO: res = 0.0; break;                                                   // :95
+    case GLRMB200_REG_QUAD: res = rp[0] * group_sum<G>(s2); break;                              // :58
+    case GLRMB200_REG_QUAD_CONSTRAINT: res = sqrt(group_sum<G>(s2)) > rp[0] + 1e-12 ? INFINITY : 0.0; break;  // :74
+    case GLRMB200_REG_ONE: res = rp[0] * group_sum<G>(sabs); break;                             // :88
+    case GLRMB200_REG_NONNEG: res = group_sum_i<G>(neg) ? INFINITY : 0.0; break;                // :105-112
+    case GLRMB200_REG_NONNEG_ONE: {                                                             // :129-136
+      const int n = group_sum_i<G>(neg);
+      const double t = group_sum<G>(s1);
+      res = n ? INFINITY : rp[0] * t;
+    } break;
+    case GLRMB200_REG_ONE_SPARSE: res = group_sum_i<G>(nz) > 1 ? INFINITY : 0.0; break;         // :239-253
+    case GLRMB200_REG_KSPARSE: res = group_sum_i<G>(nz) > (int)rp[0] ? INFINITY : 0.0; break;   // :261-276
+    case GLRMB200_REG_UNIT_ONE_SPARSE: {                                                        // :300-316
+      const int o = group_sum_i<G>(ones), x = group_sum_i<G>(other);
+      res = (x || o > 1) ? INFINITY : 0.0;
+    } break;
+    case GLRMB200_REG_SIMPLEX: {                                                                // :338-346
+      const double t = group_sum<G>(s1);
+      const int n = group_sum_i<G>(neg);
+      res = (fabs(t - 1.0) > 1e-12 || n) ? INFINITY : 0.0;
+    } break;
+    default: res = NAN; break;
+  }
+  if (code & GLRMB200_REG_LASTENTRY1) { if (group_sum_i<G>(badlast)) res = INFINITY; }
+  return res;
+}
+
+template <int G, int R>
+__device__ __forceinline__ void reg_prox(int code, const double* __restrict__ rp, double2 (&v)[R], int lg, int k, double alpha) {
+  const int base = code & GLRMB200_REG_BASE_MASK;
+  const bool wrapped = code & (GLRMB200_REG_LASTENTRY1 | GLRMB200_REG_LASTENTRY_UNPENALIZED);
+  const int kin = wrapped ? k - 1 : k;
+#define GLRM_FOREACH(BODY)                                              \
+  _Pragma("unroll") for (int r = 0; r < R; ++r) {                       \
+    const int i0 = 2 * (lg + G * r);                                    \
+    { double& e = v[r].x; const int i = i0; if (i < kin) { BODY; } }     \
+    { double& e = v[r].y; const int i = i0 + 1; if (i < kin) { BODY; } } \
+  }
+  switch (base) {
+    case GLRMB200_REG_ZERO: break;                                                              // :93
+    case GLRMB200_REG_QUAD: {                                                                   // :56
+      const double c = 1.0 / (1.0 + 2.0 * alpha * rp[0]);
+      GLRM_FOREACH(e = c * e; (void)i)
+    } break;
+    case GLRMB200_REG_QUAD_CONSTRAINT: {                                                        // :72
+      double s2 = 0.0;
+      GLRM_FOREACH(s2 += e * e; (void)i)
+      const double c = rp[0] / sqrt(group_sum<G>(s2));
+      GLRM_FOREACH(e = c * e; (void)i)
+    } break;
+    case GLRMB200_REG_ONE: {                                                                    // :83-87
+      const double t = rp[0] * alpha;
+      GLRM_FOREACH(e = jl_max0(e - t) + jl_min0(e + t); (void)i)
+    } break;
+    case GLRMB200_REG_NONNEG: GLRM_FOREACH(e = jl_max0(e); (void)i) break;                      // :103
+    case GLRMB200_REG_NONNEG_ONE: GLRM_FOREACH(e = jl_max0(e - alpha); (void)i) break;          // :122
+    case GLRMB200_REG_ONE_SPARSE:                                                               // :237
+    case GLRMB200_REG_UNIT_ONE_SPARSE: {                                                        // :297
+      ArgMax m{-INFINITY, 0x7fffffff};
+      GLRM_FOREACH(if (am_better(e, i, m.v, m.i)) { m.v = e; m.i = i; })
+      m = group_argmax<G>(m);
+      const bool unit = base == GLRMB200_REG_UNIT_ONE_SPARSE;
+      GLRM_FOREACH(e = (i == m.i) ? (unit ? 1.0 : e) : 0.0)
+    } break;
+    case GLRMB200_REG_KSPARSE: {                                                                // :277-283
+      // keep the kk entries of largest |v| (ties: lowest index first): kk rounds of group arg-max
+      const int kk = (int)rp[0];
+      unsigned keep = 0;  // bit 2r+h of this lane
+      for (int round = 0; round < kk && round < kin; ++round) {
+        ArgMax m{-INFINITY, 0x7fffffff};
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i0 = 2 * (lg + G * r);
+          if (i0 < kin && !(keep >> (2 * r) & 1u) && am_better(fabs(v[r].x), i0, m.v, m.i)) { m.v = fabs(v[r].x); m.i = i0; }
+          if (i0 + 1 < kin && !(keep >> (2 * r + 1) & 1u) && am_better(fabs(v[r].y), i0 + 1, m.v, m.i)) { m.v = fabs(v[r].y); m.i = i0 + 1; }
+        }
+        m = group_argmax<G>(m);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i0 = 2 * (lg + G * r);
+          if (m.i == i0) keep |= 1u << (2 * r);
+          if (m.i == i0 + 1) keep |= 1u << (2 * r + 1);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i0 = 2 * (lg + G * r);
+        if (i0 < kin && !(keep >> (2 * r) & 1u)) v[r].x = 0.0;
+        if (i0 + 1 < kin && !(keep >> (2 * r + 1) & 1u)) v[r].y = 0.0;
+      }
+    } break;
+    case GLRMB200_REG_SIMPLEX: {                                                                // :325-337
+      // walk the entries in descending order (group arg-max per step) instead of sorting:
+      // t = (ysum[i]-1)/i at the first i with (ysum[i]-1)/i >= y[i+1], else (ysum[n]-1)/n
+      unsigned used = 0;
+      double ysum = 0.0, t = 0.0;
+      bool found = false;
+      for (int step = 0; step < kin; ++step) {
+        ArgMax m{-INFINITY, 0x7fffffff};
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i0 = 2 * (lg + G * r);
+          if (i0 < kin && !(used >> (2 * r) & 1u) && am_better(v[r].x, i0, m.v, m.i)) { m.v = v[r].x; m.i = i0; }
+          if (i0 + 1 < kin && !(used >> (2 * r + 1) & 1u) && am_better(v[r].y, i0 + 1, m.v, m.i)) { m.v = v[r].y; m.i = i0 + 1; }
+        }
+        m = group_argmax<G>(m);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i0 = 2 * (lg + G * r);
+          if (m.i == i0) used |= 1u << (2 * r);
+          if (m.i == i0 + 1) used |= 1u << (2 * r + 1);
+        }
+        // m.v is y[step+1] (1-based); test the candidate built from the first `step` entries
+        if (step > 0 && !found && (ysum - 1.0) / (double)step >= m.v) { t = (ysum - 1.0) / (double)step; found = true; }
+        ysum += m.v;
+      }
+      if (!found) t = (ysum - 1.0) / (double)kin;
+      GLRM_FOREACH(e = jl_max0(e - t); (void)i)
+    } break;
+    default: break;
+  }
+#undef GLRM_FOREACH
+  if (code & GLRMB200_REG_LASTENTRY1) {                                                         // :168
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i0 = 2 * (lg + G * r);
+      if (i0 == k - 1) v[r].x = 1.0;
+      if (i0 + 1 == k - 1) v[r].y = 1.0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One pass over the unit's observed entries.  GRAD: accumulate g and the objective; otherwise the
+// objective only (line-search trial).  UNROLL entries per group are in flight together.
+template <int G, int R, int W, int LOSS, bool GRAD>
+__device__ __forceinline__ void entry_pass(const SweepArgs& A, int64_t start, int64_t len, int gid, int lg,
+                                           const double2 (&x)[R], const bool (&in)[R], int ucode, double us,
+                                           double up1, double up2, double2 (&g)[R], double& obj) {
+  constexpr int NG = (32 / G) * W;
+  constexpr int UNROLL = (R >= 4) ? 2 : 4;
+  const bool by_entry = (LOSS == 0) && (A.flags & FLAG_LOSS_BY_ENTRY);
+  obj = 0.0;
+  if (GRAD) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) g[r] = make_double2(0.0, 0.0);
+  }
+  for (int64_t t0 = 0; t0 < len; t0 += (int64_t)NG * UNROLL) {
+    int32_t j[UNROLL];
+    double a[UNROLL];
+    bool act[UNROLL];
+    double2 y[UNROLL][R];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t t = t0 + (int64_t)u * NG + gid;
+      act[u] = t < len;
+      const int64_t q = start + (act[u] ? t : 0);
+      j[u] = act[u] ? (A.idx ? __ldg(A.idx + q) : (int32_t)t) : 0;
+      a[u] = act[u] ? __ldg(A.val + q) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const double* yp = A.opp + (int64_t)j[u] * A.kp + 2 * lg;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        y[u][r] = (act[u] && in[r]) ? __ldg(reinterpret_cast<const double2*>(yp + 2 * G * r)) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      double dot = 0.0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) dot = fma(y[u][r].x, x[r].x, fma(y[u][r].y, x[r].y, dot));
+      dot = group_sum<G>(dot);
+      int code = ucode;
+      double s = us, p1 = up1, p2 = up2;
+      if (by_entry && act[u]) {
+        code = __ldg(A.loss_code + j[u]);
+        const double* lp = A.loss_param + (int64_t)j[u] * GLRMB200_LOSS_NPARAM;
+        s = __ldg(lp); p1 = __ldg(lp + 1); p2 = __ldg(lp + 2);
+      }
+      double l, c;
+      loss_eval<LOSS, GRAD>(code, s, p1, p2, dot, a[u], l, c);
+      if (act[u]) {
+        obj += l;
+        if (GRAD) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) { g[r].x = fma(c, y[u][r].x, g[r].x); g[r].y = fma(c, y[u][r].y, g[r].y); }
+        }
+      }
+    }
+  }
+}
+
+// reduce (obj [, g]) over all groups of the unit: shuffles inside the warp, shared memory across warps
+template <int G, int R, int W, bool WITH_G>
+__device__ __forceinline__ void unit_reduce(double& obj, double2 (&g)[R], double* red, int lane, int warp, int lg) {
+  obj = cross_group_sum<G>(obj);
+  if (WITH_G) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) { g[r].x = cross_group_sum<G>(g[r].x); g[r].y = cross_group_sum<G>(g[r].y); }
+  }
+  if (W > 1) {
+    constexpr int STRIDE = G * 2 * R + 1;
+    __syncthreads();
+    if (lane < G) {
+      if (WITH_G) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) { red[warp * STRIDE + (lg * R + r) * 2] = g[r].x; red[warp * STRIDE + (lg * R + r) * 2 + 1] = g[r].y; }
+      }
+      if (lane == 0) red[warp * STRIDE + G * 2 * R] = obj;
+    }
+    __syncthreads();
+    double o = 0.0;
+    double2 acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = make_double2(0.0, 0.0);
+    for (int w = 0; w < W; ++w) {   // fixed order
+      o += red[w * STRIDE + G * 2 * R];
+      if (WITH_G) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) { acc[r].x += red[w * STRIDE + (lg * R + r) * 2]; acc[r].y += red[w * STRIDE + (lg * R + r) * 2 + 1]; }
+      }
+    }
+    obj = o;
+    if (WITH_G) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) g[r] = acc[r];
+    }
+  }
+}
+
+template <int G, int R, int W, int LOSS>
+__device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, double* red) {
+  constexpr int NGW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int warp = (W == 1) ? 0 : (threadIdx.x >> 5);
+  const int lg = lane % G;
+  const int gid = warp * NGW + lane / G;
+  const int kp = A.kp, k = A.k;
+
+  int64_t start, len;
+  if (A.ptr) {
+    start = A.ptr[unit - A.unit_base];
+    len = A.ptr[unit - A.unit_base + 1] - start;
+  } else {
+    start = (unit - A.unit_base) * A.full_len;
+    len = A.full_len;
+  }
+  double* own = A.own + unit * (int64_t)kp;
+  double2 x[R];
+  bool in[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i0 = 2 * (lg + G * r);
+    in[r] = i0 < kp;
+    x[r] = in[r] ? *reinterpret_cast<const double2*>(own + i0) : make_double2(0.0, 0.0);
+  }
+  // loss descriptor: uniform (template / by value), per unit (Y sweep), or per entry (X sweep)
+  int ucode = LOSS;
+  double us = A.uparam[0], up1 = A.uparam[1], up2 = A.uparam[2];
+  if (LOSS == 0 && !(A.flags & FLAG_LOSS_BY_ENTRY)) {
+    ucode = A.loss_code[unit];
+    const double* lp = A.loss_param + unit * GLRMB200_LOSS_NPARAM;
+    us = lp[0]; up1 = lp[1]; up2 = lp[2];
+  }
+  const int rcode = A.reg_code[A.reg_uniform ? 0 : unit];
+  const double* rp = A.reg_param + (A.reg_uniform ? 0 : unit) * GLRMB200_REG_NPARAM;
+  const bool use_reg = !(A.flags & FLAG_NO_REG);
+
+  // ---- gradient pass (proxgrad.jl:119-135 / :163-178) ----------------------------------------
+  double2 g[R];
+  double obj_old;
+  entry_pass<G, R, W, LOSS, true>(A, start, len, gid, lg, x, in, ucode, us, up1, up2, g, obj_old);
+  unit_reduce<G, R, W, true>(obj_old, g, red, lane, warp, lg);
+  if (use_reg) obj_old += reg_eval<G, R>(rcode, rp, x, lg, k);
+
+  double alpha = A.alpha[unit];
+  double obj_rec = obj_old;
+  int ntrials = 0;
+  bool accepted = false;
+  if (!(A.flags & FLAG_EVAL_ONLY)) {
+    const double l1 = (double)(len + 1);                                 // proxgrad.jl:134
+    while (alpha > A.min_stepsize) {                                     // :136
+      const double stepsize = alpha / l1;                                // :137
+      double2 xn[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) { xn[r].x = fma(-stepsize, g[r].x, x[r].x); xn[r].y = fma(-stepsize, g[r].y, x[r].y); }  // :140
+      reg_prox<G, R>(rcode, rp, xn, lg, k, stepsize);                    // :142
+      double2 dummy[R];
+      double obj_new;
+      entry_pass<G, R, W, LOSS, false>(A, start, len, gid, lg, xn, in, ucode, us, up1, up2, dummy, obj_new);
+      unit_reduce<G, R, W, false>(obj_new, dummy, red, lane, warp, lg);
+      obj_new += reg_eval<G, R>(rcode, rp, xn, lg, k);
+      ++ntrials;
+      if (obj_new < obj_old) {                                           // :143 (strict; NaN rejects)
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r] = xn[r];                        // :144
+        alpha *= 1.05;                                                   // :145
+        obj_rec = obj_new;                                               // :190
+        accepted = true;
+        break;
+      } else {
+        alpha *= .7;                                                     // :149
+        if (alpha < A.min_stepsize) { alpha = A.min_stepsize * 1.1; break; }   // :150-153
+      }
+    }
+  }
+  if (gid == 0) {
+    if (accepted) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i0 = 2 * (lg + G * r);
+        if (in[r]) *reinterpret_cast<double2*>(own + i0) = x[r];
+      }
+    }
+    if (lg == 0) {
+      A.alpha[unit] = alpha;
+      A.obj_out[unit] = obj_rec;
+      if (ntrials && A.trial_counter) atomicAdd(A.trial_counter, (unsigned long long)ntrials);
+    }
+  }
+}
+
+constexpr int WARPS_PER_CTA_LIGHT = 4;
+constexpr int WARPS_PER_CTA_HEAVY = 8;
+
+// light units: one warp per unit, no block-level synchronisation
+template <int G, int R, int LOSS>
+__global__ void __launch_bounds__(WARPS_PER_CTA_LIGHT * 32) sweep_warp_kernel(const SweepArgs A) {
+  const int64_t slot = (int64_t)blockIdx.x * WARPS_PER_CTA_LIGHT + (threadIdx.x >> 5);
+  if (slot >= A.n_units) return;
+  process_unit<G, R, 1, LOSS>(A, A.order[slot], nullptr);
+}
+
+// heavy units: one CTA (8 warps) per unit
+template <int G, int R, int LOSS>
+__global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32) sweep_cta_kernel(const SweepArgs A) {
+  __shared__ double red[WARPS_PER_CTA_HEAVY * (G * 2 * R + 1)];
+  process_unit<G, R, WARPS_PER_CTA_HEAVY, LOSS>(A, A.order[blockIdx.x], red);
+}
+
+// out[0] = sum(v[0..n)) in a fixed order (obj = sum(obj_by_col), proxgrad.jl:205)
+__global__ void __launch_bounds__(1024) sum_kernel(const double* __restrict__ v, int64_t n, double* out) {
+  __shared__ double sh[1024];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) acc += v[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+// out[unit] = r(own[:, unit])  — the penalty terms of calc_penalty (evaluate_fit.jl:91-104)
+template <int G, int R>
+__global__ void __launch_bounds__(128) reg_eval_kernel(const double* __restrict__ own, int64_t units, int kp, int k,
+                                                       const int32_t* reg_code, const double* reg_param,
+                                                       int reg_uniform, double* out) {
+  const int lane = threadIdx.x & 31, lg = lane % G;
+  const int64_t unit = ((int64_t)blockIdx.x * 4 + (threadIdx.x >> 5)) * (32 / G) + lane / G;
+  const bool ok = unit < units;
+  double2 x[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i0 = 2 * (lg + G * r);
+    x[r] = (ok && i0 < kp) ? *reinterpret_cast<const double2*>(own + unit * (int64_t)kp + i0) : make_double2(0.0, 0.0);
+  }
+  const int64_t ru = (reg_uniform || !ok) ? 0 : unit;
+  const double v = reg_eval<G, R>(reg_code[ru], reg_param + ru * GLRMB200_REG_NPARAM, x, lg, k);
+  if (ok && lg == 0) out[unit] = v;
+}
+
+// dst[c*rows + r] = src[r*cols + c]   (row-major copy of the Julia column-major A for the X sweep)
+__global__ void transpose_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t rows, int64_t cols) {
+  __shared__ double tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = src[r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+}  // namespace glrm

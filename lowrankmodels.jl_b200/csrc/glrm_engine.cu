@@ -1,0 +1,762 @@
+// glrm_engine.cu — host side of the B200 GLRM prox-grad engine and the C ABI (include/glrm_b200.h).
+//
+// Replaces, behind a C boundary, fit!(glrm::GLRM, params::ProxGradParams) of
+// /root/reference/src/algorithms/proxgrad.jl:34-220: problem encoding + upload (create), the whole
+// alternating loop with the objective record and the stopping rule (fit), objective() of
+// src/evaluate_fit.jl:57-83.  No CPU compute path exists here: without a CUDA device every entry
+// point fails with GLRMB200_E_NO_DEVICE.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "glrm_device.cuh"
+
+using namespace glrm;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_OK(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(GLRMB200_E_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen (no link-time dependency: single-GPU users never load it)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId_t;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId_t*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId_t, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+  if (g_nccl.lib) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+  if (!h) return fail(GLRMB200_E_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) return fail(GLRMB200_E_NCCL, "libnccl lacks %s", name)
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(Broadcast, "ncclBroadcast");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  g_nccl.lib = h;
+  return 0;
+}
+#define NCCL_OK(call)                                                                              \
+  do {                                                                                             \
+    int r__ = (call);                                                                              \
+    if (r__ != 0) return fail(GLRMB200_E_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r__)); \
+  } while (0)
+static const int kNcclDouble = 8;  // ncclFloat64 (nccl.h ncclDataType_t)
+
+// ------------------------------------------------------------------------------------------------
+// engine state
+struct Side {
+  int64_t units = 0;          // total units on this side (m or n)
+  int64_t begin = 0, end = 0; // shard owned by this rank
+  int64_t full_len = 0;
+  int64_t nnz_local = 0;
+  int64_t* d_ptr = nullptr;
+  int32_t* d_idx = nullptr;
+  double* d_val = nullptr;
+  int32_t* d_order = nullptr;
+  int64_t n_heavy = 0, n_light = 0;
+  int32_t* d_reg_code = nullptr;
+  double* d_reg_param = nullptr;
+  std::vector<double> h_reg_param;  // for set_reg_scale
+  std::vector<int32_t> h_reg_code;
+  int reg_uniform = 1;
+  double* d_alpha = nullptr;
+  double* d_obj = nullptr;    // obj_by_row / obj_by_col
+  std::vector<int64_t> bounds;  // [nranks+1] shard boundaries (all ranks)
+};
+
+struct glrmb200_engine {
+  int device = 0, rank = 0, nranks = 1;
+  int64_t m = 0, n = 0, k = 0, d = 0;
+  int kp = 0;
+  int tile_g = 0, tile_r = 0;
+  int loss_template = 0;   // 0 generic, else uniform loss code instantiated at compile time
+  double uparam[3] = {1, 0, 0};
+  int64_t heavy_threshold = 1024;
+  int64_t nnz_rows_total = 0;
+  bool obs_full = false;
+  Side rows, cols;
+  int32_t* d_loss_code = nullptr;
+  double* d_loss_param = nullptr;
+  double* d_X = nullptr;
+  double* d_Y = nullptr;
+  double* d_scalars = nullptr;              // [4]
+  unsigned long long* d_trials = nullptr;   // [2]
+  double* h_pinned = nullptr;               // [8]
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  ncclComm_t comm = nullptr;
+  bool factors_resident = false;
+};
+
+static int g_device_checked = -1;
+static int check_device() {
+  if (g_device_checked > 0) return 0;
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt == 0) {
+    cudaGetLastError();
+    return fail(GLRMB200_E_NO_DEVICE, "no CUDA device is visible (%s); this engine has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  g_device_checked = cnt;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side helpers
+static int loss_dim(int code, const double* p) {
+  switch (code) {
+    case GLRMB200_LOSS_MULTINOMIAL: case GLRMB200_LOSS_OVA: case GLRMB200_LOSS_ORDISTIC: return (int)p[2];
+    case GLRMB200_LOSS_BVS: case GLRMB200_LOSS_MULTINOMIAL_ORDINAL: return (int)p[2] - 1;
+    default: return 1;
+  }
+}
+
+static int validate_label(int code, const double* p, double a) {
+  if (a != a) return GLRMB200_E_NAN;
+  switch (code) {
+    case GLRMB200_LOSS_LOGISTIC: case GLRMB200_LOSS_WEIGHTED_HINGE:
+      return (a == 1.0 || a == 0.0 || a == -1.0) ? 0 : GLRMB200_E_LABEL;
+    case GLRMB200_LOSS_MULTINOMIAL: case GLRMB200_LOSS_OVA: case GLRMB200_LOSS_BVS:
+    case GLRMB200_LOSS_ORDISTIC: case GLRMB200_LOSS_MULTINOMIAL_ORDINAL:
+      return (a == std::floor(a) && a >= 1.0 && a <= p[2]) ? 0 : GLRMB200_E_LABEL;
+    default: return 0;
+  }
+}
+
+extern "C" int glrmb200_plan_shards(const int64_t* ptr, int64_t count, int32_t nranks, int64_t* bounds) {
+  // contiguous shards balanced by observation count (ptr == NULL: by unit count)
+  if (nranks < 1 || count < 0 || !bounds) return fail(GLRMB200_E_INVALID, "plan_shards: bad arguments");
+  bounds[0] = 0;
+  bounds[nranks] = count;
+  const int64_t total = ptr ? ptr[count] - ptr[0] : count;
+  for (int r = 1; r < nranks; ++r) {
+    if (!ptr || total == 0) { bounds[r] = count * r / nranks; continue; }
+    const int64_t target = ptr[0] + (total / nranks) * r + std::min<int64_t>(r, total % nranks);
+    const int64_t* it = std::lower_bound(ptr, ptr + count + 1, target);
+    if (it > ptr && it <= ptr + count && target - *(it - 1) < *it - target) --it;   // nearest boundary
+    int64_t b = it - ptr;
+    if (b > count) b = count;
+    if (b < bounds[r - 1]) b = bounds[r - 1];
+    bounds[r] = b;
+  }
+  return 0;
+}
+
+template <class T>
+static int upload(T** dst, const T* src, size_t count) {
+  *dst = nullptr;
+  if (count == 0) count = 1, src = nullptr;
+  CUDA_OK(cudaMalloc((void**)dst, count * sizeof(T)));
+  if (src) CUDA_OK(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// degree-sorted schedule (heaviest first): LPT order for the tail, and neighbouring warps of a CTA get
+// units of similar length
+static int build_schedule(Side& S, const int64_t* ptr_global, int64_t heavy_threshold) {
+  const int64_t cnt = S.end - S.begin;
+  std::vector<int32_t> order((size_t)cnt);
+  std::iota(order.begin(), order.end(), (int32_t)S.begin);
+  if (ptr_global) {
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+      return ptr_global[a + 1] - ptr_global[a] > ptr_global[b + 1] - ptr_global[b];
+    });
+    S.n_heavy = 0;
+    while (S.n_heavy < cnt && ptr_global[order[S.n_heavy] + 1] - ptr_global[order[S.n_heavy]] >= heavy_threshold) S.n_heavy++;
+  } else {
+    S.n_heavy = S.full_len >= heavy_threshold ? cnt : 0;
+  }
+  S.n_light = cnt - S.n_heavy;
+  return upload(&S.d_order, order.data(), order.size());
+}
+
+static int setup_regs(Side& S, int64_t count, const int32_t* code, const double* param) {
+  if (count != 1 && count != S.units) return fail(GLRMB200_E_INVALID, "regularizer count must be 1 or the number of columns");
+  S.reg_uniform = (count == 1);
+  S.h_reg_code.assign(code, code + count);
+  S.h_reg_param.assign(param, param + count * GLRMB200_REG_NPARAM);
+  for (int64_t i = 0; i < count; ++i) {
+    const int base = code[i] & GLRMB200_REG_BASE_MASK;
+    if (base > GLRMB200_REG_SIMPLEX || (code[i] & ~(GLRMB200_REG_BASE_MASK | GLRMB200_REG_LASTENTRY1 | GLRMB200_REG_LASTENTRY_UNPENALIZED)))
+      return fail(GLRMB200_E_UNSUPPORTED, "regularizer code %d has no device implementation", code[i]);
+  }
+  int rc = upload(&S.d_reg_code, code, (size_t)count);
+  if (rc) return rc;
+  return upload(&S.d_reg_param, param, (size_t)count * GLRMB200_REG_NPARAM);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch over the (G, R) tile and the loss template
+struct Tile { int g, r; };
+static const Tile kTiles[] = {{4, 1}, {8, 1}, {8, 2}, {8, 4}, {16, 1}, {16, 2}, {16, 4}, {32, 1}, {32, 2}, {32, 4}};
+
+template <int G, int R, int LOSS>
+static cudaError_t launch_tile(const SweepArgs& A, int64_t n_heavy, int64_t n_light, cudaStream_t st, int64_t* launches) {
+  if (n_heavy > 0) {
+    SweepArgs H = A;
+    H.n_units = n_heavy;
+    sweep_cta_kernel<G, R, LOSS><<<(unsigned)n_heavy, WARPS_PER_CTA_HEAVY * 32, 0, st>>>(H);
+    ++*launches;
+  }
+  if (n_light > 0) {
+    SweepArgs L = A;
+    L.order = A.order + n_heavy;
+    L.n_units = n_light;
+    const int64_t grid = (n_light + WARPS_PER_CTA_LIGHT - 1) / WARPS_PER_CTA_LIGHT;
+    sweep_warp_kernel<G, R, LOSS><<<(unsigned)grid, WARPS_PER_CTA_LIGHT * 32, 0, st>>>(L);
+    ++*launches;
+  }
+  return cudaGetLastError();
+}
+
+template <int LOSS>
+static cudaError_t launch_loss(int g, int r, const SweepArgs& A, int64_t nh, int64_t nl, cudaStream_t st, int64_t* launches) {
+#define T(GG, RR) if (g == GG && r == RR) return launch_tile<GG, RR, LOSS>(A, nh, nl, st, launches)
+  T(4, 1); T(8, 1); T(8, 2); T(8, 4); T(16, 1); T(16, 2); T(16, 4); T(32, 1); T(32, 2); T(32, 4);
+#undef T
+  return cudaErrorInvalidValue;
+}
+
+static cudaError_t launch_sweep(const glrmb200_engine* E, const SweepArgs& A, int64_t nh, int64_t nl, int64_t* launches) {
+  switch (E->loss_template) {
+    case GLRMB200_LOSS_QUAD: return launch_loss<GLRMB200_LOSS_QUAD>(E->tile_g, E->tile_r, A, nh, nl, E->stream, launches);
+    case GLRMB200_LOSS_LOGISTIC: return launch_loss<GLRMB200_LOSS_LOGISTIC>(E->tile_g, E->tile_r, A, nh, nl, E->stream, launches);
+    default: return launch_loss<0>(E->tile_g, E->tile_r, A, nh, nl, E->stream, launches);
+  }
+}
+
+static cudaError_t launch_reg_eval(const glrmb200_engine* E, const double* own, const Side& S, double* out) {
+  const int g = E->tile_g, r = E->tile_r;
+  const int64_t per_cta = 4 * (32 / g);
+  const unsigned grid = (unsigned)((S.units + per_cta - 1) / per_cta);
+#define T(GG, RR) if (g == GG && r == RR) { reg_eval_kernel<GG, RR><<<grid, 128, 0, E->stream>>>(own, S.units, E->kp, (int)E->k, S.d_reg_code, S.d_reg_param, S.reg_uniform, out); return cudaGetLastError(); }
+  T(4, 1) T(8, 1) T(8, 2) T(8, 4) T(16, 1) T(16, 2) T(16, 4) T(32, 1) T(32, 2) T(32, 4)
+#undef T
+  return cudaErrorInvalidValue;
+}
+
+static SweepArgs make_args(const glrmb200_engine* E, bool x_side, int flags, double min_stepsize) {
+  const Side& S = x_side ? E->rows : E->cols;
+  SweepArgs A;
+  A.ptr = S.d_ptr;
+  A.idx = S.d_idx;
+  A.val = S.d_val;
+  A.full_len = S.full_len;
+  A.unit_base = S.begin;
+  A.order = S.d_order;
+  A.n_units = 0;
+  A.own = x_side ? E->d_X : E->d_Y;
+  A.opp = x_side ? E->d_Y : E->d_X;
+  A.kp = E->kp;
+  A.k = (int)E->k;
+  A.loss_code = E->d_loss_code;
+  A.loss_param = E->d_loss_param;
+  A.uparam[0] = E->uparam[0]; A.uparam[1] = E->uparam[1]; A.uparam[2] = E->uparam[2];
+  A.reg_code = S.d_reg_code;
+  A.reg_param = S.d_reg_param;
+  A.reg_uniform = S.reg_uniform;
+  A.flags = flags | ((x_side && E->loss_template == 0) ? FLAG_LOSS_BY_ENTRY : 0);
+  A.alpha = S.d_alpha;
+  A.min_stepsize = min_stepsize;
+  A.obj_out = S.d_obj;
+  A.trial_counter = E->d_trials + (x_side ? 0 : 1);
+  return A;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+extern "C" int glrmb200_version(void) { return GLRMB200_VERSION; }
+extern "C" const char* glrmb200_last_error(void) { return g_err; }
+extern "C" int glrmb200_device_count(int32_t* count) {
+  if (count) *count = 0;
+  int rc = check_device();
+  if (rc) return rc;
+  if (count) *count = g_device_checked;
+  return 0;
+}
+
+static void free_side(Side& S) {
+  cudaFree(S.d_ptr); cudaFree(S.d_idx); cudaFree(S.d_val); cudaFree(S.d_order);
+  cudaFree(S.d_reg_code); cudaFree(S.d_reg_param); cudaFree(S.d_alpha); cudaFree(S.d_obj);
+}
+
+extern "C" int glrmb200_destroy(glrmb200_handle E) {
+  if (!E) return 0;
+  cudaSetDevice(E->device);
+  if (E->stream) cudaStreamSynchronize(E->stream);
+  if (E->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(E->comm);
+  free_side(E->rows); free_side(E->cols);
+  cudaFree(E->d_loss_code); cudaFree(E->d_loss_param); cudaFree(E->d_X); cudaFree(E->d_Y);
+  cudaFree(E->d_scalars); cudaFree(E->d_trials);
+  if (E->h_pinned) cudaFreeHost(E->h_pinned);
+  for (auto& e : E->ev) if (e) cudaEventDestroy(e);
+  if (E->stream) cudaStreamDestroy(E->stream);
+  delete E;
+  return 0;
+}
+
+static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
+  const int64_t m = P->m, n = P->n, k = P->k;
+  if (m <= 0 || n <= 0 || k <= 0) return fail(GLRMB200_E_INVALID, "m, n, k must be positive");
+  if (m >= INT32_MAX || n >= INT32_MAX) return fail(GLRMB200_E_INVALID, "m, n must fit int32");
+  if (!P->loss_code || !P->loss_param || !P->rx_code || !P->ry_code) return fail(GLRMB200_E_INVALID, "null descriptor table");
+  E->m = m; E->n = n; E->k = k; E->d = P->d;
+  E->obs_full = P->obs_full != 0;
+
+  // ---- losses: embedding dims must sum to d (get_yidxs, losses.jl:76-93) ----------------------
+  int64_t dsum = 0;
+  bool uniform = true, vector_loss = false;
+  for (int64_t f = 0; f < n; ++f) {
+    const int code = P->loss_code[f];
+    const double* p = P->loss_param + f * GLRMB200_LOSS_NPARAM;
+    if (code < GLRMB200_LOSS_QUAD || code > GLRMB200_LOSS_MULTINOMIAL_ORDINAL)
+      return fail(GLRMB200_E_UNSUPPORTED, "loss code %d (column %lld) is unknown", code, (long long)f);
+    const int dim = loss_dim(code, p);
+    if (dim != 1 || code >= GLRMB200_LOSS_MULTINOMIAL) vector_loss = true;
+    dsum += dim;
+    if (code != P->loss_code[0] || memcmp(p, P->loss_param, 3 * sizeof(double)) != 0) uniform = false;
+  }
+  if (dsum != P->d) return fail(GLRMB200_E_INVALID, "d = %lld but the losses' embedding dimensions sum to %lld (proxgrad.jl:55-63)", (long long)P->d, (long long)dsum);
+  if (vector_loss)
+    return fail(GLRMB200_E_UNSUPPORTED, "vector-valued losses (Multinomial/OvA/BvS/Ordistic/MultinomialOrdinal) have no device implementation yet");
+  E->loss_template = 0;
+  if (uniform && (P->loss_code[0] == GLRMB200_LOSS_QUAD || P->loss_code[0] == GLRMB200_LOSS_LOGISTIC)) {
+    E->loss_template = P->loss_code[0];
+    E->uparam[0] = P->loss_param[0]; E->uparam[1] = P->loss_param[1]; E->uparam[2] = P->loss_param[2];
+  }
+
+  // ---- tile selection ---------------------------------------------------------------------------
+  E->kp = (int)((k + 3) / 4 * 4);
+  if (E->kp > 256) return fail(GLRMB200_E_UNSUPPORTED, "k = %lld: ranks above 256 are not supported", (long long)k);
+  if (E->kp <= 8) { E->tile_g = 4; E->tile_r = 1; }
+  else if (E->kp <= 16) { E->tile_g = 8; E->tile_r = 1; }
+  else if (E->kp <= 32) { E->tile_g = 8; E->tile_r = 2; }
+  else if (E->kp <= 64) { E->tile_g = 8; E->tile_r = 4; }
+  else if (E->kp <= 128) { E->tile_g = 16; E->tile_r = 4; }
+  else { E->tile_g = 32; E->tile_r = 4; }
+  if (const char* t = getenv("GLRMB200_TILE")) {   // tuning hook: "G,R"
+    int g = 0, r = 0;
+    if (sscanf(t, "%d,%d", &g, &r) == 2 && 2 * g * r >= E->kp) {
+      for (const Tile& tl : kTiles) if (tl.g == g && tl.r == r) { E->tile_g = g; E->tile_r = r; }
+    }
+  }
+  if (const char* t = getenv("GLRMB200_HEAVY")) E->heavy_threshold = std::max<long long>(1, atoll(t));
+
+  // ---- observation lists: validation (glrm.jl:63-71, losses.jl:104) ----------------------------
+  Side& R = E->rows;
+  Side& C = E->cols;
+  R.units = m; C.units = n;
+  R.bounds.assign((size_t)E->nranks + 1, 0);
+  C.bounds.assign((size_t)E->nranks + 1, 0);
+  if (E->obs_full) {
+    if (!P->dense_A) return fail(GLRMB200_E_INVALID, "obs_full needs dense_A");
+    for (int64_t f = 0; f < n; ++f) {
+      const double* p = P->loss_param + f * GLRMB200_LOSS_NPARAM;
+      for (int64_t e = 0; e < m; ++e) {
+        const int v = validate_label(P->loss_code[f], p, P->dense_A[f * m + e]);
+        if (v == GLRMB200_E_NAN) return fail(v, "Observed value in entry (%lld, %lld) is NaN.", (long long)e + 1, (long long)f + 1);
+        if (v) return fail(v, "entry (%lld, %lld): label %g is outside the domain of loss code %d", (long long)e + 1, (long long)f + 1, P->dense_A[f * m + e], P->loss_code[f]);
+      }
+    }
+    R.full_len = n; C.full_len = m;
+    E->nnz_rows_total = m * n;
+    glrmb200_plan_shards(nullptr, m, E->nranks, R.bounds.data());
+    glrmb200_plan_shards(nullptr, n, E->nranks, C.bounds.data());
+  } else {
+    if (!P->row_ptr || !P->col_ptr) return fail(GLRMB200_E_INVALID, "observation lists missing");
+    const int64_t nr = P->row_ptr[m], nc = P->col_ptr[n];
+    if (P->row_ptr[0] != 0 || P->col_ptr[0] != 0) return fail(GLRMB200_E_INVALID, "ptr arrays must start at 0");
+    if ((nr && (!P->row_idx || !P->row_val)) || (nc && (!P->col_idx || !P->col_val))) return fail(GLRMB200_E_INVALID, "observation arrays missing");
+    for (int64_t e = 0; e < m; ++e) {
+      if (P->row_ptr[e + 1] < P->row_ptr[e]) return fail(GLRMB200_E_INVALID, "row_ptr not monotone");
+      for (int64_t q = P->row_ptr[e]; q < P->row_ptr[e + 1]; ++q) {
+        const int32_t f = P->row_idx[q];
+        if (f < 0 || f >= n) return fail(GLRMB200_E_INVALID, "row_idx[%lld] = %d out of range", (long long)q, f);
+        const int v = validate_label(P->loss_code[f], P->loss_param + (int64_t)f * GLRMB200_LOSS_NPARAM, P->row_val[q]);
+        if (v == GLRMB200_E_NAN) return fail(v, "Observed value in entry (%lld, %d) is NaN.", (long long)e + 1, f + 1);
+        if (v) return fail(v, "entry (%lld, %d): label %g is outside the domain of loss code %d", (long long)e + 1, f + 1, P->row_val[q], P->loss_code[f]);
+      }
+    }
+    for (int64_t f = 0; f < n; ++f) {
+      if (P->col_ptr[f + 1] < P->col_ptr[f]) return fail(GLRMB200_E_INVALID, "col_ptr not monotone");
+      const double* p = P->loss_param + f * GLRMB200_LOSS_NPARAM;
+      for (int64_t q = P->col_ptr[f]; q < P->col_ptr[f + 1]; ++q) {
+        const int32_t e = P->col_idx[q];
+        if (e < 0 || e >= m) return fail(GLRMB200_E_INVALID, "col_idx[%lld] = %d out of range", (long long)q, e);
+        const int v = validate_label(P->loss_code[f], p, P->col_val[q]);
+        if (v == GLRMB200_E_NAN) return fail(v, "Observed value in entry (%d, %lld) is NaN.", e + 1, (long long)f + 1);
+        if (v) return fail(v, "entry (%d, %lld): label %g is outside the domain of loss code %d", e + 1, (long long)f + 1, P->col_val[q], P->loss_code[f]);
+      }
+    }
+    E->nnz_rows_total = nr;
+    glrmb200_plan_shards(P->row_ptr, m, E->nranks, R.bounds.data());
+    glrmb200_plan_shards(P->col_ptr, n, E->nranks, C.bounds.data());
+  }
+  R.begin = R.bounds[E->rank]; R.end = R.bounds[E->rank + 1];
+  C.begin = C.bounds[E->rank]; C.end = C.bounds[E->rank + 1];
+
+  // ---- device ---------------------------------------------------------------------------------------
+  int rc = check_device();
+  if (rc) return rc;
+  if (E->device < 0 || E->device >= g_device_checked) return fail(GLRMB200_E_INVALID, "device %d out of range (%d visible)", E->device, g_device_checked);
+  CUDA_OK(cudaSetDevice(E->device));
+  CUDA_OK(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
+  for (auto& e : E->ev) CUDA_OK(cudaEventCreate(&e));
+  CUDA_OK(cudaMallocHost((void**)&E->h_pinned, 8 * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&E->d_scalars, 4 * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&E->d_trials, 2 * sizeof(unsigned long long)));
+  CUDA_OK(cudaMemset(E->d_trials, 0, 2 * sizeof(unsigned long long)));
+
+  if ((rc = upload(&E->d_loss_code, P->loss_code, (size_t)n))) return rc;
+  if ((rc = upload(&E->d_loss_param, P->loss_param, (size_t)n * GLRMB200_LOSS_NPARAM))) return rc;
+  if ((rc = setup_regs(R, P->rx_count, P->rx_code, P->rx_param))) return rc;
+  if ((rc = setup_regs(C, P->ry_count, P->ry_code, P->ry_param))) return rc;
+
+  if (E->obs_full) {
+    // column side streams the Julia (column-major) A as is; the row side gets a row-major copy
+    const int64_t cb = C.begin, ce = C.end;
+    C.nnz_local = (ce - cb) * m;
+    if ((rc = upload(&C.d_val, P->dense_A + cb * m, (size_t)C.nnz_local))) return rc;
+    // row-major copy of rows [R.begin, R.end): transpose on the device from a temporary full upload
+    R.nnz_local = (R.end - R.begin) * n;
+    double* d_full = nullptr;
+    if (E->nranks == 1) d_full = C.d_val;
+    else if ((rc = upload(&d_full, P->dense_A, (size_t)(m * n)))) return rc;
+    double* d_rowmajor = nullptr;
+    CUDA_OK(cudaMalloc((void**)&d_rowmajor, (size_t)std::max<int64_t>(1, m * n) * sizeof(double)));
+    dim3 blk(32, 8), grd((unsigned)((m + 31) / 32), (unsigned)((n + 31) / 32));
+    transpose_kernel<<<grd, blk, 0, E->stream>>>(d_full, d_rowmajor, n, m);   // src = n x m row-major view of A
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(E->stream));
+    if (E->nranks == 1) {
+      R.d_val = d_rowmajor;
+    } else {
+      CUDA_OK(cudaMalloc((void**)&R.d_val, (size_t)std::max<int64_t>(1, R.nnz_local) * sizeof(double)));
+      CUDA_OK(cudaMemcpy(R.d_val, d_rowmajor + R.begin * n, (size_t)R.nnz_local * sizeof(double), cudaMemcpyDeviceToDevice));
+      cudaFree(d_rowmajor);
+      cudaFree(d_full);
+    }
+    if ((rc = build_schedule(R, nullptr, E->heavy_threshold))) return rc;
+    if ((rc = build_schedule(C, nullptr, E->heavy_threshold))) return rc;
+  } else {
+    auto up_side = [&](Side& S, const int64_t* ptr, const int32_t* idx, const double* val) -> int {
+      const int64_t cnt = S.end - S.begin, q0 = ptr[S.begin], q1 = ptr[S.end];
+      S.nnz_local = q1 - q0;
+      std::vector<int64_t> local((size_t)cnt + 1);
+      for (int64_t i = 0; i <= cnt; ++i) local[(size_t)i] = ptr[S.begin + i] - q0;
+      int r2 = upload(&S.d_ptr, local.data(), local.size());
+      if (r2) return r2;
+      if ((r2 = upload(&S.d_idx, idx ? idx + q0 : nullptr, (size_t)S.nnz_local))) return r2;
+      if ((r2 = upload(&S.d_val, val ? val + q0 : nullptr, (size_t)S.nnz_local))) return r2;
+      return build_schedule(S, ptr, E->heavy_threshold);
+    };
+    if ((rc = up_side(R, P->row_ptr, P->row_idx, P->row_val))) return rc;
+    if ((rc = up_side(C, P->col_ptr, P->col_idx, P->col_val))) return rc;
+  }
+
+  CUDA_OK(cudaMalloc((void**)&E->d_X, (size_t)m * E->kp * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&E->d_Y, (size_t)E->d * E->kp * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&R.d_alpha, (size_t)m * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&C.d_alpha, (size_t)n * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&R.d_obj, (size_t)m * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&C.d_obj, (size_t)n * sizeof(double)));
+  CUDA_OK(cudaMemset(R.d_obj, 0, (size_t)m * sizeof(double)));
+  CUDA_OK(cudaMemset(C.d_obj, 0, (size_t)n * sizeof(double)));
+  CUDA_OK(cudaMemset(R.d_alpha, 0, (size_t)m * sizeof(double)));
+  CUDA_OK(cudaMemset(C.d_alpha, 0, (size_t)n * sizeof(double)));
+  return 0;
+}
+
+extern "C" int glrmb200_create(glrmb200_handle* out, const glrmb200_problem* problem, int32_t device,
+                               int32_t rank, int32_t nranks) {
+  if (!out || !problem) return fail(GLRMB200_E_INVALID, "null argument");
+  *out = nullptr;
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(GLRMB200_E_INVALID, "bad rank %d / nranks %d", rank, nranks);
+  glrmb200_engine* E = new glrmb200_engine();
+  E->device = device; E->rank = rank; E->nranks = nranks;
+  const int rc = create_impl(E, problem);
+  if (rc) { glrmb200_destroy(E); return rc; }
+  *out = E;
+  return 0;
+}
+
+extern "C" int glrmb200_comm_unique_id(uint8_t id[128]) {
+  int rc = load_nccl();
+  if (rc) return rc;
+  ncclUniqueId_t u;
+  NCCL_OK(g_nccl.GetUniqueId(&u));
+  memcpy(id, u.internal, 128);
+  return 0;
+}
+
+extern "C" int glrmb200_comm_init(glrmb200_handle E, const uint8_t id[128]) {
+  if (!E) return fail(GLRMB200_E_STATE, "null handle");
+  if (E->nranks == 1) return 0;
+  int rc = load_nccl();
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(E->device));
+  ncclUniqueId_t u;
+  memcpy(u.internal, id, 128);
+  NCCL_OK(g_nccl.CommInitRank(&E->comm, E->nranks, u, E->rank));
+  return 0;
+}
+
+extern "C" int glrmb200_shard(glrmb200_handle E, int64_t* rb, int64_t* re, int64_t* cb, int64_t* ce) {
+  if (!E) return fail(GLRMB200_E_STATE, "null handle");
+  if (rb) *rb = E->rows.begin;
+  if (re) *re = E->rows.end;
+  if (cb) *cb = E->cols.begin;
+  if (ce) *ce = E->cols.end;
+  return 0;
+}
+
+extern "C" int glrmb200_upload_factors(glrmb200_handle E, const double* X, const double* Y) {
+  if (!E || !X || !Y) return fail(GLRMB200_E_INVALID, "null argument");
+  CUDA_OK(cudaSetDevice(E->device));
+  const size_t kb = (size_t)E->k * sizeof(double), pb = (size_t)E->kp * sizeof(double);
+  if (E->kp != E->k) {
+    CUDA_OK(cudaMemsetAsync(E->d_X, 0, (size_t)E->m * pb, E->stream));
+    CUDA_OK(cudaMemsetAsync(E->d_Y, 0, (size_t)E->d * pb, E->stream));
+  }
+  CUDA_OK(cudaMemcpy2DAsync(E->d_X, pb, X, kb, kb, (size_t)E->m, cudaMemcpyHostToDevice, E->stream));
+  CUDA_OK(cudaMemcpy2DAsync(E->d_Y, pb, Y, kb, kb, (size_t)E->d, cudaMemcpyHostToDevice, E->stream));
+  CUDA_OK(cudaStreamSynchronize(E->stream));
+  E->factors_resident = true;
+  return 0;
+}
+
+extern "C" int glrmb200_download_factors(glrmb200_handle E, double* X, double* Y) {
+  if (!E || !X || !Y) return fail(GLRMB200_E_INVALID, "null argument");
+  if (!E->factors_resident) return fail(GLRMB200_E_STATE, "no factors on the device");
+  CUDA_OK(cudaSetDevice(E->device));
+  const size_t kb = (size_t)E->k * sizeof(double), pb = (size_t)E->kp * sizeof(double);
+  CUDA_OK(cudaMemcpy2DAsync(X, kb, E->d_X, pb, kb, (size_t)E->m, cudaMemcpyDeviceToHost, E->stream));
+  CUDA_OK(cudaMemcpy2DAsync(Y, kb, E->d_Y, pb, kb, (size_t)E->d, cudaMemcpyDeviceToHost, E->stream));
+  CUDA_OK(cudaStreamSynchronize(E->stream));
+  return 0;
+}
+
+// all-gather of per-unit arrays whose shards are contiguous (`elems` doubles per unit)
+static int allgather_units(glrmb200_engine* E, double* buf, const Side& S, int64_t elems) {
+  if (E->nranks == 1) return 0;
+  if (!E->comm) return fail(GLRMB200_E_STATE, "glrmb200_comm_init was not called");
+  NCCL_OK(g_nccl.GroupStart());
+  for (int r = 0; r < E->nranks; ++r) {
+    const int64_t b = S.bounds[r], cnt = (S.bounds[r + 1] - b) * elems;
+    if (cnt == 0) continue;
+    NCCL_OK(g_nccl.Broadcast(buf + b * elems, buf + b * elems, (size_t)cnt, kNcclDouble, r, E->comm, E->stream));
+  }
+  NCCL_OK(g_nccl.GroupEnd());
+  return 0;
+}
+
+// sum of per-unit objectives -> host (through the pinned scalar)
+static int reduce_to_host(glrmb200_engine* E, const double* v, int64_t n, double* out, int64_t* launches) {
+  sum_kernel<<<1, 1024, 0, E->stream>>>(v, n, E->d_scalars);
+  CUDA_OK(cudaGetLastError());
+  ++*launches;
+  CUDA_OK(cudaMemcpyAsync(E->h_pinned, E->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  CUDA_OK(cudaStreamSynchronize(E->stream));
+  *out = E->h_pinned[0];
+  return 0;
+}
+
+// objective(glrm, X, Y) on the resident factors: losses over observed_examples + penalties
+static int objective_resident(glrmb200_engine* E, bool include_reg, double* out, int64_t* launches) {
+  SweepArgs A = make_args(E, /*x_side=*/false, FLAG_EVAL_ONLY | (include_reg ? 0 : FLAG_NO_REG), INFINITY);
+  cudaError_t ce = launch_sweep(E, A, E->cols.n_heavy, E->cols.n_light, launches);
+  if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "objective sweep launch: %s", cudaGetErrorString(ce));
+  int rc = allgather_units(E, E->cols.d_obj, E->cols, 1);
+  if (rc) return rc;
+  double total = 0.0;
+  if ((rc = reduce_to_host(E, E->cols.d_obj, E->n, &total, launches))) return rc;
+  if (include_reg) {
+    ce = launch_reg_eval(E, E->d_X, E->rows, E->rows.d_obj);
+    if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "penalty launch: %s", cudaGetErrorString(ce));
+    ++*launches;
+    double pen = 0.0;
+    if ((rc = reduce_to_host(E, E->rows.d_obj, E->m, &pen, launches))) return rc;
+    total += pen;
+  }
+  *out = total;
+  return 0;
+}
+
+__global__ void fill_kernel(double* p, int64_t n, double v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+static int fill(glrmb200_engine* E, double* p, int64_t n, double v) {
+  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, E->stream>>>(p, n, v);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int glrmb200_fit_resident(glrmb200_handle E, const glrmb200_params* prm, double* ch_objective,
+                                     double* ch_seconds, int32_t cap, int32_t* n_recorded,
+                                     glrmb200_profile* profile) {
+  if (!E || !prm || !ch_objective || !ch_seconds || !n_recorded) return fail(GLRMB200_E_INVALID, "null argument");
+  if (!E->factors_resident) return fail(GLRMB200_E_STATE, "upload factors first");
+  if (cap < prm->max_iter + 1) return fail(GLRMB200_E_INVALID, "cap %d < max_iter+1", cap);
+  if (prm->inner_iter_X < 1 || prm->inner_iter_Y < 1) return fail(GLRMB200_E_INVALID, "inner iteration counts must be >= 1");
+  CUDA_OK(cudaSetDevice(E->device));
+  glrmb200_profile prof;
+  memset(&prof, 0, sizeof(prof));
+  int rc;
+  using clk = std::chrono::steady_clock;
+
+  // ---- setup (proxgrad.jl:69-76) ---------------------------------------------------------------------
+  CUDA_OK(cudaEventRecord(E->ev[0], E->stream));
+  if ((rc = fill(E, E->rows.d_alpha, E->m, prm->stepsize))) return rc;       // :69
+  if ((rc = fill(E, E->cols.d_alpha, E->n, prm->stepsize))) return rc;       // :70
+  CUDA_OK(cudaMemsetAsync(E->d_trials, 0, 2 * sizeof(unsigned long long), E->stream));
+  const double scaled_abs_tol = prm->abs_tol * (double)E->nnz_rows_total;     // :72
+  int nrec = 0;
+  double obj0 = 0.0;
+  if ((rc = objective_resident(E, true, &obj0, &prof.other_launches))) return rc;   // :76
+  ch_objective[nrec] = obj0;
+  ch_seconds[nrec++] = 0.0;
+  CUDA_OK(cudaEventRecord(E->ev[1], E->stream));
+  CUDA_OK(cudaEventSynchronize(E->ev[1]));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, E->ev[0], E->ev[1]));
+  prof.setup_ms = ms;
+
+  auto t_iter = clk::now();
+  const auto t_loop = t_iter;
+  for (int it = 1; it <= prm->max_iter; ++it) {                                // :107
+    if (prm->inner_iter_X > 1 || prm->inner_iter_Y > 1) {                      // :112-115
+      if ((rc = fill(E, E->rows.d_alpha, E->m, prm->stepsize))) return rc;
+      if ((rc = fill(E, E->cols.d_alpha, E->n, prm->stepsize))) return rc;
+    }
+    CUDA_OK(cudaEventRecord(E->ev[0], E->stream));
+    for (int inner = 0; inner < prm->inner_iter_X; ++inner) {                  // :117-158
+      SweepArgs A = make_args(E, true, 0, prm->min_stepsize);
+      cudaError_t ce = launch_sweep(E, A, E->rows.n_heavy, E->rows.n_light, &prof.x_launches);
+      if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "update-X launch: %s", cudaGetErrorString(ce));
+    }
+    CUDA_OK(cudaEventRecord(E->ev[1], E->stream));
+    if ((rc = allgather_units(E, E->d_X, E->rows, E->kp))) return rc;
+    CUDA_OK(cudaEventRecord(E->ev[2], E->stream));
+    for (int inner = 0; inner < prm->inner_iter_Y; ++inner) {                  // :160-203
+      SweepArgs A = make_args(E, false, 0, prm->min_stepsize);
+      cudaError_t ce = launch_sweep(E, A, E->cols.n_heavy, E->cols.n_light, &prof.y_launches);
+      if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "update-Y launch: %s", cudaGetErrorString(ce));
+    }
+    CUDA_OK(cudaEventRecord(E->ev[3], E->stream));
+    if ((rc = allgather_units(E, E->d_Y, E->cols, E->kp))) return rc;
+    if ((rc = allgather_units(E, E->cols.d_obj, E->cols, 1))) return rc;
+    CUDA_OK(cudaEventRecord(E->ev[4], E->stream));
+    double obj = 0.0;
+    if ((rc = reduce_to_host(E, E->cols.d_obj, E->n, &obj, &prof.other_launches))) return rc;   // :205
+    const auto t_now = clk::now();
+    ch_objective[nrec] = obj;
+    ch_seconds[nrec++] = std::chrono::duration<double>(t_now - t_iter).count();                 // :206-207
+    t_iter = t_now;
+    float a = 0, b = 0, c = 0, d2 = 0;
+    cudaEventElapsedTime(&a, E->ev[0], E->ev[1]);
+    cudaEventElapsedTime(&b, E->ev[1], E->ev[2]);
+    cudaEventElapsedTime(&c, E->ev[2], E->ev[3]);
+    cudaEventElapsedTime(&d2, E->ev[3], E->ev[4]);
+    prof.update_x_ms += a; prof.update_y_ms += c; prof.comm_ms += b + d2;
+    prof.iterations = it;
+    const double obj_decrease = ch_objective[nrec - 2] - obj;                  // :210
+    if (it > 10 && (obj_decrease < scaled_abs_tol || obj_decrease / obj < prm->rel_tol)) break;   // :211
+  }
+  prof.loop_ms = std::chrono::duration<double, std::milli>(clk::now() - t_loop).count();
+  prof.reduce_ms = prof.loop_ms - prof.update_x_ms - prof.update_y_ms - prof.comm_ms;
+  unsigned long long tr[2] = {0, 0};
+  CUDA_OK(cudaMemcpy(tr, E->d_trials, sizeof(tr), cudaMemcpyDeviceToHost));
+  prof.x_trials = (int64_t)tr[0];
+  prof.y_trials = (int64_t)tr[1];
+  *n_recorded = nrec;
+  if (profile) *profile = prof;
+  return 0;
+}
+
+extern "C" int glrmb200_fit(glrmb200_handle E, const glrmb200_params* prm, double* X, double* Y,
+                            double* ch_objective, double* ch_seconds, int32_t cap, int32_t* n_recorded,
+                            glrmb200_profile* profile) {
+  if (!E || !X || !Y) return fail(GLRMB200_E_INVALID, "null argument");
+  // the reference's norm(Y)==0 branch is an UndefVarError (proxgrad.jl:45-47): refuse
+  bool allzero = true;
+  for (int64_t i = 0; i < E->k * E->d && allzero; ++i) allzero = (Y[i] == 0.0);
+  if (allzero) return fail(GLRMB200_E_INVALID, "norm(Y) == 0: the solver would never move (proxgrad.jl:44-47)");
+  int rc = glrmb200_upload_factors(E, X, Y);
+  if (rc) return rc;
+  if ((rc = glrmb200_fit_resident(E, prm, ch_objective, ch_seconds, cap, n_recorded, profile))) return rc;
+  return glrmb200_download_factors(E, X, Y);
+}
+
+extern "C" int glrmb200_objective(glrmb200_handle E, const double* X, const double* Y,
+                                  int32_t include_regularization, double* out) {
+  if (!E || !X || !Y || !out) return fail(GLRMB200_E_INVALID, "null argument");
+  int rc = glrmb200_upload_factors(E, X, Y);
+  if (rc) return rc;
+  int64_t launches = 0;
+  return objective_resident(E, include_regularization != 0, out, &launches);
+}
+
+extern "C" int glrmb200_set_reg_scale(glrmb200_handle E, double newscale) {
+  // scale_regularizer! -> mul!(r, newscale) sets r.scale (regularizers.jl:38); regularizers whose
+  // mul! is a no-op (constraints, ZeroReg: :76,97,114,138,255,318,348) are left untouched
+  if (!E) return fail(GLRMB200_E_STATE, "null handle");
+  CUDA_OK(cudaSetDevice(E->device));
+  for (Side* S : {&E->rows, &E->cols}) {
+    for (size_t i = 0; i < S->h_reg_code.size(); ++i) {
+      const int base = S->h_reg_code[i] & GLRMB200_REG_BASE_MASK;
+      if (base == GLRMB200_REG_QUAD || base == GLRMB200_REG_ONE) S->h_reg_param[i * GLRMB200_REG_NPARAM] = newscale;
+    }
+    CUDA_OK(cudaMemcpy(S->d_reg_param, S->h_reg_param.data(), S->h_reg_param.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+extern "C" int glrmb200_get_stepsizes(glrmb200_handle E, double* alpharow, double* alphacol) {
+  if (!E) return fail(GLRMB200_E_STATE, "null handle");
+  CUDA_OK(cudaSetDevice(E->device));
+  int rc;
+  if ((rc = allgather_units(E, E->rows.d_alpha, E->rows, 1))) return rc;
+  if ((rc = allgather_units(E, E->cols.d_alpha, E->cols, 1))) return rc;
+  CUDA_OK(cudaStreamSynchronize(E->stream));
+  if (alpharow) CUDA_OK(cudaMemcpy(alpharow, E->rows.d_alpha, (size_t)E->m * sizeof(double), cudaMemcpyDeviceToHost));
+  if (alphacol) CUDA_OK(cudaMemcpy(alphacol, E->cols.d_alpha, (size_t)E->n * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
