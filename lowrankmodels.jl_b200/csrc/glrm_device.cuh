@@ -41,6 +41,7 @@ struct SweepArgs {
   double* own;            // factor being updated   [units_total * kp]
   const double* opp;      // factor being gathered  [opp_total * kp]
   int32_t kp;             // padded rank (multiple of 4 doubles = 32 B)
+  int32_t stride;         // doubles between factor columns (kp rounded up so columns start on 128 B lines)
   int32_t k;              // rank
   const int32_t* loss_code;   // [n] per feature
   const double* loss_param;   // [n * 8]
@@ -335,62 +336,83 @@ __device__ __forceinline__ void reg_prox(int code, const double* __restrict__ rp
 
 // ------------------------------------------------------------------------------------------------
 // One pass over the unit's observed entries.  GRAD: accumulate g and the objective; otherwise the
-// objective only (line-search trial).  UNROLL entries per group are in flight together.
+// objective only (line-search trial).
+//
+// Memory pipeline.  Each warp walks its share of the list in chunks of 32 entries: lane l loads
+// (idx, val) of entry l with one coalesced streaming load, one chunk ahead of use, and the groups pick
+// their entry up by shuffle — the index load never sits in front of the gather it feeds.  The gathers
+// themselves are double-buffered: the R 16-byte loads of step s+1 are in flight while step s is reduced,
+// so every lane group always has one factor column on its way from L2.
 template <int G, int R, int W, int LOSS, bool GRAD>
-__device__ __forceinline__ void entry_pass(const SweepArgs& A, int64_t start, int64_t len, int gid, int lg,
+__device__ __forceinline__ void entry_pass(const SweepArgs& A, int64_t start, int64_t len, int warp, int lane,
                                            const double2 (&x)[R], const bool (&in)[R], int ucode, double us,
                                            double up1, double up2, double2 (&g)[R], double& obj) {
-  constexpr int NG = (32 / G) * W;
-  constexpr int UNROLL = (R >= 4) ? 2 : 4;
+  constexpr int NGW = 32 / G;
+  const int lg = lane % G, gq = lane / G;
   const bool by_entry = (LOSS == 0) && (A.flags & FLAG_LOSS_BY_ENTRY);
+  const int64_t nchunks = (len + 31) >> 5;
+  const int64_t my_chunks = (nchunks + W - 1) / W;   // same trip count in every warp of the unit
+  const int64_t nsteps = my_chunks * G;
   obj = 0.0;
   if (GRAD) {
 #pragma unroll
     for (int r = 0; r < R; ++r) g[r] = make_double2(0.0, 0.0);
   }
-  for (int64_t t0 = 0; t0 < len; t0 += (int64_t)NG * UNROLL) {
-    int32_t j[UNROLL];
-    double a[UNROLL];
-    bool act[UNROLL];
-    double2 y[UNROLL][R];
+  auto load_chunk = [&](int64_t ci, int32_t& j, double& a) {
+    const int64_t t = ((ci * W + warp) << 5) + lane;
+    const bool ok = ci < my_chunks && t < len;
+    const int64_t q = start + (ok ? t : 0);
+    j = ok ? (A.idx ? __ldcs(A.idx + q) : (int32_t)t) : -1;
+    a = ok ? __ldcs(A.val + q) : 0.0;
+  };
+  struct Ent { int32_t j; double a; int code; double s, p1, p2; };
+  auto fetch = [&](int64_t s, int32_t cj, double ca, double2 (&y)[R], Ent& e) {
+    const int src = (int)(s % G) * NGW + gq;
+    e.j = __shfl_sync(FULLMASK, cj, src);
+    e.a = __shfl_sync(FULLMASK, ca, src);
+    const bool act = e.j >= 0;
+    const double* yp = A.opp + (int64_t)(act ? e.j : 0) * A.stride + 2 * lg;
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int64_t t = t0 + (int64_t)u * NG + gid;
-      act[u] = t < len;
-      const int64_t q = start + (act[u] ? t : 0);
-      j[u] = act[u] ? (A.idx ? __ldg(A.idx + q) : (int32_t)t) : 0;
-      a[u] = act[u] ? __ldg(A.val + q) : 0.0;
+    for (int r = 0; r < R; ++r)
+      y[r] = (act && in[r]) ? __ldg(reinterpret_cast<const double2*>(yp + 2 * G * r)) : make_double2(0.0, 0.0);
+    e.code = ucode; e.s = us; e.p1 = up1; e.p2 = up2;
+    if (by_entry && act) {
+      e.code = __ldg(A.loss_code + e.j);
+      const double* lp = A.loss_param + (int64_t)e.j * GLRMB200_LOSS_NPARAM;
+      e.s = __ldg(lp); e.p1 = __ldg(lp + 1); e.p2 = __ldg(lp + 2);
     }
+  };
+  auto consume = [&](const double2 (&y)[R], const Ent& e) {
+    double dot = 0.0;
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const double* yp = A.opp + (int64_t)j[u] * A.kp + 2 * lg;
+    for (int r = 0; r < R; ++r) dot = fma(y[r].x, x[r].x, fma(y[r].y, x[r].y, dot));
+    dot = group_sum<G>(dot);
+    double l, c;
+    loss_eval<LOSS, GRAD>(e.code, e.s, e.p1, e.p2, dot, e.a, l, c);
+    if (e.j >= 0) {
+      obj += l;
+      if (GRAD) {
 #pragma unroll
-      for (int r = 0; r < R; ++r)
-        y[u][r] = (act[u] && in[r]) ? __ldg(reinterpret_cast<const double2*>(yp + 2 * G * r)) : make_double2(0.0, 0.0);
-    }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      double dot = 0.0;
-#pragma unroll
-      for (int r = 0; r < R; ++r) dot = fma(y[u][r].x, x[r].x, fma(y[u][r].y, x[r].y, dot));
-      dot = group_sum<G>(dot);
-      int code = ucode;
-      double s = us, p1 = up1, p2 = up2;
-      if (by_entry && act[u]) {
-        code = __ldg(A.loss_code + j[u]);
-        const double* lp = A.loss_param + (int64_t)j[u] * GLRMB200_LOSS_NPARAM;
-        s = __ldg(lp); p1 = __ldg(lp + 1); p2 = __ldg(lp + 2);
-      }
-      double l, c;
-      loss_eval<LOSS, GRAD>(code, s, p1, p2, dot, a[u], l, c);
-      if (act[u]) {
-        obj += l;
-        if (GRAD) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) { g[r].x = fma(c, y[u][r].x, g[r].x); g[r].y = fma(c, y[u][r].y, g[r].y); }
-        }
+        for (int r = 0; r < R; ++r) { g[r].x = fma(c, y[r].x, g[r].x); g[r].y = fma(c, y[r].y, g[r].y); }
       }
     }
+  };
+  int32_t cj, nj;
+  double ca, na;
+  load_chunk(0, cj, ca);
+  load_chunk(1, nj, na);
+  double2 yA[R], yB[R];
+  Ent eA, eB;
+  fetch(0, cj, ca, yA, eA);
+  for (int64_t s = 0; s < nsteps; s += 2) {       // G is even: steps s and s+1 share a chunk
+    fetch(s + 1, cj, ca, yB, eB);
+    consume(yA, eA);
+    if (((s + 2) % G) == 0) {                     // step s+2 opens the next chunk
+      cj = nj; ca = na;
+      load_chunk((s + 2) / G + 1, nj, na);
+    }
+    fetch(s + 2, cj, ca, yA, eA);
+    consume(yB, eB);
   }
 }
 
@@ -449,7 +471,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
     start = (unit - A.unit_base) * A.full_len;
     len = A.full_len;
   }
-  double* own = A.own + unit * (int64_t)kp;
+  double* own = A.own + unit * (int64_t)A.stride;
   double2 x[R];
   bool in[R];
 #pragma unroll
@@ -473,7 +495,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
   // ---- gradient pass (proxgrad.jl:119-135 / :163-178) ----------------------------------------
   double2 g[R];
   double obj_old;
-  entry_pass<G, R, W, LOSS, true>(A, start, len, gid, lg, x, in, ucode, us, up1, up2, g, obj_old);
+  entry_pass<G, R, W, LOSS, true>(A, start, len, warp, lane, x, in, ucode, us, up1, up2, g, obj_old);
   unit_reduce<G, R, W, true>(obj_old, g, red, lane, warp, lg);
   if (use_reg) obj_old += reg_eval<G, R>(rcode, rp, x, lg, k);
 
@@ -491,7 +513,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
       reg_prox<G, R>(rcode, rp, xn, lg, k, stepsize);                    // :142
       double2 dummy[R];
       double obj_new;
-      entry_pass<G, R, W, LOSS, false>(A, start, len, gid, lg, xn, in, ucode, us, up1, up2, dummy, obj_new);
+      entry_pass<G, R, W, LOSS, false>(A, start, len, warp, lane, xn, in, ucode, us, up1, up2, dummy, obj_new);
       unit_reduce<G, R, W, false>(obj_new, dummy, red, lane, warp, lg);
       obj_new += reg_eval<G, R>(rcode, rp, xn, lg, k);
       ++ntrials;
@@ -558,7 +580,7 @@ __global__ void __launch_bounds__(1024) sum_kernel(const double* __restrict__ v,
 
 // out[unit] = r(own[:, unit])  — the penalty terms of calc_penalty (evaluate_fit.jl:91-104)
 template <int G, int R>
-__global__ void __launch_bounds__(128) reg_eval_kernel(const double* __restrict__ own, int64_t units, int kp, int k,
+__global__ void __launch_bounds__(128) reg_eval_kernel(const double* __restrict__ own, int64_t units, int kp, int stride, int k,
                                                        const int32_t* reg_code, const double* reg_param,
                                                        int reg_uniform, double* out) {
   const int lane = threadIdx.x & 31, lg = lane % G;
@@ -568,7 +590,7 @@ __global__ void __launch_bounds__(128) reg_eval_kernel(const double* __restrict_
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int i0 = 2 * (lg + G * r);
-    x[r] = (ok && i0 < kp) ? *reinterpret_cast<const double2*>(own + unit * (int64_t)kp + i0) : make_double2(0.0, 0.0);
+    x[r] = (ok && i0 < kp) ? *reinterpret_cast<const double2*>(own + unit * (int64_t)stride + i0) : make_double2(0.0, 0.0);
   }
   const int64_t ru = (reg_uniform || !ok) ? 0 : unit;
   const double v = reg_eval<G, R>(reg_code[ru], reg_param + ru * GLRMB200_REG_NPARAM, x, lg, k);

@@ -104,6 +104,7 @@ struct glrmb200_engine {
   int device = 0, rank = 0, nranks = 1;
   int64_t m = 0, n = 0, k = 0, d = 0;
   int kp = 0;
+  int stride = 0;           // doubles between factor columns on the device
   int tile_g = 0, tile_r = 0;
   int loss_template = 0;   // 0 generic, else uniform loss code instantiated at compile time
   double uparam[3] = {1, 0, 0};
@@ -266,7 +267,7 @@ static cudaError_t launch_reg_eval(const glrmb200_engine* E, const double* own, 
   const int g = E->tile_g, r = E->tile_r;
   const int64_t per_cta = 4 * (32 / g);
   const unsigned grid = (unsigned)((S.units + per_cta - 1) / per_cta);
-#define T(GG, RR) if (g == GG && r == RR) { reg_eval_kernel<GG, RR><<<grid, 128, 0, E->stream>>>(own, S.units, E->kp, (int)E->k, S.d_reg_code, S.d_reg_param, S.reg_uniform, out); return cudaGetLastError(); }
+#define T(GG, RR) if (g == GG && r == RR) { reg_eval_kernel<GG, RR><<<grid, 128, 0, E->stream>>>(own, S.units, E->kp, E->stride, (int)E->k, S.d_reg_code, S.d_reg_param, S.reg_uniform, out); return cudaGetLastError(); }
   T(4, 1) T(8, 1) T(8, 2) T(8, 4) T(16, 1) T(16, 2) T(16, 4) T(32, 1) T(32, 2) T(32, 4)
 #undef T
   return cudaErrorInvalidValue;
@@ -285,6 +286,7 @@ static SweepArgs make_args(const glrmb200_engine* E, bool x_side, int flags, dou
   A.own = x_side ? E->d_X : E->d_Y;
   A.opp = x_side ? E->d_Y : E->d_X;
   A.kp = E->kp;
+  A.stride = E->stride;
   A.k = (int)E->k;
   A.loss_code = E->d_loss_code;
   A.loss_param = E->d_loss_param;
@@ -364,6 +366,10 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
 
   // ---- tile selection ---------------------------------------------------------------------------
   E->kp = (int)((k + 3) / 4 * 4);
+  // columns start on 128-byte lines once they are longer than one line (gathers then touch the minimum
+  // number of L1 wavefronts); short columns stay packed
+  E->stride = E->kp <= 8 ? 8 : (E->kp <= 16 ? 16 : (E->kp + 15) / 16 * 16);
+  if (const char* t = getenv("GLRMB200_PACKED")) { if (atoi(t)) E->stride = E->kp; }
   if (E->kp > 256) return fail(GLRMB200_E_UNSUPPORTED, "k = %lld: ranks above 256 are not supported", (long long)k);
   if (E->kp <= 8) { E->tile_g = 4; E->tile_r = 1; }
   else if (E->kp <= 16) { E->tile_g = 8; E->tile_r = 1; }
@@ -491,8 +497,8 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
     if ((rc = up_side(C, P->col_ptr, P->col_idx, P->col_val))) return rc;
   }
 
-  CUDA_OK(cudaMalloc((void**)&E->d_X, (size_t)m * E->kp * sizeof(double)));
-  CUDA_OK(cudaMalloc((void**)&E->d_Y, (size_t)E->d * E->kp * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&E->d_X, (size_t)m * E->stride * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&E->d_Y, (size_t)E->d * E->stride * sizeof(double)));
   CUDA_OK(cudaMalloc((void**)&R.d_alpha, (size_t)m * sizeof(double)));
   CUDA_OK(cudaMalloc((void**)&C.d_alpha, (size_t)n * sizeof(double)));
   CUDA_OK(cudaMalloc((void**)&R.d_obj, (size_t)m * sizeof(double)));
@@ -550,8 +556,8 @@ extern "C" int glrmb200_shard(glrmb200_handle E, int64_t* rb, int64_t* re, int64
 extern "C" int glrmb200_upload_factors(glrmb200_handle E, const double* X, const double* Y) {
   if (!E || !X || !Y) return fail(GLRMB200_E_INVALID, "null argument");
   CUDA_OK(cudaSetDevice(E->device));
-  const size_t kb = (size_t)E->k * sizeof(double), pb = (size_t)E->kp * sizeof(double);
-  if (E->kp != E->k) {
+  const size_t kb = (size_t)E->k * sizeof(double), pb = (size_t)E->stride * sizeof(double);
+  if (E->stride != E->k) {
     CUDA_OK(cudaMemsetAsync(E->d_X, 0, (size_t)E->m * pb, E->stream));
     CUDA_OK(cudaMemsetAsync(E->d_Y, 0, (size_t)E->d * pb, E->stream));
   }
@@ -566,7 +572,7 @@ extern "C" int glrmb200_download_factors(glrmb200_handle E, double* X, double* Y
   if (!E || !X || !Y) return fail(GLRMB200_E_INVALID, "null argument");
   if (!E->factors_resident) return fail(GLRMB200_E_STATE, "no factors on the device");
   CUDA_OK(cudaSetDevice(E->device));
-  const size_t kb = (size_t)E->k * sizeof(double), pb = (size_t)E->kp * sizeof(double);
+  const size_t kb = (size_t)E->k * sizeof(double), pb = (size_t)E->stride * sizeof(double);
   CUDA_OK(cudaMemcpy2DAsync(X, kb, E->d_X, pb, kb, (size_t)E->m, cudaMemcpyDeviceToHost, E->stream));
   CUDA_OK(cudaMemcpy2DAsync(Y, kb, E->d_Y, pb, kb, (size_t)E->d, cudaMemcpyDeviceToHost, E->stream));
   CUDA_OK(cudaStreamSynchronize(E->stream));
@@ -673,7 +679,7 @@ extern "C" int glrmb200_fit_resident(glrmb200_handle E, const glrmb200_params* p
       if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "update-X launch: %s", cudaGetErrorString(ce));
     }
     CUDA_OK(cudaEventRecord(E->ev[1], E->stream));
-    if ((rc = allgather_units(E, E->d_X, E->rows, E->kp))) return rc;
+    if ((rc = allgather_units(E, E->d_X, E->rows, E->stride))) return rc;
     CUDA_OK(cudaEventRecord(E->ev[2], E->stream));
     for (int inner = 0; inner < prm->inner_iter_Y; ++inner) {                  // :160-203
       SweepArgs A = make_args(E, false, 0, prm->min_stepsize);
@@ -681,7 +687,7 @@ extern "C" int glrmb200_fit_resident(glrmb200_handle E, const glrmb200_params* p
       if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "update-Y launch: %s", cudaGetErrorString(ce));
     }
     CUDA_OK(cudaEventRecord(E->ev[3], E->stream));
-    if ((rc = allgather_units(E, E->d_Y, E->cols, E->kp))) return rc;
+    if ((rc = allgather_units(E, E->d_Y, E->cols, E->stride))) return rc;
     if ((rc = allgather_units(E, E->cols.d_obj, E->cols, 1))) return rc;
     CUDA_OK(cudaEventRecord(E->ev[4], E->stream));
     double obj = 0.0;

@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Tuning sweep on the GPU box: one problem, several engine configurations (env hooks read at create)."""
+import itertools, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import lowrankmodels_b200 as lrm
+from bench import build_problem
+
+config = sys.argv[1] if len(sys.argv) > 1 else "C2"
+scale = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+variants = sys.argv[3:] or ["", "GLRMB200_PACKED=1", "GLRMB200_TILE=16,2", "GLRMB200_TILE=16,4", "GLRMB200_HEAVY=512",
+                            "GLRMB200_HEAVY=2048", "GLRMB200_HEAVY=4096"]
+g, cfg = build_problem(config, scale)
+ep = lrm.encode_problem(g, validate=False)
+nnz = ep.nnz
+pw = lrm.ProxGradParams(max_iter=3, abs_tol=0, rel_tol=0)
+pk = lrm.ProxGradParams(max_iter=10, abs_tol=0, rel_tol=0)
+ref = None
+for v in variants:
+    keys = []
+    for kv in v.split():
+        k_, val = kv.split("=")
+        os.environ[k_] = val
+        keys.append(k_)
+    eng = lrm.Engine(ep, validate=False)
+    eng.upload(g.X, g.Y)
+    eng.fit_resident(pw)
+    obj, _ = eng.fit_resident(pk)
+    p = eng.last_profile
+    eng.close()
+    for k_ in keys:
+        del os.environ[k_]
+    if ref is None:
+        ref = obj
+    dev = float(np.max(np.abs(obj - ref) / np.abs(ref)))
+    print(json.dumps({"variant": v or "default", "ms_per_step": p["loop_ms"] / 10, "x_ms": p["update_x_ms"] / 10,
+                      "y_ms": p["update_y_ms"] / 10, "Gentries_s": nnz / (p["loop_ms"] / 10 * 1e-3) / 1e9,
+                      "x_trials": p["x_trials"], "y_trials": p["y_trials"], "obj_last": float(obj[-1]),
+                      "max_rel_dev_vs_first": dev}), flush=True)
