@@ -40,8 +40,7 @@ struct SweepArgs {
   int64_t n_units;        // units this launch covers: order[0 .. n_units)
   double* own;            // factor being updated   [units_total * kp]
   const double* opp;      // factor being gathered  [opp_total * kp]
-  int32_t kp;             // padded rank (multiple of 4 doubles = 32 B)
-  int32_t stride;         // doubles between factor columns (kp rounded up so columns start on 128 B lines)
+  int32_t stride;         // doubles between factor columns == 2*G*R of the tile (zero-padded past k)
   int32_t k;              // rank
   const int32_t* loss_code;   // [n] per feature
   const double* loss_param;   // [n * 8]
@@ -342,59 +341,64 @@ __device__ __forceinline__ void reg_prox(int code, const double* __restrict__ rp
 // (idx, val) of entry l with one coalesced streaming load, one chunk ahead of use, and the groups pick
 // their entry up by shuffle — the index load never sits in front of the gather it feeds.  The gathers
 // themselves are double-buffered: the R 16-byte loads of step s+1 are in flight while step s is reduced,
-// so every lane group always has one factor column on its way from L2.
+// so every lane group always has one factor column on its way from L2.  The loop body is branch-free.
 template <int G, int R, int W, int LOSS, bool GRAD>
 __device__ __forceinline__ void entry_pass(const SweepArgs& A, int64_t start, int64_t len, int warp, int lane,
-                                           const double2 (&x)[R], const bool (&in)[R], int ucode, double us,
+                                           const double2 (&x)[R], int ucode, double us,
                                            double up1, double up2, double2 (&g)[R], double& obj) {
   constexpr int NGW = 32 / G;
   const int lg = lane % G, gq = lane / G;
   const bool by_entry = (LOSS == 0) && (A.flags & FLAG_LOSS_BY_ENTRY);
-  const int64_t nchunks = (len + 31) >> 5;
-  const int64_t my_chunks = (nchunks + W - 1) / W;   // same trip count in every warp of the unit
-  const int64_t nsteps = my_chunks * G;
+  const uint32_t ulen = (uint32_t)len;
+  const uint32_t nchunks = (ulen + 31u) >> 5;
+  const uint32_t my_chunks = (nchunks + W - 1) / W;   // same trip count in every warp of the unit
+  const uint32_t nsteps = my_chunks * G;
+  const char* opp_lane = reinterpret_cast<const char*>(A.opp + 2 * lg);
+  const int stride_bytes = A.stride * 8;
   obj = 0.0;
   if (GRAD) {
 #pragma unroll
     for (int r = 0; r < R; ++r) g[r] = make_double2(0.0, 0.0);
   }
-  auto load_chunk = [&](int64_t ci, int32_t& j, double& a) {
-    const int64_t t = ((ci * W + warp) << 5) + lane;
-    const bool ok = ci < my_chunks && t < len;
-    const int64_t q = start + (ok ? t : 0);
-    j = ok ? (A.idx ? __ldcs(A.idx + q) : (int32_t)t) : -1;
-    a = ok ? __ldcs(A.val + q) : 0.0;
+  auto load_chunk = [&](uint32_t ci, int32_t& j, double& a) {
+    const uint32_t t = ((ci * W + warp) << 5) + lane;
+    const bool ok = ci < my_chunks && t < ulen;
+    const int64_t q = start + (ok ? t : 0u);
+    const int32_t jr = A.idx ? __ldcs(A.idx + q) : (int32_t)t;
+    const double ar = __ldcs(A.val + q);
+    j = ok ? jr : -1;
+    a = ok ? ar : 0.0;
   };
   struct Ent { int32_t j; double a; int code; double s, p1, p2; };
-  auto fetch = [&](int64_t s, int32_t cj, double ca, double2 (&y)[R], Ent& e) {
-    const int src = (int)(s % G) * NGW + gq;
+  auto fetch = [&](uint32_t s, int32_t cj, double ca, double2 (&y)[R], Ent& e) {
+    const int src = (int)(s & (G - 1)) * NGW + gq;
     e.j = __shfl_sync(FULLMASK, cj, src);
     e.a = __shfl_sync(FULLMASK, ca, src);
-    const bool act = e.j >= 0;
-    const double* yp = A.opp + (int64_t)(act ? e.j : 0) * A.stride + 2 * lg;
+    const int32_t jj = e.j < 0 ? 0 : e.j;          // inactive slots read column 0 and are masked below
+    // stride == 2*G*R: every lane's slot exists (zeros past k), so the R loads carry immediate offsets
+    const char* yp = opp_lane + (int64_t)jj * stride_bytes;
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-      y[r] = (act && in[r]) ? __ldg(reinterpret_cast<const double2*>(yp + 2 * G * r)) : make_double2(0.0, 0.0);
+    for (int r = 0; r < R; ++r) y[r] = __ldg(reinterpret_cast<const double2*>(yp + r * G * 16));
     e.code = ucode; e.s = us; e.p1 = up1; e.p2 = up2;
-    if (by_entry && act) {
-      e.code = __ldg(A.loss_code + e.j);
-      const double* lp = A.loss_param + (int64_t)e.j * GLRMB200_LOSS_NPARAM;
+    if (by_entry) {
+      e.code = __ldg(A.loss_code + jj);
+      const double* lp = A.loss_param + (int64_t)jj * GLRMB200_LOSS_NPARAM;
       e.s = __ldg(lp); e.p1 = __ldg(lp + 1); e.p2 = __ldg(lp + 2);
     }
   };
   auto consume = [&](const double2 (&y)[R], const Ent& e) {
-    double dot = 0.0;
+    double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-    for (int r = 0; r < R; ++r) dot = fma(y[r].x, x[r].x, fma(y[r].y, x[r].y, dot));
-    dot = group_sum<G>(dot);
+    for (int r = 0; r < R; ++r) { d0 = fma(y[r].x, x[r].x, d0); d1 = fma(y[r].y, x[r].y, d1); }
+    const double dot = group_sum<G>(d0 + d1);
     double l, c;
     loss_eval<LOSS, GRAD>(e.code, e.s, e.p1, e.p2, dot, e.a, l, c);
-    if (e.j >= 0) {
-      obj += l;
-      if (GRAD) {
+    const bool act = e.j >= 0;
+    obj += act ? l : 0.0;
+    if (GRAD) {
+      c = act ? c : 0.0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) { g[r].x = fma(c, y[r].x, g[r].x); g[r].y = fma(c, y[r].y, g[r].y); }
-      }
+      for (int r = 0; r < R; ++r) { g[r].x = fma(c, y[r].x, g[r].x); g[r].y = fma(c, y[r].y, g[r].y); }
     }
   };
   int32_t cj, nj;
@@ -404,10 +408,10 @@ __device__ __forceinline__ void entry_pass(const SweepArgs& A, int64_t start, in
   double2 yA[R], yB[R];
   Ent eA, eB;
   fetch(0, cj, ca, yA, eA);
-  for (int64_t s = 0; s < nsteps; s += 2) {       // G is even: steps s and s+1 share a chunk
+  for (uint32_t s = 0; s < nsteps; s += 2) {      // G is even: steps s and s+1 share a chunk
     fetch(s + 1, cj, ca, yB, eB);
     consume(yA, eA);
-    if (((s + 2) % G) == 0) {                     // step s+2 opens the next chunk
+    if (((s + 2) & (G - 1)) == 0) {               // step s+2 opens the next chunk
       cj = nj; ca = na;
       load_chunk((s + 2) / G + 1, nj, na);
     }
@@ -461,7 +465,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
   const int warp = (W == 1) ? 0 : (threadIdx.x >> 5);
   const int lg = lane % G;
   const int gid = warp * NGW + lane / G;
-  const int kp = A.kp, k = A.k;
+  const int k = A.k;
 
   int64_t start, len;
   if (A.ptr) {
@@ -472,14 +476,10 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
     len = A.full_len;
   }
   double* own = A.own + unit * (int64_t)A.stride;
+  // columns are stored with stride 2*G*R doubles, zero past k: every lane owns R real slots
   double2 x[R];
-  bool in[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int i0 = 2 * (lg + G * r);
-    in[r] = i0 < kp;
-    x[r] = in[r] ? *reinterpret_cast<const double2*>(own + i0) : make_double2(0.0, 0.0);
-  }
+  for (int r = 0; r < R; ++r) x[r] = *reinterpret_cast<const double2*>(own + 2 * (lg + G * r));
   // loss descriptor: uniform (template / by value), per unit (Y sweep), or per entry (X sweep)
   int ucode = LOSS;
   double us = A.uparam[0], up1 = A.uparam[1], up2 = A.uparam[2];
@@ -495,7 +495,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
   // ---- gradient pass (proxgrad.jl:119-135 / :163-178) ----------------------------------------
   double2 g[R];
   double obj_old;
-  entry_pass<G, R, W, LOSS, true>(A, start, len, warp, lane, x, in, ucode, us, up1, up2, g, obj_old);
+  entry_pass<G, R, W, LOSS, true>(A, start, len, warp, lane, x, ucode, us, up1, up2, g, obj_old);
   unit_reduce<G, R, W, true>(obj_old, g, red, lane, warp, lg);
   if (use_reg) obj_old += reg_eval<G, R>(rcode, rp, x, lg, k);
 
@@ -513,7 +513,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
       reg_prox<G, R>(rcode, rp, xn, lg, k, stepsize);                    // :142
       double2 dummy[R];
       double obj_new;
-      entry_pass<G, R, W, LOSS, false>(A, start, len, warp, lane, xn, in, ucode, us, up1, up2, dummy, obj_new);
+      entry_pass<G, R, W, LOSS, false>(A, start, len, warp, lane, xn, ucode, us, up1, up2, dummy, obj_new);
       unit_reduce<G, R, W, false>(obj_new, dummy, red, lane, warp, lg);
       obj_new += reg_eval<G, R>(rcode, rp, xn, lg, k);
       ++ntrials;
@@ -533,10 +533,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
   if (gid == 0) {
     if (accepted) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int i0 = 2 * (lg + G * r);
-        if (in[r]) *reinterpret_cast<double2*>(own + i0) = x[r];
-      }
+      for (int r = 0; r < R; ++r) *reinterpret_cast<double2*>(own + 2 * (lg + G * r)) = x[r];
     }
     if (lg == 0) {
       A.alpha[unit] = alpha;
@@ -551,7 +548,7 @@ constexpr int WARPS_PER_CTA_HEAVY = 8;
 
 // light units: one warp per unit, no block-level synchronisation
 template <int G, int R, int LOSS>
-__global__ void __launch_bounds__(WARPS_PER_CTA_LIGHT * 32) sweep_warp_kernel(const SweepArgs A) {
+__global__ void __launch_bounds__(WARPS_PER_CTA_LIGHT * 32, 4) sweep_warp_kernel(const SweepArgs A) {
   const int64_t slot = (int64_t)blockIdx.x * WARPS_PER_CTA_LIGHT + (threadIdx.x >> 5);
   if (slot >= A.n_units) return;
   process_unit<G, R, 1, LOSS>(A, A.order[slot], nullptr);
@@ -559,7 +556,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA_LIGHT * 32) sweep_warp_kernel(co
 
 // heavy units: one CTA (8 warps) per unit
 template <int G, int R, int LOSS>
-__global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32) sweep_cta_kernel(const SweepArgs A) {
+__global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32, 2) sweep_cta_kernel(const SweepArgs A) {
   __shared__ double red[WARPS_PER_CTA_HEAVY * (G * 2 * R + 1)];
   process_unit<G, R, WARPS_PER_CTA_HEAVY, LOSS>(A, A.order[blockIdx.x], red);
 }
@@ -580,7 +577,7 @@ __global__ void __launch_bounds__(1024) sum_kernel(const double* __restrict__ v,
 
 // out[unit] = r(own[:, unit])  — the penalty terms of calc_penalty (evaluate_fit.jl:91-104)
 template <int G, int R>
-__global__ void __launch_bounds__(128) reg_eval_kernel(const double* __restrict__ own, int64_t units, int kp, int stride, int k,
+__global__ void __launch_bounds__(128) reg_eval_kernel(const double* __restrict__ own, int64_t units, int stride, int k,
                                                        const int32_t* reg_code, const double* reg_param,
                                                        int reg_uniform, double* out) {
   const int lane = threadIdx.x & 31, lg = lane % G;
@@ -590,7 +587,7 @@ __global__ void __launch_bounds__(128) reg_eval_kernel(const double* __restrict_
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int i0 = 2 * (lg + G * r);
-    x[r] = (ok && i0 < kp) ? *reinterpret_cast<const double2*>(own + unit * (int64_t)stride + i0) : make_double2(0.0, 0.0);
+    x[r] = ok ? *reinterpret_cast<const double2*>(own + unit * (int64_t)stride + i0) : make_double2(0.0, 0.0);
   }
   const int64_t ru = (reg_uniform || !ok) ? 0 : unit;
   const double v = reg_eval<G, R>(reg_code[ru], reg_param + ru * GLRMB200_REG_NPARAM, x, lg, k);

@@ -226,7 +226,7 @@ static int setup_regs(Side& S, int64_t count, const int32_t* code, const double*
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch over the (G, R) tile and the loss template
 struct Tile { int g, r; };
-static const Tile kTiles[] = {{4, 1}, {8, 1}, {8, 2}, {8, 4}, {16, 1}, {16, 2}, {16, 4}, {32, 1}, {32, 2}, {32, 4}};
+static const Tile kTiles[] = {{4, 1}, {8, 1}, {8, 2}, {8, 3}, {8, 4}, {16, 2}, {16, 3}, {16, 4}, {32, 2}, {32, 3}, {32, 4}};
 
 template <int G, int R, int LOSS>
 static cudaError_t launch_tile(const SweepArgs& A, int64_t n_heavy, int64_t n_light, cudaStream_t st, int64_t* launches) {
@@ -250,7 +250,7 @@ static cudaError_t launch_tile(const SweepArgs& A, int64_t n_heavy, int64_t n_li
 template <int LOSS>
 static cudaError_t launch_loss(int g, int r, const SweepArgs& A, int64_t nh, int64_t nl, cudaStream_t st, int64_t* launches) {
 #define T(GG, RR) if (g == GG && r == RR) return launch_tile<GG, RR, LOSS>(A, nh, nl, st, launches)
-  T(4, 1); T(8, 1); T(8, 2); T(8, 4); T(16, 1); T(16, 2); T(16, 4); T(32, 1); T(32, 2); T(32, 4);
+  T(4, 1); T(8, 1); T(8, 2); T(8, 3); T(8, 4); T(16, 2); T(16, 3); T(16, 4); T(32, 2); T(32, 3); T(32, 4);
 #undef T
   return cudaErrorInvalidValue;
 }
@@ -267,8 +267,8 @@ static cudaError_t launch_reg_eval(const glrmb200_engine* E, const double* own, 
   const int g = E->tile_g, r = E->tile_r;
   const int64_t per_cta = 4 * (32 / g);
   const unsigned grid = (unsigned)((S.units + per_cta - 1) / per_cta);
-#define T(GG, RR) if (g == GG && r == RR) { reg_eval_kernel<GG, RR><<<grid, 128, 0, E->stream>>>(own, S.units, E->kp, E->stride, (int)E->k, S.d_reg_code, S.d_reg_param, S.reg_uniform, out); return cudaGetLastError(); }
-  T(4, 1) T(8, 1) T(8, 2) T(8, 4) T(16, 1) T(16, 2) T(16, 4) T(32, 1) T(32, 2) T(32, 4)
+#define T(GG, RR) if (g == GG && r == RR) { reg_eval_kernel<GG, RR><<<grid, 128, 0, E->stream>>>(own, S.units, E->stride, (int)E->k, S.d_reg_code, S.d_reg_param, S.reg_uniform, out); return cudaGetLastError(); }
+  T(4, 1) T(8, 1) T(8, 2) T(8, 3) T(8, 4) T(16, 2) T(16, 3) T(16, 4) T(32, 2) T(32, 3) T(32, 4)
 #undef T
   return cudaErrorInvalidValue;
 }
@@ -285,7 +285,6 @@ static SweepArgs make_args(const glrmb200_engine* E, bool x_side, int flags, dou
   A.n_units = 0;
   A.own = x_side ? E->d_X : E->d_Y;
   A.opp = x_side ? E->d_Y : E->d_X;
-  A.kp = E->kp;
   A.stride = E->stride;
   A.k = (int)E->k;
   A.loss_code = E->d_loss_code;
@@ -365,24 +364,22 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   }
 
   // ---- tile selection ---------------------------------------------------------------------------
-  E->kp = (int)((k + 3) / 4 * 4);
-  // columns start on 128-byte lines once they are longer than one line (gathers then touch the minimum
-  // number of L1 wavefronts); short columns stay packed
-  E->stride = E->kp <= 8 ? 8 : (E->kp <= 16 ? 16 : (E->kp + 15) / 16 * 16);
-  if (const char* t = getenv("GLRMB200_PACKED")) { if (atoi(t)) E->stride = E->kp; }
+  // tile = lane-group width G x slots per lane R; a factor column is stored as 2*G*R doubles (zero past k)
+  // so that every gather is R unconditional 16-byte loads per lane with immediate offsets.  Pick the
+  // narrowest group that holds k in at most 4 slots per lane (fewest reduction shuffles, least padding).
+  E->kp = (int)((k + 1) / 2 * 2);
   if (E->kp > 256) return fail(GLRMB200_E_UNSUPPORTED, "k = %lld: ranks above 256 are not supported", (long long)k);
   if (E->kp <= 8) { E->tile_g = 4; E->tile_r = 1; }
-  else if (E->kp <= 16) { E->tile_g = 8; E->tile_r = 1; }
-  else if (E->kp <= 32) { E->tile_g = 8; E->tile_r = 2; }
-  else if (E->kp <= 64) { E->tile_g = 8; E->tile_r = 4; }
-  else if (E->kp <= 128) { E->tile_g = 16; E->tile_r = 4; }
-  else { E->tile_g = 32; E->tile_r = 4; }
+  else if (E->kp <= 64) { E->tile_g = 8; E->tile_r = (E->kp + 15) / 16; }
+  else if (E->kp <= 128) { E->tile_g = 16; E->tile_r = (E->kp + 31) / 32; }
+  else { E->tile_g = 32; E->tile_r = (E->kp + 63) / 64; }
   if (const char* t = getenv("GLRMB200_TILE")) {   // tuning hook: "G,R"
     int g = 0, r = 0;
     if (sscanf(t, "%d,%d", &g, &r) == 2 && 2 * g * r >= E->kp) {
       for (const Tile& tl : kTiles) if (tl.g == g && tl.r == r) { E->tile_g = g; E->tile_r = r; }
     }
   }
+  E->stride = 2 * E->tile_g * E->tile_r;
   if (const char* t = getenv("GLRMB200_HEAVY")) E->heavy_threshold = std::max<long long>(1, atoll(t));
 
   // ---- observation lists: validation (glrm.jl:63-71, losses.jl:104) ----------------------------
