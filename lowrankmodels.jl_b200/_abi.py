@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libglrm_b200.so")
+LIB_PATH = os.environ.get("GLRMB200_LIB", os.path.join(_HERE, "csrc", "libglrm_b200.so"))  # env: tuning builds
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

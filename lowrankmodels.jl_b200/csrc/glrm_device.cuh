@@ -27,6 +27,7 @@
 namespace glrm {
 
 constexpr unsigned FULLMASK = 0xffffffffu;
+#define TRIAL_TILE_DOUBLES(G) ((G) <= 8 ? 2 * 32 * ((G) + 1) : 1)   /* two [32][G+1] partial-dot tiles per warp (narrow groups only) */
 enum : int { FLAG_EVAL_ONLY = 1, FLAG_NO_REG = 2, FLAG_LOSS_BY_ENTRY = 4 };
 
 struct SweepArgs {
@@ -342,7 +343,7 @@ __device__ __forceinline__ void reg_prox(int code, const double* __restrict__ rp
 // their entry up by shuffle — the index load never sits in front of the gather it feeds.  The gathers
 // themselves are double-buffered: the R 16-byte loads of step s+1 are in flight while step s is reduced,
 // so every lane group always has one factor column on its way from L2.  The loop body is branch-free.
-template <int G, int R, int W, int LOSS, bool GRAD>
+template <int G, int R, int W, int LOSS, bool GRAD, int PIPE_DEPTH>
 __device__ __forceinline__ void entry_pass(const SweepArgs& A, int64_t start, int64_t len, int warp, int lane,
                                            const double2 (&x)[R], int ucode, double us,
                                            double up1, double up2, double2 (&g)[R], double& obj) {
@@ -401,23 +402,122 @@ __device__ __forceinline__ void entry_pass(const SweepArgs& A, int64_t start, in
       for (int r = 0; r < R; ++r) { g[r].x = fma(c, y[r].x, g[r].x); g[r].y = fma(c, y[r].y, g[r].y); }
     }
   };
-  int32_t cj, nj;
+  // software pipeline of depth D: D-1 steps of gathers are always in flight per lane group
+  // (in-flight entries per SM = warps x groups x (D-1); with ~600-cycle loaded L2 latency this, not
+  // instruction issue, bounds the sweep — see DESIGN.md "Little's law").
+  constexpr int D = PIPE_DEPTH;
+  int32_t fj, nj;            // (idx) of the chunk the fetch stream is in, and of the following chunk
+  double fa, na;
+  load_chunk(0, fj, fa);
+  load_chunk(1, nj, na);
+  double2 y[D][R];
+  Ent e[D];
+  auto fetch_step = [&](uint32_t f, double2 (&yy)[R], Ent& ee) {
+    if (f != 0 && (f & (G - 1)) == 0) {           // the fetch stream enters the next chunk
+      fj = nj; fa = na;
+      load_chunk(f / G + 1, nj, na);
+    }
+    fetch(f, fj, fa, yy, ee);
+  };
+#pragma unroll
+  for (int u = 0; u < D - 1; ++u) fetch_step(u, y[u], e[u]);
+  for (uint32_t s = 0; s < nsteps; s += D) {      // nsteps is a multiple of G, G of D
+#pragma unroll
+    for (int u = 0; u < D; ++u) {
+      fetch_step(s + u + D - 1, y[(u + D - 1) % D], e[(u + D - 1) % D]);
+      consume(y[u], e[u]);
+    }
+  }
+}
+
+// Line-search trial pass: objective only.  No gradient means the gathered column is dead once its
+// partial dot product exists, so the cross-lane reduction is taken off the critical path: every lane
+// stores its partial (one STS per step) into a per-warp [32 entries][G lanes] tile, and once the 32
+// entries of a chunk are in, lane l finishes entry l — sums its G partials in a fixed order, evaluates
+// the loss with the A value it already holds from the coalesced chunk load, and accumulates.  No
+// shuffles, 32 losses per instruction stream (vs 32/G), and the gathers of the next chunk are already
+// in flight while a chunk is being finished.
+template <int G, int R, int W, int LOSS, int PIPE_DEPTH>
+__device__ __forceinline__ double trial_pass(const SweepArgs& A, int64_t start, int64_t len, int warp, int lane,
+                                             const double2 (&x)[R], int ucode, double us, double up1,
+                                             double up2, double* part) {
+  constexpr int NGW = 32 / G;
+  constexpr int ROW = G + 1;                       // odd row pitch: conflict-free transposed reads
+  constexpr int D = PIPE_DEPTH;
+  const int lg = lane % G, gq = lane / G;
+  const bool by_entry = (LOSS == 0) && (A.flags & FLAG_LOSS_BY_ENTRY);
+  const uint32_t ulen = (uint32_t)len;
+  const uint32_t nchunks = (ulen + 31u) >> 5;
+  const uint32_t my_chunks = (nchunks + W - 1) / W;
+  const uint32_t nsteps = my_chunks * G;
+  const char* opp_lane = reinterpret_cast<const char*>(A.opp + 2 * lg);
+  const int stride_bytes = A.stride * 8;
+  double obj = 0.0;
+  auto load_chunk = [&](uint32_t ci, int32_t& j, double& a) {
+    const uint32_t t = ((ci * W + warp) << 5) + lane;
+    const bool ok = ci < my_chunks && t < ulen;
+    const int64_t q = start + (ok ? t : 0u);
+    const int32_t jr = A.idx ? __ldcs(A.idx + q) : (int32_t)t;
+    const double ar = __ldcs(A.val + q);
+    j = ok ? jr : -1;
+    a = ok ? ar : 0.0;
+  };
+  int32_t cj, nj;   // chunk being consumed / next chunk: lane l holds entry l of the chunk
   double ca, na;
   load_chunk(0, cj, ca);
   load_chunk(1, nj, na);
-  double2 yA[R], yB[R];
-  Ent eA, eB;
-  fetch(0, cj, ca, yA, eA);
-  for (uint32_t s = 0; s < nsteps; s += 2) {      // G is even: steps s and s+1 share a chunk
-    fetch(s + 1, cj, ca, yB, eB);
-    consume(yA, eA);
-    if (((s + 2) & (G - 1)) == 0) {               // step s+2 opens the next chunk
-      cj = nj; ca = na;
-      load_chunk((s + 2) / G + 1, nj, na);
+  uint32_t cons_chunk = 0;
+  auto fetch = [&](uint32_t f, double2 (&y)[R]) {
+    const int32_t sj = (f / G == cons_chunk) ? cj : nj;       // the fetch stream runs < G steps ahead
+    const int src = (int)(f & (G - 1)) * NGW + gq;
+    const int32_t j = __shfl_sync(FULLMASK, sj, src);
+    const char* yp = opp_lane + (int64_t)(j < 0 ? 0 : j) * stride_bytes;
+#pragma unroll
+    for (int r = 0; r < R; ++r) y[r] = __ldg(reinterpret_cast<const double2*>(yp + r * G * 16));
+  };
+  auto consume = [&](uint32_t c, const double2 (&y)[R]) {
+    double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) { d0 = fma(y[r].x, x[r].x, d0); d1 = fma(y[r].y, x[r].y, d1); }
+    const uint32_t cs = c & (G - 1);
+    double* buf = part + ((c / G) & 1u) * (32 * ROW);
+    buf[(cs * NGW + gq) * ROW + lg] = d0 + d1;
+    if (cs == G - 1) {                              // chunk complete: lane l finishes entry l
+      __syncwarp();
+      const double* row = buf + lane * ROW;
+      double u = row[0];
+#pragma unroll
+      for (int i = 1; i < G; ++i) u += row[i];
+      int code = ucode;
+      double ls = us, p1 = up1, p2 = up2;
+      if (by_entry) {
+        const int32_t jj = cj < 0 ? 0 : cj;
+        code = __ldg(A.loss_code + jj);
+        const double* lp = A.loss_param + (int64_t)jj * GLRMB200_LOSS_NPARAM;
+        ls = __ldg(lp); p1 = __ldg(lp + 1); p2 = __ldg(lp + 2);
+      }
+      double l, cdummy;
+      loss_eval<LOSS, false>(code, ls, p1, p2, u, ca, l, cdummy);
+      obj += (cj >= 0) ? l : 0.0;
+      cj = nj; ca = na;                             // consumption moves to the next chunk
+      ++cons_chunk;
+      load_chunk(cons_chunk + 1, nj, na);
     }
-    fetch(s + 2, cj, ca, yA, eA);
-    consume(yB, eB);
+  };
+  double2 y[D][R];
+#pragma unroll
+  for (int u = 0; u < D - 1; ++u) fetch(u, y[u]);
+  for (uint32_t s = 0; s < nsteps; s += D) {
+#pragma unroll
+    for (int u = 0; u < D; ++u) {
+      fetch(s + u + D - 1, y[(u + D - 1) % D]);
+      consume(s + u, y[u]);
+    }
   }
+  // warp total in a fixed order (all lanes end with the same bits)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) obj += __shfl_xor_sync(FULLMASK, obj, o);
+  return obj;
 }
 
 // reduce (obj [, g]) over all groups of the unit: shuffles inside the warp, shared memory across warps
@@ -458,8 +558,8 @@ __device__ __forceinline__ void unit_reduce(double& obj, double2 (&g)[R], double
   }
 }
 
-template <int G, int R, int W, int LOSS>
-__device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, double* red) {
+template <int G, int R, int W, int LOSS, int DEPTH>
+__device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, double* red, double* part) {
   constexpr int NGW = 32 / G;
   const int lane = threadIdx.x & 31;
   const int warp = (W == 1) ? 0 : (threadIdx.x >> 5);
@@ -495,7 +595,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
   // ---- gradient pass (proxgrad.jl:119-135 / :163-178) ----------------------------------------
   double2 g[R];
   double obj_old;
-  entry_pass<G, R, W, LOSS, true>(A, start, len, warp, lane, x, ucode, us, up1, up2, g, obj_old);
+  entry_pass<G, R, W, LOSS, true, DEPTH>(A, start, len, warp, lane, x, ucode, us, up1, up2, g, obj_old);
   unit_reduce<G, R, W, true>(obj_old, g, red, lane, warp, lg);
   if (use_reg) obj_old += reg_eval<G, R>(rcode, rp, x, lg, k);
 
@@ -511,10 +611,22 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
 #pragma unroll
       for (int r = 0; r < R; ++r) { xn[r].x = fma(-stepsize, g[r].x, x[r].x); xn[r].y = fma(-stepsize, g[r].y, x[r].y); }  // :140
       reg_prox<G, R>(rcode, rp, xn, lg, k, stepsize);                    // :142
-      double2 dummy[R];
       double obj_new;
-      entry_pass<G, R, W, LOSS, false>(A, start, len, warp, lane, xn, ucode, us, up1, up2, dummy, obj_new);
-      unit_reduce<G, R, W, false>(obj_new, dummy, red, lane, warp, lg);
+      if constexpr (G <= 8) {                       // shared-memory transposed reduction (k <= 64)
+        obj_new = trial_pass<G, R, W, LOSS, DEPTH>(A, start, len, warp, lane, xn, ucode, us, up1, up2,
+                                                   part + (W == 1 ? (threadIdx.x >> 5) : warp) * TRIAL_TILE_DOUBLES(G));
+        if (W > 1) {                                // cross-warp total through shared memory, fixed order
+          __syncthreads();
+          if (lane == 0) red[warp] = obj_new;
+          __syncthreads();
+          obj_new = 0.0;
+          for (int w = 0; w < W; ++w) obj_new += red[w];
+        }
+      } else {                                      // wide groups: shuffle-reduced pass
+        double2 dummy[R];
+        entry_pass<G, R, W, LOSS, false, DEPTH>(A, start, len, warp, lane, xn, ucode, us, up1, up2, dummy, obj_new);
+        unit_reduce<G, R, W, false>(obj_new, dummy, red, lane, warp, lg);
+      }
       obj_new += reg_eval<G, R>(rcode, rp, xn, lg, k);
       ++ntrials;
       if (obj_new < obj_old) {                                           // :143 (strict; NaN rejects)
@@ -546,19 +658,32 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
 constexpr int WARPS_PER_CTA_LIGHT = 4;
 constexpr int WARPS_PER_CTA_HEAVY = 8;
 
+// pipeline depth / residency per tile: D gather buffers of R double2 each; 12 warps per SM for the
+// wide tiles (<= 168 registers), 16 for the narrow ones
+#ifndef GLRM_PIPE_DEPTH
+#define GLRM_PIPE_DEPTH 2
+#endif
+template <int R> struct TileCfg {
+  static constexpr int DEPTH = GLRM_PIPE_DEPTH;
+  static constexpr int LIGHT_CTAS = (R >= 3 && GLRM_PIPE_DEPTH > 2) ? 3 : 4;
+  static constexpr int HEAVY_CTAS = (R >= 3 && GLRM_PIPE_DEPTH > 2) ? 1 : 2;
+};
+
 // light units: one warp per unit, no block-level synchronisation
 template <int G, int R, int LOSS>
-__global__ void __launch_bounds__(WARPS_PER_CTA_LIGHT * 32, 4) sweep_warp_kernel(const SweepArgs A) {
+__global__ void __launch_bounds__(WARPS_PER_CTA_LIGHT * 32, TileCfg<R>::LIGHT_CTAS) sweep_warp_kernel(const SweepArgs A) {
   const int64_t slot = (int64_t)blockIdx.x * WARPS_PER_CTA_LIGHT + (threadIdx.x >> 5);
+  __shared__ double part[WARPS_PER_CTA_LIGHT * TRIAL_TILE_DOUBLES(G)];
   if (slot >= A.n_units) return;
-  process_unit<G, R, 1, LOSS>(A, A.order[slot], nullptr);
+  process_unit<G, R, 1, LOSS, TileCfg<R>::DEPTH>(A, A.order[slot], nullptr, part);
 }
 
 // heavy units: one CTA (8 warps) per unit
 template <int G, int R, int LOSS>
-__global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32, 2) sweep_cta_kernel(const SweepArgs A) {
+__global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32, TileCfg<R>::HEAVY_CTAS) sweep_cta_kernel(const SweepArgs A) {
   __shared__ double red[WARPS_PER_CTA_HEAVY * (G * 2 * R + 1)];
-  process_unit<G, R, WARPS_PER_CTA_HEAVY, LOSS>(A, A.order[blockIdx.x], red);
+  __shared__ double part[WARPS_PER_CTA_HEAVY * TRIAL_TILE_DOUBLES(G)];
+  process_unit<G, R, WARPS_PER_CTA_HEAVY, LOSS, TileCfg<R>::DEPTH>(A, A.order[blockIdx.x], red, part);
 }
 
 // out[0] = sum(v[0..n)) in a fixed order (obj = sum(obj_by_col), proxgrad.jl:205)
