@@ -370,8 +370,9 @@ __device__ __forceinline__ void entry_pass(const SweepArgs& A, int64_t start, in
     j = ok ? jr : -1;
     a = ok ? ar : 0.0;
   };
-  struct Ent { int32_t j; double a; int code; double s, p1, p2; };
+  struct Ent { int32_t j; double a; int code; double s, p1, p2; uint32_t cs; };
   auto fetch = [&](uint32_t s, int32_t cj, double ca, double2 (&y)[R], Ent& e) {
+    e.cs = s & (G - 1);
     const int src = (int)(s & (G - 1)) * NGW + gq;
     e.j = __shfl_sync(FULLMASK, cj, src);
     e.a = __shfl_sync(FULLMASK, ca, src);
@@ -394,8 +395,10 @@ __device__ __forceinline__ void entry_pass(const SweepArgs& A, int64_t start, in
     const double dot = group_sum<G>(d0 + d1);
     double l, c;
     loss_eval<LOSS, GRAD>(e.code, e.s, e.p1, e.p2, dot, e.a, l, c);
+    // objective bookkeeping mirrors trial_pass bit for bit: one accumulator per chunk slot (here it lives
+    // in lane lg == step-in-chunk of the group), summed over chunks in order, then one fixed warp tree.
     const bool act = e.j >= 0;
-    obj += act ? l : 0.0;
+    obj += (act && lg == (int)e.cs) ? l : 0.0;
     if (GRAD) {
       c = act ? c : 0.0;
 #pragma unroll
@@ -428,6 +431,10 @@ __device__ __forceinline__ void entry_pass(const SweepArgs& A, int64_t start, in
       consume(y[u], e[u]);
     }
   }
+  // slot t = cs*NGW + gq was accumulated in lane gq*G + cs: bring it to lane t, then the same tree as trial_pass
+  obj = __shfl_sync(FULLMASK, obj, (lane % NGW) * G + lane / NGW);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) obj += __shfl_xor_sync(FULLMASK, obj, o);
 }
 
 // Line-search trial pass: objective only.  No gradient means the gathered column is dead once its
@@ -484,10 +491,18 @@ __device__ __forceinline__ double trial_pass(const SweepArgs& A, int64_t start, 
     buf[(cs * NGW + gq) * ROW + lg] = d0 + d1;
     if (cs == G - 1) {                              // chunk complete: lane l finishes entry l
       __syncwarp();
+      // same association as group_sum's xor butterfly, so a point evaluated by the gradient pass and by a
+      // trial pass yields identical bits (the reference's strict `<` relies on f(x) == f(x))
       const double* row = buf + lane * ROW;
-      double u = row[0];
+      double v[G];
 #pragma unroll
-      for (int i = 1; i < G; ++i) u += row[i];
+      for (int i = 0; i < G; ++i) v[i] = row[i];
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < o; ++i) v[i] += v[i + o];
+      }
+      const double u = v[0];
       int code = ucode;
       double ls = us, p1 = up1, p2 = up2;
       if (by_entry) {
@@ -520,41 +535,40 @@ __device__ __forceinline__ double trial_pass(const SweepArgs& A, int64_t start, 
   return obj;
 }
 
-// reduce (obj [, g]) over all groups of the unit: shuffles inside the warp, shared memory across warps
-template <int G, int R, int W, bool WITH_G>
-__device__ __forceinline__ void unit_reduce(double& obj, double2 (&g)[R], double* red, int lane, int warp, int lg) {
-  obj = cross_group_sum<G>(obj);
-  if (WITH_G) {
+// sum of the per-warp objective totals in a fixed order (W > 1); every thread gets the same bits
+template <int W>
+__device__ __forceinline__ double block_sum_obj(double obj, double* red, int lane, int warp) {
+  if (W == 1) return obj;
+  __syncthreads();
+  if (lane == 0) red[warp] = obj;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < W; ++w) t += red[w];
+  return t;
+}
+
+// reduce g over all groups of the unit: shuffles inside the warp, shared memory across warps
+template <int G, int R, int W>
+__device__ __forceinline__ void unit_reduce_g(double2 (&g)[R], double* red, int lane, int warp, int lg) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) { g[r].x = cross_group_sum<G>(g[r].x); g[r].y = cross_group_sum<G>(g[r].y); }
-  }
+  for (int r = 0; r < R; ++r) { g[r].x = cross_group_sum<G>(g[r].x); g[r].y = cross_group_sum<G>(g[r].y); }
   if (W > 1) {
-    constexpr int STRIDE = G * 2 * R + 1;
+    constexpr int STRIDE = G * 2 * R;
     __syncthreads();
     if (lane < G) {
-      if (WITH_G) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) { red[warp * STRIDE + (lg * R + r) * 2] = g[r].x; red[warp * STRIDE + (lg * R + r) * 2 + 1] = g[r].y; }
-      }
-      if (lane == 0) red[warp * STRIDE + G * 2 * R] = obj;
+      for (int r = 0; r < R; ++r) { red[warp * STRIDE + (lg * R + r) * 2] = g[r].x; red[warp * STRIDE + (lg * R + r) * 2 + 1] = g[r].y; }
     }
     __syncthreads();
-    double o = 0.0;
     double2 acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = make_double2(0.0, 0.0);
     for (int w = 0; w < W; ++w) {   // fixed order
-      o += red[w * STRIDE + G * 2 * R];
-      if (WITH_G) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) { acc[r].x += red[w * STRIDE + (lg * R + r) * 2]; acc[r].y += red[w * STRIDE + (lg * R + r) * 2 + 1]; }
-      }
+      for (int r = 0; r < R; ++r) { acc[r].x += red[w * STRIDE + (lg * R + r) * 2]; acc[r].y += red[w * STRIDE + (lg * R + r) * 2 + 1]; }
     }
-    obj = o;
-    if (WITH_G) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) g[r] = acc[r];
-    }
+    for (int r = 0; r < R; ++r) g[r] = acc[r];
   }
 }
 
@@ -596,7 +610,8 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
   double2 g[R];
   double obj_old;
   entry_pass<G, R, W, LOSS, true, DEPTH>(A, start, len, warp, lane, x, ucode, us, up1, up2, g, obj_old);
-  unit_reduce<G, R, W, true>(obj_old, g, red, lane, warp, lg);
+  obj_old = block_sum_obj<W>(obj_old, red, lane, warp);
+  unit_reduce_g<G, R, W>(g, red, lane, warp, lg);
   if (use_reg) obj_old += reg_eval<G, R>(rcode, rp, x, lg, k);
 
   double alpha = A.alpha[unit];
@@ -615,17 +630,11 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
       if constexpr (G <= 8) {                       // shared-memory transposed reduction (k <= 64)
         obj_new = trial_pass<G, R, W, LOSS, DEPTH>(A, start, len, warp, lane, xn, ucode, us, up1, up2,
                                                    part + (W == 1 ? (threadIdx.x >> 5) : warp) * TRIAL_TILE_DOUBLES(G));
-        if (W > 1) {                                // cross-warp total through shared memory, fixed order
-          __syncthreads();
-          if (lane == 0) red[warp] = obj_new;
-          __syncthreads();
-          obj_new = 0.0;
-          for (int w = 0; w < W; ++w) obj_new += red[w];
-        }
+        obj_new = block_sum_obj<W>(obj_new, red, lane, warp);
       } else {                                      // wide groups: shuffle-reduced pass
         double2 dummy[R];
         entry_pass<G, R, W, LOSS, false, DEPTH>(A, start, len, warp, lane, xn, ucode, us, up1, up2, dummy, obj_new);
-        unit_reduce<G, R, W, false>(obj_new, dummy, red, lane, warp, lg);
+        obj_new = block_sum_obj<W>(obj_new, red, lane, warp);
       }
       obj_new += reg_eval<G, R>(rcode, rp, xn, lg, k);
       ++ntrials;
