@@ -184,48 +184,78 @@ __device__ __forceinline__ double reg_eval(int code, const double* __restrict__ 
   const int base = code & GLRMB200_REG_BASE_MASK;
   const bool wrapped = code & (GLRMB200_REG_LASTENTRY1 | GLRMB200_REG_LASTENTRY_UNPENALIZED);
   const int kin = wrapped ? k - 1 : k;
-  double s1 = 0.0, s2 = 0.0, sabs = 0.0;
-  int neg = 0, nz = 0, ones = 0, other = 0, badlast = 0;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int i0 = 2 * (lg + G * r);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const double e = h ? v[r].y : v[r].x;
-      const int i = i0 + h;
-      if (i < kin) {
-        s1 += e; s2 += e * e; sabs += fabs(e);
-        neg += (e < 0.0); nz += (e != 0.0); ones += (e == 1.0); other += (e != 0.0 && e != 1.0);
-      }
-      if ((code & GLRMB200_REG_LASTENTRY1) && i == k - 1 && e != 1.0) badlast = 1;   // :171
-    }
+  // BODY is applied to every element the inner regularizer sees (index < kin); padded slots are skipped
+#define GLRM_EACH(BODY)                                                  \
+  _Pragma("unroll") for (int r = 0; r < R; ++r) {                        \
+    const int i0 = 2 * (lg + G * r);                                     \
+    { const double e = v[r].x; if (i0 < kin) { BODY; } }                  \
+    { const double e = v[r].y; if (i0 + 1 < kin) { BODY; } }              \
   }
   double res;
   switch (base) {
     case GLRMB200_REG_ZERO: res = 0.0; break;                                                   // :95
-    case GLRMB200_REG_QUAD: res = rp[0] * group_sum<G>(s2); break;                              // :58
-    case GLRMB200_REG_QUAD_CONSTRAINT: res = sqrt(group_sum<G>(s2)) > rp[0] + 1e-12 ? INFINITY : 0.0; break;  // :74
-    case GLRMB200_REG_ONE: res = rp[0] * group_sum<G>(sabs); break;                             // :88
-    case GLRMB200_REG_NONNEG: res = group_sum_i<G>(neg) ? INFINITY : 0.0; break;                // :105-112
+    case GLRMB200_REG_QUAD: {                                                                   // :58
+      double s2 = 0.0;
+      GLRM_EACH(s2 = fma(e, e, s2))
+      res = rp[0] * group_sum<G>(s2);
+    } break;
+    case GLRMB200_REG_QUAD_CONSTRAINT: {                                                        // :74
+      double s2 = 0.0;
+      GLRM_EACH(s2 = fma(e, e, s2))
+      res = sqrt(group_sum<G>(s2)) > rp[0] + 1e-12 ? INFINITY : 0.0;
+    } break;
+    case GLRMB200_REG_ONE: {                                                                    // :88
+      double sabs = 0.0;
+      GLRM_EACH(sabs += fabs(e))
+      res = rp[0] * group_sum<G>(sabs);
+    } break;
+    case GLRMB200_REG_NONNEG: {                                                                 // :105-112
+      int neg = 0;
+      GLRM_EACH(neg |= (e < 0.0))
+      res = group_sum_i<G>(neg) ? INFINITY : 0.0;
+    } break;
     case GLRMB200_REG_NONNEG_ONE: {                                                             // :129-136
+      int neg = 0;
+      double s1 = 0.0;
+      GLRM_EACH(neg |= (e < 0.0); s1 += e)
       const int n = group_sum_i<G>(neg);
       const double t = group_sum<G>(s1);
       res = n ? INFINITY : rp[0] * t;
     } break;
-    case GLRMB200_REG_ONE_SPARSE: res = group_sum_i<G>(nz) > 1 ? INFINITY : 0.0; break;         // :239-253
-    case GLRMB200_REG_KSPARSE: res = group_sum_i<G>(nz) > (int)rp[0] ? INFINITY : 0.0; break;   // :261-276
+    case GLRMB200_REG_ONE_SPARSE:                                                               // :239-253
+    case GLRMB200_REG_KSPARSE: {                                                                // :261-276
+      int nz = 0;
+      GLRM_EACH(nz += (e != 0.0))
+      const int lim = base == GLRMB200_REG_ONE_SPARSE ? 1 : (int)rp[0];
+      res = group_sum_i<G>(nz) > lim ? INFINITY : 0.0;
+    } break;
     case GLRMB200_REG_UNIT_ONE_SPARSE: {                                                        // :300-316
+      int ones = 0, other = 0;
+      GLRM_EACH(ones += (e == 1.0); other |= (e != 0.0 && e != 1.0))
       const int o = group_sum_i<G>(ones), x = group_sum_i<G>(other);
       res = (x || o > 1) ? INFINITY : 0.0;
     } break;
     case GLRMB200_REG_SIMPLEX: {                                                                // :338-346
+      int neg = 0;
+      double s1 = 0.0;
+      GLRM_EACH(neg |= (e < 0.0); s1 += e)
       const double t = group_sum<G>(s1);
       const int n = group_sum_i<G>(neg);
       res = (fabs(t - 1.0) > 1e-12 || n) ? INFINITY : 0.0;
     } break;
     default: res = NAN; break;
   }
-  if (code & GLRMB200_REG_LASTENTRY1) { if (group_sum_i<G>(badlast)) res = INFINITY; }
+#undef GLRM_EACH
+  if (code & GLRMB200_REG_LASTENTRY1) {                                                         // :171
+    int badlast = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i0 = 2 * (lg + G * r);
+      if (i0 == k - 1 && v[r].x != 1.0) badlast = 1;
+      if (i0 + 1 == k - 1 && v[r].y != 1.0) badlast = 1;
+    }
+    if (group_sum_i<G>(badlast)) res = INFINITY;
+  }
   return res;
 }
 
@@ -409,16 +439,18 @@ __device__ __forceinline__ void entry_pass(const SweepArgs& A, int64_t start, in
   // (in-flight entries per SM = warps x groups x (D-1); with ~600-cycle loaded L2 latency this, not
   // instruction issue, bounds the sweep — see DESIGN.md "Little's law").
   constexpr int D = PIPE_DEPTH;
-  int32_t fj, nj;            // (idx) of the chunk the fetch stream is in, and of the following chunk
-  double fa, na;
+  int32_t fj, nj, mj;        // (idx, val) of the chunk the fetch stream is in and of the two chunks after it:
+  double fa, na, ma;         // the index stream comes from DRAM, so it is requested two chunks (64 entries) early
   load_chunk(0, fj, fa);
   load_chunk(1, nj, na);
+  load_chunk(2, mj, ma);
   double2 y[D][R];
   Ent e[D];
   auto fetch_step = [&](uint32_t f, double2 (&yy)[R], Ent& ee) {
     if (f != 0 && (f & (G - 1)) == 0) {           // the fetch stream enters the next chunk
       fj = nj; fa = na;
-      load_chunk(f / G + 1, nj, na);
+      nj = mj; na = ma;
+      load_chunk(f / G + 2, mj, ma);
     }
     fetch(f, fj, fa, yy, ee);
   };
@@ -469,10 +501,11 @@ __device__ __forceinline__ double trial_pass(const SweepArgs& A, int64_t start, 
     j = ok ? jr : -1;
     a = ok ? ar : 0.0;
   };
-  int32_t cj, nj;   // chunk being consumed / next chunk: lane l holds entry l of the chunk
-  double ca, na;
+  int32_t cj, nj, mj;   // chunk being consumed and the two after it: lane l holds entry l of the chunk
+  double ca, na, ma;
   load_chunk(0, cj, ca);
   load_chunk(1, nj, na);
+  load_chunk(2, mj, ma);
   uint32_t cons_chunk = 0;
   auto fetch = [&](uint32_t f, double2 (&y)[R]) {
     const int32_t sj = (f / G == cons_chunk) ? cj : nj;       // the fetch stream runs < G steps ahead
@@ -515,8 +548,9 @@ __device__ __forceinline__ double trial_pass(const SweepArgs& A, int64_t start, 
       loss_eval<LOSS, false>(code, ls, p1, p2, u, ca, l, cdummy);
       obj += (cj >= 0) ? l : 0.0;
       cj = nj; ca = na;                             // consumption moves to the next chunk
+      nj = mj; na = ma;
       ++cons_chunk;
-      load_chunk(cons_chunk + 1, nj, na);
+      load_chunk(cons_chunk + 2, mj, ma);
     }
   };
   double2 y[D][R];
@@ -572,8 +606,23 @@ __device__ __forceinline__ void unit_reduce_g(double2 (&g)[R], double* red, int 
   }
 }
 
+// pipeline depth / residency per tile: DEPTH gather buffers (R double2 each) in the gradient pass, TRIAL_DEPTH
+// in the trial passes (x and g live in shared memory there, so the registers go to in-flight gathers)
+#ifndef GLRM_PIPE_DEPTH
+#define GLRM_PIPE_DEPTH 2
+#endif
+#ifndef GLRM_TRIAL_DEPTH
+#define GLRM_TRIAL_DEPTH 4
+#endif
+template <int R> struct TileCfg {
+  static constexpr int DEPTH = GLRM_PIPE_DEPTH;
+  static constexpr int TRIAL_DEPTH = GLRM_TRIAL_DEPTH;
+  static constexpr int LIGHT_CTAS = 4;
+  static constexpr int HEAVY_CTAS = 2;
+};
+
 template <int G, int R, int W, int LOSS, int DEPTH>
-__device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, double* red, double* part) {
+__device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, double* red, double* part, double* xg) {
   constexpr int NGW = 32 / G;
   const int lane = threadIdx.x & 31;
   const int warp = (W == 1) ? 0 : (threadIdx.x >> 5);
@@ -617,19 +666,32 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
   double alpha = A.alpha[unit];
   double obj_rec = obj_old;
   int ntrials = 0;
-  bool accepted = false;
-  if (!(A.flags & FLAG_EVAL_ONLY)) {
+  if (!(A.flags & FLAG_EVAL_ONLY) && alpha > A.min_stepsize) {
+    // x and g are only needed to form trial points: park them in shared memory so the trial passes can
+    // spend the registers on a deeper gather pipeline
+    double2* xs = reinterpret_cast<double2*>(xg);
+    double2* gs = xs + G * R;
+    if (W > 1) __syncthreads();
+    if (gid == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) { xs[r * G + lg] = x[r]; gs[r * G + lg] = g[r]; }
+    }
+    if (W > 1) __syncthreads(); else __syncwarp();
     const double l1 = (double)(len + 1);                                 // proxgrad.jl:134
     while (alpha > A.min_stepsize) {                                     // :136
       const double stepsize = alpha / l1;                                // :137
       double2 xn[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) { xn[r].x = fma(-stepsize, g[r].x, x[r].x); xn[r].y = fma(-stepsize, g[r].y, x[r].y); }  // :140
+      for (int r = 0; r < R; ++r) {
+        const double2 xr = xs[r * G + lg], gr = gs[r * G + lg];
+        xn[r].x = fma(-stepsize, gr.x, xr.x); xn[r].y = fma(-stepsize, gr.y, xr.y);                   // :140
+      }
       reg_prox<G, R>(rcode, rp, xn, lg, k, stepsize);                    // :142
       double obj_new;
       if constexpr (G <= 8) {                       // shared-memory transposed reduction (k <= 64)
-        obj_new = trial_pass<G, R, W, LOSS, DEPTH>(A, start, len, warp, lane, xn, ucode, us, up1, up2,
-                                                   part + (W == 1 ? (threadIdx.x >> 5) : warp) * TRIAL_TILE_DOUBLES(G));
+        obj_new = trial_pass<G, R, W, LOSS, TileCfg<R>::TRIAL_DEPTH>(
+            A, start, len, warp, lane, xn, ucode, us, up1, up2,
+            part + (W == 1 ? (threadIdx.x >> 5) : warp) * TRIAL_TILE_DOUBLES(G));
         obj_new = block_sum_obj<W>(obj_new, red, lane, warp);
       } else {                                      // wide groups: shuffle-reduced pass
         double2 dummy[R];
@@ -639,11 +701,12 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
       obj_new += reg_eval<G, R>(rcode, rp, xn, lg, k);
       ++ntrials;
       if (obj_new < obj_old) {                                           // :143 (strict; NaN rejects)
+        if (gid == 0) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) x[r] = xn[r];                        // :144
+          for (int r = 0; r < R; ++r) *reinterpret_cast<double2*>(own + 2 * (lg + G * r)) = xn[r];   // :144
+        }
         alpha *= 1.05;                                                   // :145
         obj_rec = obj_new;                                               // :190
-        accepted = true;
         break;
       } else {
         alpha *= .7;                                                     // :149
@@ -651,40 +714,24 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
       }
     }
   }
-  if (gid == 0) {
-    if (accepted) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) *reinterpret_cast<double2*>(own + 2 * (lg + G * r)) = x[r];
-    }
-    if (lg == 0) {
-      A.alpha[unit] = alpha;
-      A.obj_out[unit] = obj_rec;
-      if (ntrials && A.trial_counter) atomicAdd(A.trial_counter, (unsigned long long)ntrials);
-    }
+  if (gid == 0 && lg == 0) {
+    A.alpha[unit] = alpha;
+    A.obj_out[unit] = obj_rec;
+    if (ntrials && A.trial_counter) atomicAdd(A.trial_counter, (unsigned long long)ntrials);
   }
 }
 
 constexpr int WARPS_PER_CTA_LIGHT = 4;
 constexpr int WARPS_PER_CTA_HEAVY = 8;
 
-// pipeline depth / residency per tile: D gather buffers of R double2 each; 12 warps per SM for the
-// wide tiles (<= 168 registers), 16 for the narrow ones
-#ifndef GLRM_PIPE_DEPTH
-#define GLRM_PIPE_DEPTH 2
-#endif
-template <int R> struct TileCfg {
-  static constexpr int DEPTH = GLRM_PIPE_DEPTH;
-  static constexpr int LIGHT_CTAS = (R >= 3 && GLRM_PIPE_DEPTH > 2) ? 3 : 4;
-  static constexpr int HEAVY_CTAS = (R >= 3 && GLRM_PIPE_DEPTH > 2) ? 1 : 2;
-};
-
 // light units: one warp per unit, no block-level synchronisation
 template <int G, int R, int LOSS>
 __global__ void __launch_bounds__(WARPS_PER_CTA_LIGHT * 32, TileCfg<R>::LIGHT_CTAS) sweep_warp_kernel(const SweepArgs A) {
   const int64_t slot = (int64_t)blockIdx.x * WARPS_PER_CTA_LIGHT + (threadIdx.x >> 5);
   __shared__ double part[WARPS_PER_CTA_LIGHT * TRIAL_TILE_DOUBLES(G)];
+  __shared__ __align__(16) double xg[WARPS_PER_CTA_LIGHT * 4 * G * R];
   if (slot >= A.n_units) return;
-  process_unit<G, R, 1, LOSS, TileCfg<R>::DEPTH>(A, A.order[slot], nullptr, part);
+  process_unit<G, R, 1, LOSS, TileCfg<R>::DEPTH>(A, A.order[slot], nullptr, part, xg + (threadIdx.x >> 5) * 4 * G * R);
 }
 
 // heavy units: one CTA (8 warps) per unit
@@ -692,7 +739,8 @@ template <int G, int R, int LOSS>
 __global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32, TileCfg<R>::HEAVY_CTAS) sweep_cta_kernel(const SweepArgs A) {
   __shared__ double red[WARPS_PER_CTA_HEAVY * (G * 2 * R + 1)];
   __shared__ double part[WARPS_PER_CTA_HEAVY * TRIAL_TILE_DOUBLES(G)];
-  process_unit<G, R, WARPS_PER_CTA_HEAVY, LOSS, TileCfg<R>::DEPTH>(A, A.order[blockIdx.x], red, part);
+  __shared__ __align__(16) double xg[4 * G * R];
+  process_unit<G, R, WARPS_PER_CTA_HEAVY, LOSS, TileCfg<R>::DEPTH>(A, A.order[blockIdx.x], red, part, xg);
 }
 
 // out[0] = sum(v[0..n)) in a fixed order (obj = sum(obj_by_col), proxgrad.jl:205)
