@@ -42,6 +42,8 @@ struct SweepArgs {
   double* own;            // factor being updated   [units_total * kp]
   const double* opp;      // factor being gathered  [opp_total * kp]
   int32_t stride;         // doubles between factor columns == 2*G*R of the tile (zero-padded past k)
+  int32_t last_lanes;     // lanes of a group whose LAST slot holds real data (ceil(k/2) - G*(R-1)); the others
+                          // re-read lane 0's 16 bytes there (same sector: no traffic) against a zero x slot
   int32_t k;              // rank
   const int32_t* loss_code;   // [n] per feature
   const double* loss_param;   // [n * 8]
@@ -385,6 +387,7 @@ __device__ __forceinline__ void entry_pass(const SweepArgs& A, int64_t start, in
   const uint32_t my_chunks = (nchunks + W - 1) / W;   // same trip count in every warp of the unit
   const uint32_t nsteps = my_chunks * G;
   const char* opp_lane = reinterpret_cast<const char*>(A.opp + 2 * lg);
+  const char* opp_last = reinterpret_cast<const char*>(A.opp + 2 * ((lg < A.last_lanes ? lg : 0) + G * (R - 1)));
   const int stride_bytes = A.stride * 8;
   obj = 0.0;
   if (GRAD) {
@@ -407,10 +410,12 @@ __device__ __forceinline__ void entry_pass(const SweepArgs& A, int64_t start, in
     e.j = __shfl_sync(FULLMASK, cj, src);
     e.a = __shfl_sync(FULLMASK, ca, src);
     const int32_t jj = e.j < 0 ? 0 : e.j;          // inactive slots read column 0 and are masked below
-    // stride == 2*G*R: every lane's slot exists (zeros past k), so the R loads carry immediate offsets
+    // R unconditional 16-byte loads per lane with immediate offsets; in the last slot only the lanes that
+    // hold real elements read their own 16 bytes
     const char* yp = opp_lane + (int64_t)jj * stride_bytes;
 #pragma unroll
-    for (int r = 0; r < R; ++r) y[r] = __ldg(reinterpret_cast<const double2*>(yp + r * G * 16));
+    for (int r = 0; r < R - 1; ++r) y[r] = __ldg(reinterpret_cast<const double2*>(yp + r * G * 16));
+    y[R - 1] = __ldg(reinterpret_cast<const double2*>(opp_last + (int64_t)jj * stride_bytes));
     e.code = ucode; e.s = us; e.p1 = up1; e.p2 = up2;
     if (by_entry) {
       e.code = __ldg(A.loss_code + jj);
@@ -490,6 +495,7 @@ __device__ __forceinline__ double trial_pass(const SweepArgs& A, int64_t start, 
   const uint32_t my_chunks = (nchunks + W - 1) / W;
   const uint32_t nsteps = my_chunks * G;
   const char* opp_lane = reinterpret_cast<const char*>(A.opp + 2 * lg);
+  const char* opp_last = reinterpret_cast<const char*>(A.opp + 2 * ((lg < A.last_lanes ? lg : 0) + G * (R - 1)));
   const int stride_bytes = A.stride * 8;
   double obj = 0.0;
   auto load_chunk = [&](uint32_t ci, int32_t& j, double& a) {
@@ -511,9 +517,11 @@ __device__ __forceinline__ double trial_pass(const SweepArgs& A, int64_t start, 
     const int32_t sj = (f / G == cons_chunk) ? cj : nj;       // the fetch stream runs < G steps ahead
     const int src = (int)(f & (G - 1)) * NGW + gq;
     const int32_t j = __shfl_sync(FULLMASK, sj, src);
-    const char* yp = opp_lane + (int64_t)(j < 0 ? 0 : j) * stride_bytes;
+    const int64_t joff = (int64_t)(j < 0 ? 0 : j) * stride_bytes;
+    const char* yp = opp_lane + joff;
 #pragma unroll
-    for (int r = 0; r < R; ++r) y[r] = __ldg(reinterpret_cast<const double2*>(yp + r * G * 16));
+    for (int r = 0; r < R - 1; ++r) y[r] = __ldg(reinterpret_cast<const double2*>(yp + r * G * 16));
+    y[R - 1] = __ldg(reinterpret_cast<const double2*>(opp_last + joff));
   };
   auto consume = [&](uint32_t c, const double2 (&y)[R]) {
     double d0 = 0.0, d1 = 0.0;
@@ -675,6 +683,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
     if (gid == 0) {
 #pragma unroll
       for (int r = 0; r < R; ++r) { xs[r * G + lg] = x[r]; gs[r * G + lg] = g[r]; }
+      if (lg >= A.last_lanes) gs[(R - 1) * G + lg] = make_double2(0.0, 0.0);   // duplicates gathered against a zero x slot
     }
     if (W > 1) __syncthreads(); else __syncwarp();
     const double l1 = (double)(len + 1);                                 // proxgrad.jl:134

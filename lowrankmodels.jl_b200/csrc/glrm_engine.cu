@@ -286,6 +286,7 @@ static SweepArgs make_args(const glrmb200_engine* E, bool x_side, int flags, dou
   A.own = x_side ? E->d_X : E->d_Y;
   A.opp = x_side ? E->d_Y : E->d_X;
   A.stride = E->stride;
+  A.last_lanes = E->kp / 2 - E->tile_g * (E->tile_r - 1);
   A.k = (int)E->k;
   A.loss_code = E->d_loss_code;
   A.loss_param = E->d_loss_param;
