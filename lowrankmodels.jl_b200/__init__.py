@@ -18,6 +18,6 @@ from .regularizers import (KSparseConstraint, MNLOrdinalReg, NonNegConstraint, N
                            fixed_last_latent_features, fixed_latent_features, lastentry1,
                            lastentry_unpenalized)
 from .encode import encode_params, encode_problem
-from . import _abi, synth
+from . import _abi, distributed, synth
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -149,18 +149,6 @@ static int loss_dim(int code, const double* p) {
   }
 }
 
-static int validate_label(int code, const double* p, double a) {
-  if (a != a) return GLRMB200_E_NAN;
-  switch (code) {
-    case GLRMB200_LOSS_LOGISTIC: case GLRMB200_LOSS_WEIGHTED_HINGE:
-      return (a == 1.0 || a == 0.0 || a == -1.0) ? 0 : GLRMB200_E_LABEL;
-    case GLRMB200_LOSS_MULTINOMIAL: case GLRMB200_LOSS_OVA: case GLRMB200_LOSS_BVS:
-    case GLRMB200_LOSS_ORDISTIC: case GLRMB200_LOSS_MULTINOMIAL_ORDINAL:
-      return (a == std::floor(a) && a >= 1.0 && a <= p[2]) ? 0 : GLRMB200_E_LABEL;
-    default: return 0;
-  }
-}
-
 extern "C" int glrmb200_plan_shards(const int64_t* ptr, int64_t count, int32_t nranks, int64_t* bounds) {
   // contiguous shards balanced by observation count (ptr == NULL: by unit count)
   if (nranks < 1 || count < 0 || !bounds) return fail(GLRMB200_E_INVALID, "plan_shards: bad arguments");
@@ -391,14 +379,6 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   C.bounds.assign((size_t)E->nranks + 1, 0);
   if (E->obs_full) {
     if (!P->dense_A) return fail(GLRMB200_E_INVALID, "obs_full needs dense_A");
-    for (int64_t f = 0; f < n; ++f) {
-      const double* p = P->loss_param + f * GLRMB200_LOSS_NPARAM;
-      for (int64_t e = 0; e < m; ++e) {
-        const int v = validate_label(P->loss_code[f], p, P->dense_A[f * m + e]);
-        if (v == GLRMB200_E_NAN) return fail(v, "Observed value in entry (%lld, %lld) is NaN.", (long long)e + 1, (long long)f + 1);
-        if (v) return fail(v, "entry (%lld, %lld): label %g is outside the domain of loss code %d", (long long)e + 1, (long long)f + 1, P->dense_A[f * m + e], P->loss_code[f]);
-      }
-    }
     R.full_len = n; C.full_len = m;
     E->nnz_rows_total = m * n;
     glrmb200_plan_shards(nullptr, m, E->nranks, R.bounds.data());
@@ -408,27 +388,11 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
     const int64_t nr = P->row_ptr[m], nc = P->col_ptr[n];
     if (P->row_ptr[0] != 0 || P->col_ptr[0] != 0) return fail(GLRMB200_E_INVALID, "ptr arrays must start at 0");
     if ((nr && (!P->row_idx || !P->row_val)) || (nc && (!P->col_idx || !P->col_val))) return fail(GLRMB200_E_INVALID, "observation arrays missing");
-    for (int64_t e = 0; e < m; ++e) {
+    for (int64_t e = 0; e < m; ++e)
       if (P->row_ptr[e + 1] < P->row_ptr[e]) return fail(GLRMB200_E_INVALID, "row_ptr not monotone");
-      for (int64_t q = P->row_ptr[e]; q < P->row_ptr[e + 1]; ++q) {
-        const int32_t f = P->row_idx[q];
-        if (f < 0 || f >= n) return fail(GLRMB200_E_INVALID, "row_idx[%lld] = %d out of range", (long long)q, f);
-        const int v = validate_label(P->loss_code[f], P->loss_param + (int64_t)f * GLRMB200_LOSS_NPARAM, P->row_val[q]);
-        if (v == GLRMB200_E_NAN) return fail(v, "Observed value in entry (%lld, %d) is NaN.", (long long)e + 1, f + 1);
-        if (v) return fail(v, "entry (%lld, %d): label %g is outside the domain of loss code %d", (long long)e + 1, f + 1, P->row_val[q], P->loss_code[f]);
-      }
-    }
-    for (int64_t f = 0; f < n; ++f) {
+    for (int64_t f = 0; f < n; ++f)
       if (P->col_ptr[f + 1] < P->col_ptr[f]) return fail(GLRMB200_E_INVALID, "col_ptr not monotone");
-      const double* p = P->loss_param + f * GLRMB200_LOSS_NPARAM;
-      for (int64_t q = P->col_ptr[f]; q < P->col_ptr[f + 1]; ++q) {
-        const int32_t e = P->col_idx[q];
-        if (e < 0 || e >= m) return fail(GLRMB200_E_INVALID, "col_idx[%lld] = %d out of range", (long long)q, e);
-        const int v = validate_label(P->loss_code[f], p, P->col_val[q]);
-        if (v == GLRMB200_E_NAN) return fail(v, "Observed value in entry (%d, %lld) is NaN.", e + 1, (long long)f + 1);
-        if (v) return fail(v, "entry (%d, %lld): label %g is outside the domain of loss code %d", e + 1, (long long)f + 1, P->col_val[q], P->loss_code[f]);
-      }
-    }
+    // index bounds, NaN and label domains are checked on the device after the upload (validate_*_kernel)
     E->nnz_rows_total = nr;
     glrmb200_plan_shards(P->row_ptr, m, E->nranks, R.bounds.data());
     glrmb200_plan_shards(P->col_ptr, n, E->nranks, C.bounds.data());
@@ -479,6 +443,25 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
     }
     if ((rc = build_schedule(R, nullptr, E->heavy_threshold))) return rc;
     if ((rc = build_schedule(C, nullptr, E->heavy_threshold))) return rc;
+    {
+      unsigned long long* d_bad = nullptr;
+      CUDA_OK(cudaMalloc((void**)&d_bad, sizeof(unsigned long long)));
+      CUDA_OK(cudaMemset(d_bad, 0xff, sizeof(unsigned long long)));
+      const int64_t total = C.nnz_local;
+      if (total > 0) validate_dense_kernel<<<(unsigned)((total + 255) / 256), 256, 0, E->stream>>>(C.d_val, total, m, E->d_loss_code + C.begin, E->d_loss_param + C.begin * GLRMB200_LOSS_NPARAM, d_bad);
+      CUDA_OK(cudaGetLastError());
+      unsigned long long bad = 0;
+      CUDA_OK(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
+      CUDA_OK(cudaStreamSynchronize(E->stream));
+      cudaFree(d_bad);
+      if (bad != ~0ULL) {
+        const int kind = -(int)(bad & 15ULL);
+        const int64_t pos = (int64_t)(bad >> 4);
+        const int64_t f = C.begin + pos / m, e = pos % m;
+        if (kind == GLRMB200_E_NAN) return fail(kind, "Observed value in entry (%lld, %lld) is NaN.", (long long)e + 1, (long long)f + 1);
+        return fail(kind, "entry (%lld, %lld): label %g is outside the domain of loss code %d", (long long)e + 1, (long long)f + 1, P->dense_A[f * m + e], P->loss_code[f]);
+      }
+    }
   } else {
     auto up_side = [&](Side& S, const int64_t* ptr, const int32_t* idx, const double* val) -> int {
       const int64_t cnt = S.end - S.begin, q0 = ptr[S.begin], q1 = ptr[S.end];
@@ -493,6 +476,32 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
     };
     if ((rc = up_side(R, P->row_ptr, P->row_idx, P->row_val))) return rc;
     if ((rc = up_side(C, P->col_ptr, P->col_idx, P->col_val))) return rc;
+    unsigned long long* d_bad = nullptr;
+    CUDA_OK(cudaMalloc((void**)&d_bad, 2 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMemset(d_bad, 0xff, 2 * sizeof(unsigned long long)));
+    if (R.nnz_local > 0)
+      validate_rows_kernel<<<(unsigned)((R.nnz_local + 255) / 256), 256, 0, E->stream>>>(R.d_idx, R.d_val, R.nnz_local, n, E->d_loss_code, E->d_loss_param, d_bad);
+    if (C.end > C.begin)
+      validate_cols_kernel<<<(unsigned)((C.end - C.begin + 7) / 8), 256, 0, E->stream>>>(C.d_ptr, C.d_idx, C.d_val, C.end - C.begin, C.begin, m, E->d_loss_code, E->d_loss_param, d_bad + 1);
+    CUDA_OK(cudaGetLastError());
+    unsigned long long bad[2] = {0, 0};
+    CUDA_OK(cudaMemcpyAsync(bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
+    CUDA_OK(cudaStreamSynchronize(E->stream));
+    cudaFree(d_bad);
+    for (int side = 0; side < 2; ++side) {
+      if (bad[side] == ~0ULL) continue;
+      const int kind = -(int)(bad[side] & 15ULL);
+      const Side& S = side == 0 ? R : C;
+      const int64_t* ptr = side == 0 ? P->row_ptr : P->col_ptr;
+      const int64_t q = ptr[S.begin] + (int64_t)(bad[side] >> 4);
+      const int64_t unit = (std::upper_bound(ptr, ptr + (side == 0 ? m : n) + 1, q) - ptr) - 1;
+      const int64_t other = side == 0 ? P->row_idx[q] : P->col_idx[q];
+      const int64_t e = side == 0 ? unit : other, f = side == 0 ? other : unit;
+      const double v = side == 0 ? P->row_val[q] : P->col_val[q];
+      if (kind == GLRMB200_E_INVALID) return fail(kind, "%s[%lld] = %lld out of range", side == 0 ? "row_idx" : "col_idx", (long long)q, (long long)other);
+      if (kind == GLRMB200_E_NAN) return fail(kind, "Observed value in entry (%lld, %lld) is NaN.", (long long)e + 1, (long long)f + 1);
+      return fail(kind, "entry (%lld, %lld): label %g is outside the domain of loss code %d", (long long)e + 1, (long long)f + 1, v, P->loss_code[f]);
+    }
   }
 
   CUDA_OK(cudaMalloc((void**)&E->d_X, (size_t)m * E->stride * sizeof(double)));

@@ -1,0 +1,54 @@
+"""Host-side plumbing for N > 1 (one process per GPU).  torch.distributed is used only for rendezvous:
+broadcasting NCCL's unique id and host-side barriers / reductions of timings; the data-path exchange
+(one all-gather of the freshly updated factor per half-iteration) runs inside the
+engine over NCCL (csrc/glrm_engine.cu: allgather_units)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+
+
+def plan_shards(ptr, count, nranks):
+    """Contiguous unit ranges balanced by observation count (C ABI glrmb200_plan_shards; host-only).
+    ptr: int64 array [count+1] or None.  Returns int64 bounds [nranks+1]."""
+    b = np.zeros(nranks + 1, dtype=np.int64)
+    p = None if ptr is None else np.ascontiguousarray(ptr, dtype=np.int64)
+    _abi.check(_abi.lib().glrmb200_plan_shards(_abi.i64ptr(p) if p is not None else None, int(count), int(nranks),
+                                               _abi.i64ptr(b)))
+    return b
+
+
+def shard_bounds(ep, nranks):
+    """(row_bounds, col_bounds) for an EncodedProblem, exactly as glrmb200_create computes them."""
+    s = ep.struct
+    if s.obs_full:
+        return plan_shards(None, s.m, nranks), plan_shards(None, s.n, nranks)
+    return plan_shards(ep.keep["row_ptr"], s.m, nranks), plan_shards(ep.keep["col_ptr"], s.n, nranks)
+
+
+def broadcast_unique_id(dist, rank, make_id):
+    """Rank 0 creates NCCL's 128-byte unique id, every rank receives it (any torch.distributed backend)."""
+    box = [make_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    assert isinstance(box[0], (bytes, bytearray)) and len(box[0]) == 128
+    return bytes(box[0])
+
+
+def allgather_columns(dist, mat, bounds, elems_per_unit=1):
+    """In-place all-gather of a column-major (k, units) array whose unit ranges [bounds[r], bounds[r+1]) are
+    owned by rank r — the host-side twin of the engine's allgather_units (used by the CPU/gloo tests)."""
+    import torch
+    world = len(bounds) - 1
+    for r in range(world):
+        lo, hi = int(bounds[r]) * elems_per_unit, int(bounds[r + 1]) * elems_per_unit
+        if hi > lo:
+            t = torch.from_numpy(np.ascontiguousarray(mat[..., lo:hi].T if mat.ndim == 2 else mat[lo:hi]))
+            dist.broadcast(t, src=r)
+            if mat.ndim == 2:
+                mat[:, lo:hi] = t.numpy().T
+            else:
+                mat[lo:hi] = t.numpy()
+    return mat

@@ -858,6 +858,95 @@ int oracle_fit(const glrmb200_problem* P, const glrmb200_params* prm, double* X,
   return err;
 }
 
+/* One half-sweep over the units [begin, end) only (sparse-evaluated form): which = 0 updates rows of X
+ * (proxgrad.jl:118-156), which = 1 updates columns of Y (:162-201).  alpha is alpharow / alphacol (in/out,
+ * full length), obj_by_unit receives obj_by_row / obj_by_col for the touched units.  Used by the world_size-2
+ * CPU tests to show that "each rank sweeps its shard, then all-gather" reproduces the unsharded sweep. */
+int oracle_half_sweep(const glrmb200_problem* P, const glrmb200_params* prm, double* X, double* Y,
+                      double* alpha, int32_t which, int64_t begin, int64_t end, double* obj_by_unit) {
+  view_t V;
+  if (view_init(&V, P)) return 4;
+  const int64_t k = V.k;
+  int err = 0;
+  int maxD = 1;
+  for (int64_t f = 0; f < V.n; ++f) if (V.dim[f] > maxD) maxD = V.dim[f];
+  double* g = (double*)malloc(sizeof(double) * (size_t)(k * maxD));
+  double* nw = (double*)malloc(sizeof(double) * (size_t)(k * maxD));
+  double xy_dummy = 0;
+  for (int64_t u = begin; u < end; ++u) {
+    if (which == 0) {
+      const int64_t e = u;
+      double* xe = X + e * k;
+      for (int64_t r = 0; r < k; ++r) g[r] = 0.0;
+      const int64_t len = row_len(&V, e);
+      for (int64_t t = 0; t < len; ++t) {
+        int64_t f; double a;
+        row_entry(&V, e, t, &f, &a);
+        const int D = V.dim[f];
+        double uu[ORACLE_MAX_D], cg[ORACLE_MAX_D];
+        for (int c = 0; c < D; ++c) uu[c] = dotk(xe, Y + (V.ystart[f] + c) * k, k);
+        loss_grad(P->loss_code[f], P->loss_param + f * GLRMB200_LOSS_NPARAM, uu, D, a, cg, &err);
+        for (int c = 0; c < D; ++c) for (int64_t r = 0; r < k; ++r) g[r] += cg[c] * Y[(V.ystart[f] + c) * k + r];
+      }
+      const double l = (double)(len + 1);
+      const double obj_old = row_objective(&V, e, xe, Y, 0, &xy_dummy, &err);
+      obj_by_unit[e] = obj_old;
+      memcpy(nw, xe, sizeof(double) * (size_t)k);
+      while (alpha[e] > prm->min_stepsize) {
+        const double stepsize = alpha[e] / l;
+        for (int64_t r = 0; r < k; ++r) nw[r] += -stepsize * g[r];
+        reg_prox(*rx_code(&V, e), rx_par(&V, e), nw, k, 1, stepsize);
+        if (row_objective(&V, e, nw, Y, 0, &xy_dummy, &err) < obj_old) {
+          memcpy(xe, nw, sizeof(double) * (size_t)k);
+          alpha[e] *= 1.05;
+          break;
+        } else {
+          memcpy(nw, xe, sizeof(double) * (size_t)k);
+          alpha[e] *= .7;
+          if (alpha[e] < prm->min_stepsize) { alpha[e] = prm->min_stepsize * 1.1; break; }
+        }
+      }
+    } else {
+      const int64_t f = u;
+      const int D = V.dim[f];
+      double* yf = Y + V.ystart[f] * k;
+      for (int64_t r = 0; r < k * D; ++r) g[r] = 0.0;
+      const int64_t len = col_len(&V, f);
+      for (int64_t t = 0; t < len; ++t) {
+        int64_t e; double a;
+        col_entry(&V, f, t, &e, &a);
+        const double* xe = X + e * k;
+        double uu[ORACLE_MAX_D], cg[ORACLE_MAX_D];
+        for (int c = 0; c < D; ++c) uu[c] = dotk(xe, yf + c * k, k);
+        loss_grad(P->loss_code[f], P->loss_param + f * GLRMB200_LOSS_NPARAM, uu, D, a, cg, &err);
+        for (int c = 0; c < D; ++c) for (int64_t r = 0; r < k; ++r) g[c * k + r] += cg[c] * xe[r];
+      }
+      const double l = (double)(len + 1);
+      obj_by_unit[f] = col_objective(&V, f, yf, X, 0, &xy_dummy, &err);
+      memcpy(nw, yf, sizeof(double) * (size_t)(k * D));
+      while (alpha[f] > prm->min_stepsize) {
+        const double stepsize = alpha[f] / l;
+        for (int64_t r = 0; r < k * D; ++r) nw[r] += -stepsize * g[r];
+        reg_prox(*ry_code(&V, f), ry_par(&V, f), nw, k, D, stepsize);
+        const double new_obj = col_objective(&V, f, nw, X, 0, &xy_dummy, &err);
+        if (new_obj < obj_by_unit[f]) {
+          memcpy(yf, nw, sizeof(double) * (size_t)(k * D));
+          alpha[f] *= 1.05;
+          obj_by_unit[f] = new_obj;
+          break;
+        } else {
+          memcpy(nw, yf, sizeof(double) * (size_t)(k * D));
+          alpha[f] *= .7;
+          if (alpha[f] < prm->min_stepsize) { alpha[f] = prm->min_stepsize * 1.1; break; }
+        }
+      }
+    }
+  }
+  free(g); free(nw);
+  view_free(&V);
+  return err;
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

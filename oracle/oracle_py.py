@@ -40,6 +40,8 @@ def lib():
                                  C.POINTER(C.c_int32), C.c_int32, C.c_int32, _dp, _dp,
                                  C.POINTER(C.c_int64)]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_half_sweep.restype = C.c_int
+        L.oracle_half_sweep.argtypes = [C.c_void_p, C.c_void_p, _dp, _dp, _dp, C.c_int32, C.c_int64, C.c_int64, _dp]
         _lib = L
     return _lib
 
@@ -112,3 +114,11 @@ def fit(ep, params_struct, X, Y, mode=1, nthreads=0):
         raise ValueError(f"oracle_fit error {rc}")
     return dict(objective=obj[:nrec.value].copy(), seconds=sec[:nrec.value].copy(), alpharow=ar, alphacol=ac,
                 trials=(trials[0], trials[1]))
+
+
+def half_sweep(ep, params_struct, X, Y, alpha, which, begin, end, obj_by_unit):
+    """Update units [begin, end) of X (which=0) or Y (which=1) in place (sparse-evaluated form)."""
+    rc = lib().oracle_half_sweep(C.addressof(ep.struct), C.addressof(params_struct), _d(X), _d(Y), _d(alpha),
+                                 which, begin, end, _d(obj_by_unit))
+    if rc:
+        raise ValueError(f"oracle_half_sweep error {rc}")

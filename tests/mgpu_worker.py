@@ -1,0 +1,54 @@
+"""Launched by tests/test_gpu_multi.py under torch.distributed.run (one rank per GPU): the sharded fit
+(NCCL all-gather per half-iteration inside the engine) must reproduce the single-GPU fit bit for bit."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import lowrankmodels_b200 as lrm
+    from helpers import glrm_from_config
+    from lowrankmodels_b200 import distributed as D, synth
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+    ok = True
+    for name, cfg, loss, reg in (("C2/16", synth.config2(scale=16), lrm.QuadLoss(), lrm.QuadReg(0.1)),
+                                 ("C3/16", synth.config3(scale=16), lrm.LogisticLoss(), lrm.NonNegConstraint()),
+                                 ("C1", synth.config1(), lrm.QuadLoss(), lrm.QuadReg(0.1))):
+        g = glrm_from_config(cfg, loss, reg, reg)
+        ep = lrm.encode_problem(g)
+        p = lrm.ProxGradParams(max_iter=6, abs_tol=0, rel_tol=0)
+        X, Y = g.X.copy(order="F"), g.Y.copy(order="F")
+        eng = lrm.Engine(ep, device=local, rank=rank, nranks=world)
+        eng.comm_init(D.broadcast_unique_id(dist, rank, lrm.Engine.unique_id))
+        rb, re_, cb, ce = eng.shard()
+        brow, bcol = D.shard_bounds(ep, world)
+        assert (rb, re_, cb, ce) == (brow[rank], brow[rank + 1], bcol[rank], bcol[rank + 1])
+        obj, _ = eng.fit(p, X, Y)
+        ar, ac = eng.stepsizes()
+        eng.close()
+        if rank == 0:
+            X1, Y1 = g.X.copy(order="F"), g.Y.copy(order="F")
+            with lrm.Engine(ep, device=local) as e1:
+                obj1, _ = e1.fit(p, X1, Y1)
+                ar1, ac1 = e1.stepsizes()
+            same = (obj == obj1).all() and (X == X1).all() and (Y == Y1).all() and (ar == ar1).all() and (ac == ac1).all()
+            print(f"{name}: {world}-GPU vs 1-GPU identical={same} obj_last={obj[-1]:.9e}", flush=True)
+            ok = ok and bool(same)
+    flag = torch.tensor([1.0 if ok else 0.0])
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -61,27 +61,25 @@ def test_no_device_means_error_not_cpu_fallback():
     assert ei.value.code == -3      # GLRMB200_E_NO_DEVICE
 
 
-def test_validation_errors_come_before_any_device_work():
+def test_shape_errors_come_before_any_device_work_and_host_mirror_checks_labels():
     g = glrm_from_config(synth.config1(), lrm.QuadLoss(), lrm.QuadReg(0.1), lrm.QuadReg(0.1))
     ep = lrm.encode_problem(g)
     ep.struct.d = 99
     h = _abi.Handle()
     rc = _abi.lib().glrmb200_create(C.byref(h), C.byref(ep.struct), 0, 0, 1)
     assert rc == -1 and b"embedding" in _abi.lib().glrmb200_last_error()
-    # NaN among the observations (glrm.jl:63-71)
-    ep = lrm.encode_problem(g)
-    ep.keep["dense_A"][3, 4] = np.nan
-    rc = _abi.lib().glrmb200_create(C.byref(h), C.byref(ep.struct), 0, 0, 1)
-    assert rc == -7 and b"(4, 5) is NaN" in _abi.lib().glrmb200_last_error()
-    # a label outside {1, 0, -1} for a Boolean loss (myBool, losses.jl:104)
+    # NaN among the observations (glrm.jl:63-71): the host mirror's constructor refuses it
+    A = synth.config1()["A"].copy()
+    A[3, 4] = np.nan
+    with pytest.raises(ValueError, match=r"\(4, 5\) is NaN"):
+        lrm.GLRM(A, lrm.QuadLoss(), lrm.ZeroReg(), lrm.ZeroReg(), 2)
+    # a label outside {1, 0, -1} for a Boolean loss (myBool, losses.jl:104): refused when encoding
     A = np.where(synth.normal_matrix(1, 1, 20, 10) > 0, 1.0, -1.0)
     A[2, 3] = 2.0
     g2 = lrm.GLRM(A, lrm.LogisticLoss(), lrm.ZeroReg(), lrm.ZeroReg(), 2)
     with pytest.raises(ValueError):
         lrm.encode_problem(g2)
-    ep2 = lrm.encode_problem(g2, validate=False)
-    rc = _abi.lib().glrmb200_create(C.byref(h), C.byref(ep2.struct), 0, 0, 1)
-    assert rc == -6
+    # (the C ABI repeats both checks on the device: tests/test_gpu_parity.py::test_errors_through_the_abi)
 
 
 def test_host_mirror_constructor_checks():

@@ -1,0 +1,91 @@
+"""world_size-2 gloo tests (CPU): the host side of the N>1 path — shard planning through the C ABI, the
+unique-id rendezvous, and the property the multi-GPU design rests on: "every rank sweeps its own nnz-balanced
+shard, then the updated factor is all-gathered" reproduces the unsharded sweep bit for bit (rows of X are
+independent given Y, columns of Y given X: proxgrad.jl:118,162)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import lowrankmodels_b200 as lrm
+        import oracle_py
+        from helpers import glrm_from_config
+        from lowrankmodels_b200 import distributed as D, synth
+
+        cfg = synth.config2(scale=32)
+        g = glrm_from_config(cfg, lrm.QuadLoss(), lrm.QuadReg(0.1), lrm.QuadReg(0.1))
+        ep = lrm.encode_problem(g)
+        rb, cb = D.shard_bounds(ep, world)
+        # every rank plans the same shards, they tile the ranges, and they balance the observations
+        import torch
+        t = torch.from_numpy(np.concatenate([rb, cb]).copy())
+        ref = t.clone()
+        dist.broadcast(ref, src=0)
+        assert (t == ref).all()
+        assert rb[0] == 0 and rb[-1] == cfg["m"] and cb[0] == 0 and cb[-1] == cfg["n"]
+        nnz_r = np.diff(ep.keep["row_ptr"][rb])
+        assert nnz_r.max() - nnz_r.min() <= 2 * np.diff(ep.keep["row_ptr"]).max()
+        # unique-id rendezvous (any 128 bytes stand in for ncclUniqueId on the CPU)
+        uid = D.broadcast_unique_id(dist, rank, lambda: bytes(range(128)))
+        assert uid == bytes(range(128))
+
+        # sharded sweeps + all-gather == the unsharded oracle fit
+        p = lrm.ProxGradParams(max_iter=3, abs_tol=0, rel_tol=0)
+        ps = lrm.encode_params(p)
+        X, Y = g.X.copy(order="F"), g.Y.copy(order="F")
+        ar, ac = np.full(cfg["m"], p.stepsize), np.full(cfg["n"], p.stepsize)
+        orow, ocol = np.zeros(cfg["m"]), np.zeros(cfg["n"])
+        traj = []
+        for _ in range(p.max_iter):
+            oracle_py.half_sweep(ep, ps, X, Y, ar, 0, int(rb[rank]), int(rb[rank + 1]), orow)
+            D.allgather_columns(dist, X, rb)
+            oracle_py.half_sweep(ep, ps, X, Y, ac, 1, int(cb[rank]), int(cb[rank + 1]), ocol)
+            D.allgather_columns(dist, Y, cb)
+            D.allgather_columns(dist, ocol, cb)
+            traj.append(float(np.sum(ocol)))
+        Xo, Yo = g.X.copy(order="F"), g.Y.copy(order="F")
+        want = oracle_py.fit(ep, ps, Xo, Yo, mode=1, nthreads=1)
+        assert (X == Xo).all() and (Y == Yo).all()
+        np.testing.assert_allclose(traj, want["objective"][1:], rtol=1e-13)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_sweep_matches_unsharded():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == "ok", f"rank {rank}: {msg}"

@@ -234,6 +234,28 @@ def test_errors_through_the_abi():
         with pytest.raises(_abi.GLRMB200Error) as ei:                               # norm(Y) == 0
             eng.fit(lrm.ProxGradParams(max_iter=2), g.X.copy(order="F"), np.zeros_like(g.Y, order="F"))
         assert ei.value.code == -1
+    # device-side validation of the observations: NaN (glrm.jl:63-71), Boolean label domain (losses.jl:104),
+    # index bounds — dense and list forms
+    h = _abi.Handle()
+    L = _abi.lib()
+    ep = lrm.encode_problem(g)
+    ep.keep["dense_A"][3, 4] = np.nan
+    assert L.glrmb200_create(C.byref(h), C.byref(ep.struct), 0, 0, 1) == -7
+    assert b"(4, 5) is NaN" in L.glrmb200_last_error()
+    Ab, obs, X0 = small_sparse(seed=6, labels="bool")
+    Ab[obs[5, 0], obs[5, 1]] = 2.0
+    gb = lrm.GLRM(Ab, lrm.LogisticLoss(), lrm.ZeroReg(), lrm.ZeroReg(), 4, obs=obs, X=X0)
+    epb = lrm.encode_problem(gb, validate=False)
+    assert L.glrmb200_create(C.byref(h), C.byref(epb.struct), 0, 0, 1) == -6
+    assert f"({obs[5, 0] + 1}, {obs[5, 1] + 1})".encode() in L.glrmb200_last_error()
+    gq = lrm.GLRM(Ab, lrm.QuadLoss(), lrm.ZeroReg(), lrm.ZeroReg(), 4, obs=obs, X=X0)
+    epq = lrm.encode_problem(gq)
+    epq.keep["col_idx"][7] = 10_000
+    assert L.glrmb200_create(C.byref(h), C.byref(epq.struct), 0, 0, 1) == -1
+    assert b"col_idx[7]" in L.glrmb200_last_error()
+    epq.keep["col_idx"][7] = 0
+    epq.keep["row_val"][11] = np.nan
+    assert L.glrmb200_create(C.byref(h), C.byref(epq.struct), 0, 0, 1) == -7
     A = np.floor(synth.uniform(1, 1, np.arange(60)).reshape(20, 3) * 3) + 1
     g2 = lrm.GLRM(A, lrm.MultinomialLoss(3), lrm.ZeroReg(), lrm.ZeroReg(), 2)
     with pytest.raises(_abi.GLRMB200Error) as ei:
