@@ -39,7 +39,8 @@ struct SweepArgs {
   int64_t unit_base;      // first unit of the shard (ptr is indexed by unit - unit_base)
   const int32_t* order;   // schedule: unit ids, heaviest first
   int64_t n_units;        // units this launch covers: order[0 .. n_units)
-  double* own;            // factor being updated   [units_total * kp]
+  double* own;            // factor being updated   [units_total * stride]
+  const int64_t* own_col; // unit -> column of `own` (nullptr: identity); set when block columns shift the numbering
   const double* opp;      // factor being gathered  [opp_total * kp]
   int32_t stride;         // doubles between factor columns == 2*G*R of the tile (zero-padded past k)
   int32_t last_lanes;     // lanes of a group whose LAST slot holds real data (ceil(k/2) - G*(R-1)); the others
@@ -646,7 +647,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
     start = (unit - A.unit_base) * A.full_len;
     len = A.full_len;
   }
-  double* own = A.own + unit * (int64_t)A.stride;
+  double* own = A.own + (A.own_col ? A.own_col[unit] : unit) * (int64_t)A.stride;
   // columns are stored with stride 2*G*R doubles, zero past k: every lane owns R real slots
   double2 x[R];
 #pragma unroll

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "glrm_device.cuh"
+#include "glrm_vec.cuh"
 
 using namespace glrm;
 
@@ -90,6 +91,8 @@ struct Side {
   double* d_val = nullptr;
   int32_t* d_order = nullptr;
   int64_t n_heavy = 0, n_light = 0;
+  int32_t* d_order_vec = nullptr;   // units that go through vec_sweep_kernel (block columns / all rows of a problem with them)
+  int64_t n_vec = 0;
   int32_t* d_reg_code = nullptr;
   double* d_reg_param = nullptr;
   std::vector<double> h_reg_param;  // for set_reg_scale
@@ -111,6 +114,9 @@ struct glrmb200_engine {
   int64_t heavy_threshold = 1024;
   int64_t nnz_rows_total = 0;
   bool obs_full = false;
+  bool has_vec = false;              // some column has a vector-valued loss
+  int64_t* d_ystart = nullptr;       // [n+1]
+  std::vector<int64_t> ystart;
   Side rows, cols;
   int32_t* d_loss_code = nullptr;
   double* d_loss_param = nullptr;
@@ -178,22 +184,26 @@ static int upload(T** dst, const T* src, size_t count) {
 }
 
 // degree-sorted schedule (heaviest first): LPT order for the tail, and neighbouring warps of a CTA get
-// units of similar length
-static int build_schedule(Side& S, const int64_t* ptr_global, int64_t heavy_threshold) {
+// units of similar length.  `is_vec` (optional) routes units to the vector-loss kernel instead.
+static int build_schedule(Side& S, const int64_t* ptr_global, int64_t heavy_threshold, const std::vector<char>* is_vec = nullptr) {
   const int64_t cnt = S.end - S.begin;
-  std::vector<int32_t> order((size_t)cnt);
-  std::iota(order.begin(), order.end(), (int32_t)S.begin);
-  if (ptr_global) {
-    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-      return ptr_global[a + 1] - ptr_global[a] > ptr_global[b + 1] - ptr_global[b];
-    });
-    S.n_heavy = 0;
-    while (S.n_heavy < cnt && ptr_global[order[S.n_heavy] + 1] - ptr_global[order[S.n_heavy]] >= heavy_threshold) S.n_heavy++;
-  } else {
-    S.n_heavy = S.full_len >= heavy_threshold ? cnt : 0;
+  std::vector<int32_t> order, vec;
+  order.reserve((size_t)cnt);
+  for (int64_t u = S.begin; u < S.end; ++u) {
+    if (is_vec && (*is_vec)[(size_t)u]) vec.push_back((int32_t)u); else order.push_back((int32_t)u);
   }
-  S.n_light = cnt - S.n_heavy;
-  return upload(&S.d_order, order.data(), order.size());
+  auto deg = [&](int32_t u) { return ptr_global ? ptr_global[u + 1] - ptr_global[u] : S.full_len; };
+  if (ptr_global) {
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return deg(a) > deg(b); });
+    std::stable_sort(vec.begin(), vec.end(), [&](int32_t a, int32_t b) { return deg(a) > deg(b); });
+  }
+  S.n_heavy = 0;
+  while (S.n_heavy < (int64_t)order.size() && deg(order[(size_t)S.n_heavy]) >= heavy_threshold) S.n_heavy++;
+  S.n_light = (int64_t)order.size() - S.n_heavy;
+  S.n_vec = (int64_t)vec.size();
+  int rc = upload(&S.d_order, order.data(), order.size());
+  if (rc) return rc;
+  return upload(&S.d_order_vec, vec.data(), vec.size());
 }
 
 static int setup_regs(Side& S, int64_t count, const int32_t* code, const double* param) {
@@ -251,6 +261,30 @@ static cudaError_t launch_sweep(const glrmb200_engine* E, const SweepArgs& A, in
   }
 }
 
+// units that involve vector-valued losses (csrc/glrm_vec.cuh): one warp per unit
+static cudaError_t launch_vec(const glrmb200_engine* E, const SweepArgs& A, bool x_side, const Side& S, int64_t* launches) {
+  if (S.n_vec == 0) return cudaSuccess;
+  VecArgs V;
+  V.s = A;
+  V.s.order = S.d_order_vec;
+  V.s.n_units = S.n_vec;
+  V.s.own_col = nullptr;
+  V.ystart = E->d_ystart;
+  V.x_side = x_side ? 1 : 0;
+  const unsigned grid = (unsigned)((S.n_vec + 3) / 4);
+  const int g = E->tile_g, r = E->tile_r;
+#define T(GG, RR)                                                                                    \
+  if (g == GG && r == RR) {                                                                          \
+    if (x_side) vec_sweep_kernel<GG, RR, 1><<<grid, 128, 0, E->stream>>>(V);                          \
+    else vec_sweep_kernel<GG, RR, VEC_DMAX><<<grid, 128, 0, E->stream>>>(V);                          \
+    ++*launches;                                                                                     \
+    return cudaGetLastError();                                                                       \
+  }
+  T(4, 1) T(8, 1) T(8, 2)
+#undef T
+  return cudaErrorInvalidValue;
+}
+
 static cudaError_t launch_reg_eval(const glrmb200_engine* E, const double* own, const Side& S, double* out) {
   const int g = E->tile_g, r = E->tile_r;
   const int64_t per_cta = 4 * (32 / g);
@@ -272,6 +306,7 @@ static SweepArgs make_args(const glrmb200_engine* E, bool x_side, int flags, dou
   A.order = S.d_order;
   A.n_units = 0;
   A.own = x_side ? E->d_X : E->d_Y;
+  A.own_col = (!x_side && E->has_vec) ? E->d_ystart : nullptr;
   A.opp = x_side ? E->d_Y : E->d_X;
   A.stride = E->stride;
   A.last_lanes = E->kp / 2 - E->tile_g * (E->tile_r - 1);
@@ -303,7 +338,7 @@ extern "C" int glrmb200_device_count(int32_t* count) {
 }
 
 static void free_side(Side& S) {
-  cudaFree(S.d_ptr); cudaFree(S.d_idx); cudaFree(S.d_val); cudaFree(S.d_order);
+  cudaFree(S.d_ptr); cudaFree(S.d_idx); cudaFree(S.d_val); cudaFree(S.d_order); cudaFree(S.d_order_vec);
   cudaFree(S.d_reg_code); cudaFree(S.d_reg_param); cudaFree(S.d_alpha); cudaFree(S.d_obj);
 }
 
@@ -313,7 +348,7 @@ extern "C" int glrmb200_destroy(glrmb200_handle E) {
   if (E->stream) cudaStreamSynchronize(E->stream);
   if (E->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(E->comm);
   free_side(E->rows); free_side(E->cols);
-  cudaFree(E->d_loss_code); cudaFree(E->d_loss_param); cudaFree(E->d_X); cudaFree(E->d_Y);
+  cudaFree(E->d_loss_code); cudaFree(E->d_loss_param); cudaFree(E->d_X); cudaFree(E->d_Y); cudaFree(E->d_ystart);
   cudaFree(E->d_scalars); cudaFree(E->d_trials);
   if (E->h_pinned) cudaFreeHost(E->h_pinned);
   for (auto& e : E->ev) if (e) cudaEventDestroy(e);
@@ -332,22 +367,32 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
 
   // ---- losses: embedding dims must sum to d (get_yidxs, losses.jl:76-93) ----------------------
   int64_t dsum = 0;
-  bool uniform = true, vector_loss = false;
+  bool uniform = true;
+  E->ystart.assign((size_t)n + 1, 0);
+  std::vector<char> col_is_vec((size_t)n, 0);
   for (int64_t f = 0; f < n; ++f) {
     const int code = P->loss_code[f];
     const double* p = P->loss_param + f * GLRMB200_LOSS_NPARAM;
     if (code < GLRMB200_LOSS_QUAD || code > GLRMB200_LOSS_MULTINOMIAL_ORDINAL)
       return fail(GLRMB200_E_UNSUPPORTED, "loss code %d (column %lld) is unknown", code, (long long)f);
     const int dim = loss_dim(code, p);
-    if (dim != 1 || code >= GLRMB200_LOSS_MULTINOMIAL) vector_loss = true;
+    if (code >= GLRMB200_LOSS_MULTINOMIAL) {
+      E->has_vec = true;
+      col_is_vec[(size_t)f] = 1;
+      if (dim < 1 || dim > VEC_DMAX)
+        return fail(GLRMB200_E_UNSUPPORTED, "column %lld: embedding dimension %d is outside 1..%d supported on the device", (long long)f, dim, VEC_DMAX);
+      if ((code == GLRMB200_LOSS_OVA || code == GLRMB200_LOSS_BVS) &&
+          ((int)p[3] < GLRMB200_LOSS_QUAD || (int)p[3] > GLRMB200_LOSS_WEIGHTED_HINGE))
+        return fail(GLRMB200_E_UNSUPPORTED, "column %lld: bin_loss code %d must be a scalar loss", (long long)f, (int)p[3]);
+    }
+    E->ystart[(size_t)f] = dsum;
     dsum += dim;
     if (code != P->loss_code[0] || memcmp(p, P->loss_param, 3 * sizeof(double)) != 0) uniform = false;
   }
+  E->ystart[(size_t)n] = dsum;
   if (dsum != P->d) return fail(GLRMB200_E_INVALID, "d = %lld but the losses' embedding dimensions sum to %lld (proxgrad.jl:55-63)", (long long)P->d, (long long)dsum);
-  if (vector_loss)
-    return fail(GLRMB200_E_UNSUPPORTED, "vector-valued losses (Multinomial/OvA/BvS/Ordistic/MultinomialOrdinal) have no device implementation yet");
   E->loss_template = 0;
-  if (uniform && (P->loss_code[0] == GLRMB200_LOSS_QUAD || P->loss_code[0] == GLRMB200_LOSS_LOGISTIC)) {
+  if (uniform && !E->has_vec && (P->loss_code[0] == GLRMB200_LOSS_QUAD || P->loss_code[0] == GLRMB200_LOSS_LOGISTIC)) {
     E->loss_template = P->loss_code[0];
     E->uparam[0] = P->loss_param[0]; E->uparam[1] = P->loss_param[1]; E->uparam[2] = P->loss_param[2];
   }
@@ -369,6 +414,8 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
     }
   }
   E->stride = 2 * E->tile_g * E->tile_r;
+  if (E->has_vec && E->tile_r > 2)
+    return fail(GLRMB200_E_UNSUPPORTED, "vector-valued losses are supported on the device for k <= 32 this round (k = %lld)", (long long)k);
   if (const char* t = getenv("GLRMB200_HEAVY")) E->heavy_threshold = std::max<long long>(1, atoll(t));
 
   // ---- observation lists: validation (glrm.jl:63-71, losses.jl:104) ----------------------------
@@ -416,6 +463,17 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   if ((rc = upload(&E->d_loss_param, P->loss_param, (size_t)n * GLRMB200_LOSS_NPARAM))) return rc;
   if ((rc = setup_regs(R, P->rx_count, P->rx_code, P->rx_param))) return rc;
   if ((rc = setup_regs(C, P->ry_count, P->ry_code, P->ry_param))) return rc;
+  std::vector<char> all_rows_vec(E->has_vec ? (size_t)m : 0, 1);   // with block columns every row takes the vector path
+  if (E->has_vec) {
+    if ((rc = upload(&E->d_ystart, E->ystart.data(), E->ystart.size()))) return rc;
+    for (int64_t f = 0; f < n; ++f) {
+      if (!col_is_vec[(size_t)f]) continue;
+      const int base = P->ry_code[P->ry_count == 1 ? 0 : f] & GLRMB200_REG_BASE_MASK;
+      if (!(base == GLRMB200_REG_ZERO || base == GLRMB200_REG_QUAD || base == GLRMB200_REG_ONE ||
+            base == GLRMB200_REG_NONNEG || base == GLRMB200_REG_NONNEG_ONE))
+        return fail(GLRMB200_E_UNSUPPORTED, "column %lld: regularizer code %d on a block column (only element-wise regularizers decompose over the k x d_f block)", (long long)f, base);
+    }
+  }
 
   if (E->obs_full) {
     // column side streams the Julia (column-major) A as is; the row side gets a row-major copy
@@ -441,8 +499,8 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
       cudaFree(d_rowmajor);
       cudaFree(d_full);
     }
-    if ((rc = build_schedule(R, nullptr, E->heavy_threshold))) return rc;
-    if ((rc = build_schedule(C, nullptr, E->heavy_threshold))) return rc;
+    if ((rc = build_schedule(R, nullptr, E->heavy_threshold, E->has_vec ? &all_rows_vec : nullptr))) return rc;
+    if ((rc = build_schedule(C, nullptr, E->heavy_threshold, E->has_vec ? &col_is_vec : nullptr))) return rc;
     {
       unsigned long long* d_bad = nullptr;
       CUDA_OK(cudaMalloc((void**)&d_bad, sizeof(unsigned long long)));
@@ -463,7 +521,7 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
       }
     }
   } else {
-    auto up_side = [&](Side& S, const int64_t* ptr, const int32_t* idx, const double* val) -> int {
+    auto up_side = [&](Side& S, const int64_t* ptr, const int32_t* idx, const double* val, const std::vector<char>* vecflags) -> int {
       const int64_t cnt = S.end - S.begin, q0 = ptr[S.begin], q1 = ptr[S.end];
       S.nnz_local = q1 - q0;
       std::vector<int64_t> local((size_t)cnt + 1);
@@ -472,10 +530,10 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
       if (r2) return r2;
       if ((r2 = upload(&S.d_idx, idx ? idx + q0 : nullptr, (size_t)S.nnz_local))) return r2;
       if ((r2 = upload(&S.d_val, val ? val + q0 : nullptr, (size_t)S.nnz_local))) return r2;
-      return build_schedule(S, ptr, E->heavy_threshold);
+      return build_schedule(S, ptr, E->heavy_threshold, E->has_vec ? vecflags : nullptr);
     };
-    if ((rc = up_side(R, P->row_ptr, P->row_idx, P->row_val))) return rc;
-    if ((rc = up_side(C, P->col_ptr, P->col_idx, P->col_val))) return rc;
+    if ((rc = up_side(R, P->row_ptr, P->row_idx, P->row_val, &all_rows_vec))) return rc;
+    if ((rc = up_side(C, P->col_ptr, P->col_idx, P->col_val, &col_is_vec))) return rc;
     unsigned long long* d_bad = nullptr;
     CUDA_OK(cudaMalloc((void**)&d_bad, 2 * sizeof(unsigned long long)));
     CUDA_OK(cudaMemset(d_bad, 0xff, 2 * sizeof(unsigned long long)));
@@ -587,12 +645,14 @@ extern "C" int glrmb200_download_factors(glrmb200_handle E, double* X, double* Y
 }
 
 // all-gather of per-unit arrays whose shards are contiguous (`elems` doubles per unit)
-static int allgather_units(glrmb200_engine* E, double* buf, const Side& S, int64_t elems) {
+static int allgather_units(glrmb200_engine* E, double* buf, const Side& S, int64_t elems, const int64_t* colmap = nullptr) {
   if (E->nranks == 1) return 0;
   if (!E->comm) return fail(GLRMB200_E_STATE, "glrmb200_comm_init was not called");
   NCCL_OK(g_nccl.GroupStart());
   for (int r = 0; r < E->nranks; ++r) {
-    const int64_t b = S.bounds[r], cnt = (S.bounds[r + 1] - b) * elems;
+    const int64_t b = colmap ? colmap[S.bounds[r]] : S.bounds[r];
+    const int64_t e = colmap ? colmap[S.bounds[r + 1]] : S.bounds[r + 1];
+    const int64_t cnt = (e - b) * elems;
     if (cnt == 0) continue;
     NCCL_OK(g_nccl.Broadcast(buf + b * elems, buf + b * elems, (size_t)cnt, kNcclDouble, r, E->comm, E->stream));
   }
@@ -615,6 +675,7 @@ static int reduce_to_host(glrmb200_engine* E, const double* v, int64_t n, double
 static int objective_resident(glrmb200_engine* E, bool include_reg, double* out, int64_t* launches) {
   SweepArgs A = make_args(E, /*x_side=*/false, FLAG_EVAL_ONLY | (include_reg ? 0 : FLAG_NO_REG), INFINITY);
   cudaError_t ce = launch_sweep(E, A, E->cols.n_heavy, E->cols.n_light, launches);
+  if (ce == cudaSuccess) ce = launch_vec(E, A, false, E->cols, launches);
   if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "objective sweep launch: %s", cudaGetErrorString(ce));
   int rc = allgather_units(E, E->cols.d_obj, E->cols, 1);
   if (rc) return rc;
@@ -683,6 +744,7 @@ extern "C" int glrmb200_fit_resident(glrmb200_handle E, const glrmb200_params* p
     for (int inner = 0; inner < prm->inner_iter_X; ++inner) {                  // :117-158
       SweepArgs A = make_args(E, true, 0, prm->min_stepsize);
       cudaError_t ce = launch_sweep(E, A, E->rows.n_heavy, E->rows.n_light, &prof.x_launches);
+      if (ce == cudaSuccess) ce = launch_vec(E, A, true, E->rows, &prof.x_launches);
       if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "update-X launch: %s", cudaGetErrorString(ce));
     }
     CUDA_OK(cudaEventRecord(E->ev[1], E->stream));
@@ -691,10 +753,11 @@ extern "C" int glrmb200_fit_resident(glrmb200_handle E, const glrmb200_params* p
     for (int inner = 0; inner < prm->inner_iter_Y; ++inner) {                  // :160-203
       SweepArgs A = make_args(E, false, 0, prm->min_stepsize);
       cudaError_t ce = launch_sweep(E, A, E->cols.n_heavy, E->cols.n_light, &prof.y_launches);
+      if (ce == cudaSuccess) ce = launch_vec(E, A, false, E->cols, &prof.y_launches);
       if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "update-Y launch: %s", cudaGetErrorString(ce));
     }
     CUDA_OK(cudaEventRecord(E->ev[3], E->stream));
-    if ((rc = allgather_units(E, E->d_Y, E->cols, E->stride))) return rc;
+    if ((rc = allgather_units(E, E->d_Y, E->cols, E->stride, E->has_vec ? E->ystart.data() : nullptr))) return rc;
     if ((rc = allgather_units(E, E->cols.d_obj, E->cols, 1))) return rc;
     CUDA_OK(cudaEventRecord(E->ev[4], E->stream));
     double obj = 0.0;

@@ -35,6 +35,11 @@ def myBool(a):  # losses.jl:104
     raise ValueError("InexactError")
 
 
+def _exp(x):  # Julia's exp overflows to Inf instead of raising
+    with np.errstate(over="ignore"):
+        return float(np.exp(x))
+
+
 def _sign(x):
     return float(int(x > 0) - int(x < 0))
 
@@ -55,7 +60,7 @@ def evaluate(l, u, a):
     if name == "PeriodicLoss":                                                   # :216
         return s * (1 - math.cos((a - u) * (2 * math.pi) / l.T))
     if name == "PoissonLoss":                                                    # :237-239
-        return s * (math.exp(u) - a * u + (0 if a == 0 else a * (math.log(a) - 1)))
+        return s * (_exp(u) - a * u + (0 if a == 0 else a * (math.log(a) - 1)))
     if name == "OrdinalHingeLoss":                                               # :258-278
         if u > l.max - 1:
             n = min(math.floor(u), l.max - 1) - a
@@ -136,7 +141,7 @@ def grad(l, u, a):
     if name == "PeriodicLoss":                                                   # :218
         return -s * ((2 * math.pi) / l.T) * math.sin((a - u) * (2 * math.pi) / l.T)
     if name == "PoissonLoss":
-        return s * (math.exp(u) - a)                                              # :241
+        return s * (_exp(u) - a)                                                  # :241
     if name == "OrdinalHingeLoss":                                               # :280-292
         if u > a:
             g = min(math.ceil(u), l.max) - a

@@ -146,6 +146,53 @@ def test_heterogeneous_scalar_columns_and_per_row_regs(orc):
     check(orc, g, lrm.ProxGradParams(max_iter=10), rtol=1e-6, factors=False)
 
 
+def mixed_problem(m=40, k=3, seed=2, dup=True):
+    """test/hello_world.jl:5-45: real / boolean / ordinal / categorical columns with their own scales."""
+    n = 11
+    u = synth.uniform(seed, 61, np.arange(m * n)).reshape(m, n)
+    z = synth.normal_matrix(seed, 62, m, n)
+    A = z.copy()
+    A[:, 2] = np.where(z[:, 2] > 0, 1, -1)
+    A[:, 3] = np.floor(u[:, 3] * 5) + 1          # OrdinalHinge 1..5
+    A[:, 4] = np.floor(u[:, 4] * 4) + 1          # BvS levels 1..4      (embedding dim 3)
+    A[:, 5] = np.floor(u[:, 5] * 3) + 1          # Multinomial 1..3     (3)
+    A[:, 6] = np.floor(u[:, 6] * 3) + 1          # OvA 1..3             (3)
+    A[:, 7] = np.floor(u[:, 7] * 4)              # Poisson counts
+    A[:, 9] = np.floor(u[:, 9] * 4) + 1          # Ordistic 1..4        (4)
+    A[:, 10] = np.floor(u[:, 10] * 5) + 1        # MultinomialOrdinal 1..5 (4)
+    losses = [lrm.QuadLoss(1.5), lrm.HuberLoss(0.7), lrm.HingeLoss(1.2), lrm.OrdinalHingeLoss(1, 5, 0.9),
+              lrm.BvSLoss(4, 1.1), lrm.MultinomialLoss(3, 0.8), lrm.OvALoss(3, 1.3, bin_loss=lrm.HingeLoss(0.9)),
+              lrm.PoissonLoss(), lrm.QuantileLoss(1.0, quantile=0.7), lrm.OrdisticLoss(4, 0.6),
+              lrm.MultinomialOrdinalLoss(5, 0.7)]
+    d = lrm.embedding_dim(losses)
+    rx = [lrm.QuadReg(0.1) if e % 4 == 0 else lrm.OneReg(0.05) if e % 4 == 1 else lrm.NonNegConstraint()
+          if e % 4 == 2 else lrm.KSparseConstraint(2) for e in range(m)]
+    ry = [lrm.QuadReg(0.1 + 0.01 * f) if f % 2 == 0 else lrm.OneReg(0.03) for f in range(n)]
+    ii, jj = np.nonzero(u < 0.7)
+    obs = np.stack([ii, jj], axis=1)
+    if dup:
+        obs = np.concatenate([obs, obs[:25]])
+    return lrm.GLRM(A, losses, rx, ry, k, obs=obs, X=np.abs(synth.normal_matrix(seed, 63, k, m)) * 0.3,
+                    Y=synth.normal_matrix(seed, 64, k, d) * 0.3)
+
+
+def test_vector_valued_losses_mixed_columns(orc):
+    """Multinomial / OvA / BvS / Ordistic / MultinomialOrdinal block columns next to scalar ones (losses.jl:354-608)."""
+    check(orc, mixed_problem(), lrm.ProxGradParams(max_iter=10), rtol=1e-6, factors=False)
+    g = mixed_problem(m=25, k=5, seed=3, dup=False)
+    lrm.add_offset(g)                                                   # lastentry1 rows, lastentry_unpenalized blocks
+    check(orc, g, lrm.ProxGradParams(max_iter=6, inner_iter=2), rtol=1e-6, factors=False)
+
+
+def test_config4_scaled_twin(orc):
+    """BASELINE config 4 (/16 twin: 62 500 x 62, fully observed): 50 % QuadLoss, 30 % HingeLoss, 20 % MultinomialLoss(5), k=20."""
+    c = synth.config4(scale=16)
+    losses = ([lrm.QuadLoss()] * c["n_quad"] + [lrm.HingeLoss()] * c["n_hinge"] + [lrm.MultinomialLoss(c["levels"])] * c["n_multi"])
+    g = lrm.GLRM(c["A"], losses, lrm.QuadReg(0.1), lrm.QuadReg(0.1), c["k"], X=c["X0"], Y=c["Y0"])
+    got, want = check(orc, g, lrm.ProxGradParams(max_iter=3, abs_tol=0, rel_tol=0), rtol=1e-6, factors=False)
+    assert_traj_close(got["objective"], want["objective"], SPEC)
+
+
 def test_offset_and_inner_iterations(orc):
     A, obs, X0 = small_sparse(seed=8)
     g = lrm.GLRM(A, lrm.QuadLoss(), lrm.QuadReg(0.1), lrm.QuadReg(0.1), 4, obs=obs, X=X0,
@@ -257,10 +304,12 @@ def test_errors_through_the_abi():
     epq.keep["row_val"][11] = np.nan
     assert L.glrmb200_create(C.byref(h), C.byref(epq.struct), 0, 0, 1) == -7
     A = np.floor(synth.uniform(1, 1, np.arange(60)).reshape(20, 3) * 3) + 1
-    g2 = lrm.GLRM(A, lrm.MultinomialLoss(3), lrm.ZeroReg(), lrm.ZeroReg(), 2)
-    with pytest.raises(_abi.GLRMB200Error) as ei:
-        lrm.Engine(g2)
-    assert ei.value.code == -2                                                      # no device implementation yet
+    for g2 in (lrm.GLRM(A, lrm.MultinomialLoss(3), lrm.ZeroReg(), lrm.ZeroReg(), 40),           # block columns need k <= 32
+               lrm.GLRM(A * 3, lrm.MultinomialLoss(9), lrm.ZeroReg(), lrm.ZeroReg(), 2),        # embedding dim > 8
+               lrm.GLRM(A, lrm.MultinomialLoss(3), lrm.ZeroReg(), lrm.UnitOneSparseConstraint(), 2)):  # non-separable block reg
+        with pytest.raises(_abi.GLRMB200Error) as ei:
+            lrm.Engine(g2)
+        assert ei.value.code == -2                                                  # GLRMB200_E_UNSUPPORTED, never a CPU fallback
 
 
 def test_full_size_config2_properties():
