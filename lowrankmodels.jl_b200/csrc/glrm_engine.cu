@@ -126,6 +126,8 @@ struct glrmb200_engine {
   unsigned long long* d_trials = nullptr;   // [2]
   double* h_pinned = nullptr;               // [8]
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;            // the warp-tier launch of a sweep runs here, concurrently with the CTA tier
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   ncclComm_t comm = nullptr;
   bool factors_resident = false;
@@ -226,12 +228,21 @@ static int setup_regs(Side& S, int64_t count, const int32_t* code, const double*
 struct Tile { int g, r; };
 static const Tile kTiles[] = {{4, 1}, {8, 1}, {8, 2}, {8, 3}, {8, 4}, {16, 2}, {16, 3}, {16, 4}, {32, 2}, {32, 3}, {32, 4}};
 
+struct Streams { cudaStream_t main, side; cudaEvent_t fork, join; };
+
+// the two tiers of a sweep touch disjoint units: the warp tier is forked onto the side stream so it fills the
+// SMs the CTA tier leaves idle in its tail, and joined back before anything else is enqueued
 template <int G, int R, int LOSS>
-static cudaError_t launch_tile(const SweepArgs& A, int64_t n_heavy, int64_t n_light, cudaStream_t st, int64_t* launches) {
+static cudaError_t launch_tile(const SweepArgs& A, int64_t n_heavy, int64_t n_light, const Streams& st, int64_t* launches) {
+  const bool both = n_heavy > 0 && n_light > 0 && st.side;
+  if (both) {
+    cudaEventRecord(st.fork, st.main);
+    cudaStreamWaitEvent(st.side, st.fork, 0);
+  }
   if (n_heavy > 0) {
     SweepArgs H = A;
     H.n_units = n_heavy;
-    sweep_cta_kernel<G, R, LOSS><<<(unsigned)n_heavy, WARPS_PER_CTA_HEAVY * 32, 0, st>>>(H);
+    sweep_cta_kernel<G, R, LOSS><<<(unsigned)n_heavy, WARPS_PER_CTA_HEAVY * 32, 0, st.main>>>(H);
     ++*launches;
   }
   if (n_light > 0) {
@@ -239,14 +250,18 @@ static cudaError_t launch_tile(const SweepArgs& A, int64_t n_heavy, int64_t n_li
     L.order = A.order + n_heavy;
     L.n_units = n_light;
     const int64_t grid = (n_light + WARPS_PER_CTA_LIGHT - 1) / WARPS_PER_CTA_LIGHT;
-    sweep_warp_kernel<G, R, LOSS><<<(unsigned)grid, WARPS_PER_CTA_LIGHT * 32, 0, st>>>(L);
+    sweep_warp_kernel<G, R, LOSS><<<(unsigned)grid, WARPS_PER_CTA_LIGHT * 32, 0, both ? st.side : st.main>>>(L);
     ++*launches;
+  }
+  if (both) {
+    cudaEventRecord(st.join, st.side);
+    cudaStreamWaitEvent(st.main, st.join, 0);
   }
   return cudaGetLastError();
 }
 
 template <int LOSS>
-static cudaError_t launch_loss(int g, int r, const SweepArgs& A, int64_t nh, int64_t nl, cudaStream_t st, int64_t* launches) {
+static cudaError_t launch_loss(int g, int r, const SweepArgs& A, int64_t nh, int64_t nl, const Streams& st, int64_t* launches) {
 #define T(GG, RR) if (g == GG && r == RR) return launch_tile<GG, RR, LOSS>(A, nh, nl, st, launches)
   T(4, 1); T(8, 1); T(8, 2); T(8, 3); T(8, 4); T(16, 2); T(16, 3); T(16, 4); T(32, 2); T(32, 3); T(32, 4);
 #undef T
@@ -254,10 +269,12 @@ static cudaError_t launch_loss(int g, int r, const SweepArgs& A, int64_t nh, int
 }
 
 static cudaError_t launch_sweep(const glrmb200_engine* E, const SweepArgs& A, int64_t nh, int64_t nl, int64_t* launches) {
+  static const bool two_streams = !(getenv("GLRMB200_ONE_STREAM") && atoi(getenv("GLRMB200_ONE_STREAM")));
+  const Streams st{E->stream, two_streams ? E->stream2 : nullptr, E->ev_fork, E->ev_join};
   switch (E->loss_template) {
-    case GLRMB200_LOSS_QUAD: return launch_loss<GLRMB200_LOSS_QUAD>(E->tile_g, E->tile_r, A, nh, nl, E->stream, launches);
-    case GLRMB200_LOSS_LOGISTIC: return launch_loss<GLRMB200_LOSS_LOGISTIC>(E->tile_g, E->tile_r, A, nh, nl, E->stream, launches);
-    default: return launch_loss<0>(E->tile_g, E->tile_r, A, nh, nl, E->stream, launches);
+    case GLRMB200_LOSS_QUAD: return launch_loss<GLRMB200_LOSS_QUAD>(E->tile_g, E->tile_r, A, nh, nl, st, launches);
+    case GLRMB200_LOSS_LOGISTIC: return launch_loss<GLRMB200_LOSS_LOGISTIC>(E->tile_g, E->tile_r, A, nh, nl, st, launches);
+    default: return launch_loss<0>(E->tile_g, E->tile_r, A, nh, nl, st, launches);
   }
 }
 
@@ -352,6 +369,9 @@ extern "C" int glrmb200_destroy(glrmb200_handle E) {
   cudaFree(E->d_scalars); cudaFree(E->d_trials);
   if (E->h_pinned) cudaFreeHost(E->h_pinned);
   for (auto& e : E->ev) if (e) cudaEventDestroy(e);
+  if (E->ev_fork) cudaEventDestroy(E->ev_fork);
+  if (E->ev_join) cudaEventDestroy(E->ev_join);
+  if (E->stream2) cudaStreamDestroy(E->stream2);
   if (E->stream) cudaStreamDestroy(E->stream);
   delete E;
   return 0;
@@ -453,6 +473,9 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   if (E->device < 0 || E->device >= g_device_checked) return fail(GLRMB200_E_INVALID, "device %d out of range (%d visible)", E->device, g_device_checked);
   CUDA_OK(cudaSetDevice(E->device));
   CUDA_OK(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&E->stream2, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&E->ev_fork, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&E->ev_join, cudaEventDisableTiming));
   for (auto& e : E->ev) CUDA_OK(cudaEventCreate(&e));
   CUDA_OK(cudaMallocHost((void**)&E->h_pinned, 8 * sizeof(double)));
   CUDA_OK(cudaMalloc((void**)&E->d_scalars, 4 * sizeof(double)));
