@@ -191,6 +191,10 @@ def pinned_like(a):
 
 
 def run_ours(args):
+    # exactly ONE line may reach stdout (NCCL prints its version banner there): park fd 1 on stderr until the end
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import lowrankmodels_b200 as lrm
@@ -341,6 +345,8 @@ def run_ours(args):
                                                 "2 timed iterations after 1 warm-up", "seconds_per_iter": per_iter}
         val2, per2, _, _, _ = cpu_reference_run(args.config, 3, 1, mode=1)
         line["cpu_baseline"]["sparse_evaluated_value"] = val2
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -20,6 +20,7 @@
 // the unit lands on.
 #pragma once
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 #include <math.h>
 #include "../../include/glrm_b200.h"
@@ -615,6 +616,46 @@ __device__ __forceinline__ void unit_reduce_g(double2 (&g)[R], double* red, int 
   }
 }
 
+// ---- thread-block-cluster tier: CS CTAs share one super-heavy unit ---------------------------------------------
+// Partial results are exchanged through distributed shared memory and summed in cluster-rank order, so the
+// result does not depend on which CTA finishes first (nor on the GPU the unit is scheduled on).
+template <int CS>
+__device__ __forceinline__ double cluster_sum_obj(double v, double* slot) {
+  if (CS == 1) return v;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  if (threadIdx.x == 0) *slot = v;
+  cl.sync();
+  double t = 0.0;
+  for (int r = 0; r < CS; ++r) t += *cl.map_shared_rank(slot, r);
+  cl.sync();
+  return t;
+}
+template <int G, int R, int CS>
+__device__ __forceinline__ void cluster_sum_g(double2 (&g)[R], double2* buf, int gid, int lg) {
+  if (CS == 1) return;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  if (gid == 0) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) buf[r * G + lg] = g[r];
+  }
+  cl.sync();
+  if (gid == 0) {
+    double2 acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = make_double2(0.0, 0.0);
+    for (int c = 0; c < CS; ++c) {
+      const double2* rb = cl.map_shared_rank(buf, c);
+#pragma unroll
+      for (int r = 0; r < R; ++r) { const double2 v = rb[r * G + lg]; acc[r].x += v.x; acc[r].y += v.y; }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) g[r] = acc[r];
+  }
+  cl.sync();
+}
+
 // pipeline depth / residency per tile: DEPTH gather buffers (R double2 each) in the gradient pass, TRIAL_DEPTH
 // in the trial passes (x and g live in shared memory there, so the registers go to in-flight gathers)
 #ifndef GLRM_PIPE_DEPTH
@@ -630,14 +671,19 @@ template <int R> struct TileCfg {
   static constexpr int HEAVY_CTAS = 2;
 };
 
-template <int G, int R, int W, int LOSS, int DEPTH>
-__device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, double* red, double* part, double* xg) {
+template <int G, int R, int W, int LOSS, int DEPTH, int CS = 1>
+__device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, double* red, double* part, double* xg, double* clbuf = nullptr) {
   constexpr int NGW = 32 / G;
   const int lane = threadIdx.x & 31;
   const int warp = (W == 1) ? 0 : (threadIdx.x >> 5);
   const int lg = lane % G;
   const int gid = warp * NGW + lane / G;
   const int k = A.k;
+  // with a cluster, the unit's chunks are dealt round-robin over all CS*W warps
+  constexpr int WT = W * CS;
+  int crank = 0;
+  if (CS > 1) crank = (int)cooperative_groups::this_cluster().block_rank();
+  const int gwarp = crank * W + warp;
 
   int64_t start, len;
   if (A.ptr) {
@@ -667,9 +713,11 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
   // ---- gradient pass (proxgrad.jl:119-135 / :163-178) ----------------------------------------
   double2 g[R];
   double obj_old;
-  entry_pass<G, R, W, LOSS, true, DEPTH>(A, start, len, warp, lane, x, ucode, us, up1, up2, g, obj_old);
+  entry_pass<G, R, WT, LOSS, true, DEPTH>(A, start, len, gwarp, lane, x, ucode, us, up1, up2, g, obj_old);
   obj_old = block_sum_obj<W>(obj_old, red, lane, warp);
+  obj_old = cluster_sum_obj<CS>(obj_old, clbuf);
   unit_reduce_g<G, R, W>(g, red, lane, warp, lg);
+  cluster_sum_g<G, R, CS>(g, reinterpret_cast<double2*>(clbuf + 2), gid, lg);
   if (use_reg) obj_old += reg_eval<G, R>(rcode, rp, x, lg, k);
 
   double alpha = A.alpha[unit];
@@ -699,19 +747,21 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
       reg_prox<G, R>(rcode, rp, xn, lg, k, stepsize);                    // :142
       double obj_new;
       if constexpr (G <= 8) {                       // shared-memory transposed reduction (k <= 64)
-        obj_new = trial_pass<G, R, W, LOSS, TileCfg<R>::TRIAL_DEPTH>(
-            A, start, len, warp, lane, xn, ucode, us, up1, up2,
+        obj_new = trial_pass<G, R, WT, LOSS, TileCfg<R>::TRIAL_DEPTH>(
+            A, start, len, gwarp, lane, xn, ucode, us, up1, up2,
             part + (W == 1 ? (threadIdx.x >> 5) : warp) * TRIAL_TILE_DOUBLES(G));
         obj_new = block_sum_obj<W>(obj_new, red, lane, warp);
+        obj_new = cluster_sum_obj<CS>(obj_new, clbuf);
       } else {                                      // wide groups: shuffle-reduced pass
         double2 dummy[R];
-        entry_pass<G, R, W, LOSS, false, DEPTH>(A, start, len, warp, lane, xn, ucode, us, up1, up2, dummy, obj_new);
+        entry_pass<G, R, WT, LOSS, false, DEPTH>(A, start, len, gwarp, lane, xn, ucode, us, up1, up2, dummy, obj_new);
         obj_new = block_sum_obj<W>(obj_new, red, lane, warp);
+        obj_new = cluster_sum_obj<CS>(obj_new, clbuf);
       }
       obj_new += reg_eval<G, R>(rcode, rp, xn, lg, k);
       ++ntrials;
       if (obj_new < obj_old) {                                           // :143 (strict; NaN rejects)
-        if (gid == 0) {
+        if (gid == 0 && crank == 0) {
 #pragma unroll
           for (int r = 0; r < R; ++r) *reinterpret_cast<double2*>(own + 2 * (lg + G * r)) = xn[r];   // :144
         }
@@ -724,7 +774,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
       }
     }
   }
-  if (gid == 0 && lg == 0) {
+  if (gid == 0 && lg == 0 && crank == 0) {
     A.alpha[unit] = alpha;
     A.obj_out[unit] = obj_rec;
     if (ntrials && A.trial_counter) atomicAdd(A.trial_counter, (unsigned long long)ntrials);
@@ -751,6 +801,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32, TileCfg<R>::HEAVY_CT
   __shared__ double part[WARPS_PER_CTA_HEAVY * TRIAL_TILE_DOUBLES(G)];
   __shared__ __align__(16) double xg[4 * G * R];
   process_unit<G, R, WARPS_PER_CTA_HEAVY, LOSS, TileCfg<R>::DEPTH>(A, A.order[blockIdx.x], red, part, xg);
+}
+
+// super-heavy units: a cluster of CLUSTER_CTAS CTAs (8 warps each) per unit
+constexpr int CLUSTER_CTAS = 8;
+template <int G, int R, int LOSS>
+__global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32, TileCfg<R>::HEAVY_CTAS) sweep_cluster_kernel(const SweepArgs A) {
+  __shared__ double red[WARPS_PER_CTA_HEAVY * (G * 2 * R + 1)];
+  __shared__ double part[WARPS_PER_CTA_HEAVY * TRIAL_TILE_DOUBLES(G)];
+  __shared__ __align__(16) double xg[4 * G * R];
+  __shared__ __align__(16) double clbuf[2 + 2 * G * R];
+  process_unit<G, R, WARPS_PER_CTA_HEAVY, LOSS, TileCfg<R>::DEPTH, CLUSTER_CTAS>(A, A.order[blockIdx.x / CLUSTER_CTAS], red, part, xg, clbuf);
 }
 
 // out[0] = sum(v[0..n)) in a fixed order (obj = sum(obj_by_col), proxgrad.jl:205)

@@ -90,7 +90,7 @@ struct Side {
   int32_t* d_idx = nullptr;
   double* d_val = nullptr;
   int32_t* d_order = nullptr;
-  int64_t n_heavy = 0, n_light = 0;
+  int64_t n_cluster = 0, n_heavy = 0, n_light = 0;   // schedule = [cluster tier | CTA tier | warp tier]
   int32_t* d_order_vec = nullptr;   // units that go through vec_sweep_kernel (block columns / all rows of a problem with them)
   int64_t n_vec = 0;
   int32_t* d_reg_code = nullptr;
@@ -112,6 +112,7 @@ struct glrmb200_engine {
   int loss_template = 0;   // 0 generic, else uniform loss code instantiated at compile time
   double uparam[3] = {1, 0, 0};
   int64_t heavy_threshold = 1024;
+  int64_t cluster_threshold = 8192;
   int64_t nnz_rows_total = 0;
   bool obs_full = false;
   bool has_vec = false;              // some column has a vector-valued loss
@@ -187,7 +188,7 @@ static int upload(T** dst, const T* src, size_t count) {
 
 // degree-sorted schedule (heaviest first): LPT order for the tail, and neighbouring warps of a CTA get
 // units of similar length.  `is_vec` (optional) routes units to the vector-loss kernel instead.
-static int build_schedule(Side& S, const int64_t* ptr_global, int64_t heavy_threshold, const std::vector<char>* is_vec = nullptr) {
+static int build_schedule(Side& S, const int64_t* ptr_global, int64_t heavy_threshold, int64_t cluster_threshold, const std::vector<char>* is_vec = nullptr) {
   const int64_t cnt = S.end - S.begin;
   std::vector<int32_t> order, vec;
   order.reserve((size_t)cnt);
@@ -199,9 +200,11 @@ static int build_schedule(Side& S, const int64_t* ptr_global, int64_t heavy_thre
     std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return deg(a) > deg(b); });
     std::stable_sort(vec.begin(), vec.end(), [&](int32_t a, int32_t b) { return deg(a) > deg(b); });
   }
+  S.n_cluster = 0;
+  while (S.n_cluster < (int64_t)order.size() && deg(order[(size_t)S.n_cluster]) >= cluster_threshold) S.n_cluster++;
   S.n_heavy = 0;
-  while (S.n_heavy < (int64_t)order.size() && deg(order[(size_t)S.n_heavy]) >= heavy_threshold) S.n_heavy++;
-  S.n_light = (int64_t)order.size() - S.n_heavy;
+  while (S.n_cluster + S.n_heavy < (int64_t)order.size() && deg(order[(size_t)(S.n_cluster + S.n_heavy)]) >= heavy_threshold) S.n_heavy++;
+  S.n_light = (int64_t)order.size() - S.n_heavy - S.n_cluster;
   S.n_vec = (int64_t)vec.size();
   int rc = upload(&S.d_order, order.data(), order.size());
   if (rc) return rc;
@@ -233,11 +236,30 @@ struct Streams { cudaStream_t main, side; cudaEvent_t fork, join; };
 // the two tiers of a sweep touch disjoint units: the warp tier is forked onto the side stream so it fills the
 // SMs the CTA tier leaves idle in its tail, and joined back before anything else is enqueued
 template <int G, int R, int LOSS>
-static cudaError_t launch_tile(const SweepArgs& A, int64_t n_heavy, int64_t n_light, const Streams& st, int64_t* launches) {
-  const bool both = n_heavy > 0 && n_light > 0 && st.side;
+static cudaError_t launch_tile(const SweepArgs& A0, int64_t n_cluster, int64_t n_heavy, int64_t n_light, const Streams& st, int64_t* launches) {
+  const bool both = (n_heavy > 0 || n_cluster > 0) && n_light > 0 && st.side;
+  SweepArgs A = A0;
+  A.order = A0.order + n_cluster;
   if (both) {
     cudaEventRecord(st.fork, st.main);
     cudaStreamWaitEvent(st.side, st.fork, 0);
+  }
+  if (n_cluster > 0) {                       // super-heavy units first (LPT): a cluster of CTAs per unit
+    SweepArgs K = A0;
+    K.n_units = n_cluster;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_cluster * CLUSTER_CTAS), 1, 1);
+    cfg.blockDim = dim3(WARPS_PER_CTA_HEAVY * 32, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st.main;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER_CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t ce = cudaLaunchKernelEx(&cfg, sweep_cluster_kernel<G, R, LOSS>, K);
+    if (ce != cudaSuccess) return ce;
+    ++*launches;
   }
   if (n_heavy > 0) {
     SweepArgs H = A;
@@ -261,20 +283,21 @@ static cudaError_t launch_tile(const SweepArgs& A, int64_t n_heavy, int64_t n_li
 }
 
 template <int LOSS>
-static cudaError_t launch_loss(int g, int r, const SweepArgs& A, int64_t nh, int64_t nl, const Streams& st, int64_t* launches) {
-#define T(GG, RR) if (g == GG && r == RR) return launch_tile<GG, RR, LOSS>(A, nh, nl, st, launches)
+static cudaError_t launch_loss(int g, int r, const SweepArgs& A, int64_t nc, int64_t nh, int64_t nl, const Streams& st, int64_t* launches) {
+#define T(GG, RR) if (g == GG && r == RR) return launch_tile<GG, RR, LOSS>(A, nc, nh, nl, st, launches)
   T(4, 1); T(8, 1); T(8, 2); T(8, 3); T(8, 4); T(16, 2); T(16, 3); T(16, 4); T(32, 2); T(32, 3); T(32, 4);
 #undef T
   return cudaErrorInvalidValue;
 }
 
-static cudaError_t launch_sweep(const glrmb200_engine* E, const SweepArgs& A, int64_t nh, int64_t nl, int64_t* launches) {
+static cudaError_t launch_sweep(const glrmb200_engine* E, const SweepArgs& A, const Side& S, int64_t* launches) {
+  const int64_t nc = S.n_cluster, nh = S.n_heavy, nl = S.n_light;
   static const bool two_streams = !(getenv("GLRMB200_ONE_STREAM") && atoi(getenv("GLRMB200_ONE_STREAM")));
   const Streams st{E->stream, two_streams ? E->stream2 : nullptr, E->ev_fork, E->ev_join};
   switch (E->loss_template) {
-    case GLRMB200_LOSS_QUAD: return launch_loss<GLRMB200_LOSS_QUAD>(E->tile_g, E->tile_r, A, nh, nl, st, launches);
-    case GLRMB200_LOSS_LOGISTIC: return launch_loss<GLRMB200_LOSS_LOGISTIC>(E->tile_g, E->tile_r, A, nh, nl, st, launches);
-    default: return launch_loss<0>(E->tile_g, E->tile_r, A, nh, nl, st, launches);
+    case GLRMB200_LOSS_QUAD: return launch_loss<GLRMB200_LOSS_QUAD>(E->tile_g, E->tile_r, A, nc, nh, nl, st, launches);
+    case GLRMB200_LOSS_LOGISTIC: return launch_loss<GLRMB200_LOSS_LOGISTIC>(E->tile_g, E->tile_r, A, nc, nh, nl, st, launches);
+    default: return launch_loss<0>(E->tile_g, E->tile_r, A, nc, nh, nl, st, launches);
   }
 }
 
@@ -437,6 +460,8 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   if (E->has_vec && E->tile_r > 2)
     return fail(GLRMB200_E_UNSUPPORTED, "vector-valued losses are supported on the device for k <= 32 this round (k = %lld)", (long long)k);
   if (const char* t = getenv("GLRMB200_HEAVY")) E->heavy_threshold = std::max<long long>(1, atoll(t));
+  if (const char* t = getenv("GLRMB200_CLUSTER")) E->cluster_threshold = std::max<long long>(1, atoll(t));
+  if (E->cluster_threshold < E->heavy_threshold) E->cluster_threshold = E->heavy_threshold;
 
   // ---- observation lists: validation (glrm.jl:63-71, losses.jl:104) ----------------------------
   Side& R = E->rows;
@@ -522,8 +547,8 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
       cudaFree(d_rowmajor);
       cudaFree(d_full);
     }
-    if ((rc = build_schedule(R, nullptr, E->heavy_threshold, E->has_vec ? &all_rows_vec : nullptr))) return rc;
-    if ((rc = build_schedule(C, nullptr, E->heavy_threshold, E->has_vec ? &col_is_vec : nullptr))) return rc;
+    if ((rc = build_schedule(R, nullptr, E->heavy_threshold, E->cluster_threshold, E->has_vec ? &all_rows_vec : nullptr))) return rc;
+    if ((rc = build_schedule(C, nullptr, E->heavy_threshold, E->cluster_threshold, E->has_vec ? &col_is_vec : nullptr))) return rc;
     {
       unsigned long long* d_bad = nullptr;
       CUDA_OK(cudaMalloc((void**)&d_bad, sizeof(unsigned long long)));
@@ -553,7 +578,7 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
       if (r2) return r2;
       if ((r2 = upload(&S.d_idx, idx ? idx + q0 : nullptr, (size_t)S.nnz_local))) return r2;
       if ((r2 = upload(&S.d_val, val ? val + q0 : nullptr, (size_t)S.nnz_local))) return r2;
-      return build_schedule(S, ptr, E->heavy_threshold, E->has_vec ? vecflags : nullptr);
+      return build_schedule(S, ptr, E->heavy_threshold, E->cluster_threshold, E->has_vec ? vecflags : nullptr);
     };
     if ((rc = up_side(R, P->row_ptr, P->row_idx, P->row_val, &all_rows_vec))) return rc;
     if ((rc = up_side(C, P->col_ptr, P->col_idx, P->col_val, &col_is_vec))) return rc;
@@ -697,7 +722,7 @@ static int reduce_to_host(glrmb200_engine* E, const double* v, int64_t n, double
 // objective(glrm, X, Y) on the resident factors: losses over observed_examples + penalties
 static int objective_resident(glrmb200_engine* E, bool include_reg, double* out, int64_t* launches) {
   SweepArgs A = make_args(E, /*x_side=*/false, FLAG_EVAL_ONLY | (include_reg ? 0 : FLAG_NO_REG), INFINITY);
-  cudaError_t ce = launch_sweep(E, A, E->cols.n_heavy, E->cols.n_light, launches);
+  cudaError_t ce = launch_sweep(E, A, E->cols, launches);
   if (ce == cudaSuccess) ce = launch_vec(E, A, false, E->cols, launches);
   if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "objective sweep launch: %s", cudaGetErrorString(ce));
   int rc = allgather_units(E, E->cols.d_obj, E->cols, 1);
@@ -766,7 +791,7 @@ extern "C" int glrmb200_fit_resident(glrmb200_handle E, const glrmb200_params* p
     CUDA_OK(cudaEventRecord(E->ev[0], E->stream));
     for (int inner = 0; inner < prm->inner_iter_X; ++inner) {                  // :117-158
       SweepArgs A = make_args(E, true, 0, prm->min_stepsize);
-      cudaError_t ce = launch_sweep(E, A, E->rows.n_heavy, E->rows.n_light, &prof.x_launches);
+      cudaError_t ce = launch_sweep(E, A, E->rows, &prof.x_launches);
       if (ce == cudaSuccess) ce = launch_vec(E, A, true, E->rows, &prof.x_launches);
       if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "update-X launch: %s", cudaGetErrorString(ce));
     }
@@ -775,7 +800,7 @@ extern "C" int glrmb200_fit_resident(glrmb200_handle E, const glrmb200_params* p
     CUDA_OK(cudaEventRecord(E->ev[2], E->stream));
     for (int inner = 0; inner < prm->inner_iter_Y; ++inner) {                  // :160-203
       SweepArgs A = make_args(E, false, 0, prm->min_stepsize);
-      cudaError_t ce = launch_sweep(E, A, E->cols.n_heavy, E->cols.n_light, &prof.y_launches);
+      cudaError_t ce = launch_sweep(E, A, E->cols, &prof.y_launches);
       if (ce == cudaSuccess) ce = launch_vec(E, A, false, E->cols, &prof.y_launches);
       if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "update-Y launch: %s", cudaGetErrorString(ce));
     }

@@ -231,6 +231,23 @@ def test_heavy_units_cta_path(orc, monkeypatch):
     check(orc, g, lrm.ProxGradParams(max_iter=8))
 
 
+def test_super_heavy_units_cluster_path(orc, monkeypatch):
+    """Force units with >= 16 observations through the 8-CTA thread-block-cluster kernel (DSMEM reductions)."""
+    monkeypatch.setenv("GLRMB200_HEAVY", "8")
+    monkeypatch.setenv("GLRMB200_CLUSTER", "16")
+    A, obs, X0 = small_sparse(seed=26, m=300, n=45, density=0.5)
+    g = lrm.GLRM(A, lrm.QuadLoss(), lrm.QuadReg(0.1), lrm.OneReg(0.05), 4, obs=obs,
+                 X=synth.normal_matrix(27, 1, 4, 300), Y=synth.normal_matrix(27, 2, 4, 45))
+    check(orc, g, lrm.ProxGradParams(max_iter=8))
+    c = synth.config5(scale=5000, k=6, n=8, centroids=4)               # dense: 2000-entry columns, 8-entry rows
+    g = glrm_from_config(c, lrm.QuadLoss(), lrm.UnitOneSparseConstraint(), lrm.ZeroReg())
+    check(orc, g, lrm.ProxGradParams(max_iter=6))
+    Ab, obsb, Xb = small_sparse(seed=28, m=400, n=30, density=0.6, labels="bool")
+    g = lrm.GLRM(Ab, lrm.LogisticLoss(), lrm.NonNegConstraint(), lrm.NonNegConstraint(), 4, obs=obsb, X=Xb,
+                 Y=synth.normal_matrix(29, 3, 4, 30))
+    check(orc, g, lrm.ProxGradParams(max_iter=8))
+
+
 @pytest.mark.parametrize("cfgname", ["C2", "C3"])
 def test_config2_and_3_scaled_twins(orc, cfgname):
     """The /8 twins of BASELINE configs 2 and 3 (17 311 x 3 343, 312 504 obs, k=50), fixed work."""
