@@ -238,6 +238,8 @@ def run_ours(args):
         uid = [lrm.Engine.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         eng.comm_init(uid[0])
+        if not os.environ.get("GLRMB200_NO_PEER"):
+            eng.peer_init(dist)             # fused exchange: peer stores from the update kernels (CUDA IPC over NVLink)
     eng.upload(X0, Y0)
     pw = lrm.ProxGradParams(max_iter=max(args.warmup, 1), abs_tol=0, rel_tol=0)
     pk = lrm.ProxGradParams(max_iter=args.steps, abs_tol=0, rel_tol=0)
@@ -307,6 +309,8 @@ def run_ours(args):
         uid = [lrm.Engine.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         eng2.comm_init(uid[0])
+        if not os.environ.get("GLRMB200_NO_PEER"):
+            eng2.peer_init(dist)
     obj2, _ = eng2.fit(pk, Xh, Yh)
     eng2.close()
     barrier()
@@ -330,7 +334,10 @@ def run_ours(args):
         "config": {"workload": workload_name(args.config, args.scale, g, nnz),
                    "l2": "inputs larger than L2 (CSR+CSC index/value streams 480 MB + factors 66 MB vs 126 MB L2); "
                          "no explicit flush",
-                   "parallelism": f"rows/columns sharded over {world} GPU(s), NCCL all-gather per half-iteration",
+                   "parallelism": (f"rows/columns sharded over {world} GPU(s); " + ("single GPU" if world == 1 else
+                                   "NCCL all-gather per half-iteration" if os.environ.get("GLRMB200_NO_PEER") else
+                                   "accepted columns stored into every peer from the update kernels (CUDA IPC over NVLink), "
+                                   "NCCL barrier per half-iteration")),
                    "update_x_ms": x_ms, "update_y_ms": y_ms, "comm_ms": comm_ms,
                    "mean_trials": {"x": T_x, "y": T_y}, "per_rank_ms_x_y_comm_loop": per_rank,
                    "objective_first_last": [float(obj[0]), float(obj[-1])],

@@ -205,6 +205,16 @@ int glrmb200_comm_init(glrmb200_handle h, const uint8_t id[128]);
  * ptr = row_ptr / col_ptr ([count+1]) or NULL (balance by unit count); bounds receives nranks+1 entries. */
 int glrmb200_plan_shards(const int64_t* ptr, int64_t count, int32_t nranks, int64_t* bounds);
 
+/* Fused exchange over NVLink peer memory (optional, after glrmb200_comm_init).  Every rank exports CUDA IPC
+ * handles of its factor replicas (glrmb200_ipc_export, GLRMB200_IPC_BYTES bytes), the host all-gathers the blobs
+ * (rank order) and hands them to glrmb200_ipc_open; from then on the update kernels store every accepted factor
+ * column (and the unit's objective) directly into all peers while the sweep runs, and the per-half-iteration NCCL
+ * all-gather shrinks to a barrier.  glrmb200_comm_barrier must be called by all ranks before glrmb200_destroy. */
+#define GLRMB200_IPC_BYTES 192
+int glrmb200_ipc_export(glrmb200_handle h, uint8_t out[GLRMB200_IPC_BYTES]);
+int glrmb200_ipc_open(glrmb200_handle h, const uint8_t* all_blobs /* nranks * GLRMB200_IPC_BYTES */);
+int glrmb200_comm_barrier(glrmb200_handle h);
+
 /* Row range [row_begin,row_end) and column range [col_begin,col_end) this handle updates
  * (nnz-balanced contiguous shards; whole range when nranks==1). */
 int glrmb200_shard(glrmb200_handle h, int64_t* row_begin, int64_t* row_end,

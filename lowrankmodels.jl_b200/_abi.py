@@ -57,6 +57,9 @@ SYMBOLS = [
     ("glrmb200_create", C.c_int, [C.POINTER(Handle), C.POINTER(Problem), C.c_int32, C.c_int32, C.c_int32]),
     ("glrmb200_comm_unique_id", C.c_int, [C.POINTER(C.c_uint8)]),
     ("glrmb200_comm_init", C.c_int, [Handle, C.POINTER(C.c_uint8)]),
+    ("glrmb200_ipc_export", C.c_int, [Handle, C.POINTER(C.c_uint8)]),
+    ("glrmb200_ipc_open", C.c_int, [Handle, C.POINTER(C.c_uint8)]),
+    ("glrmb200_comm_barrier", C.c_int, [Handle]),
     ("glrmb200_shard", C.c_int, [Handle, c_int64_p, c_int64_p, c_int64_p, c_int64_p]),
     ("glrmb200_fit", C.c_int, [Handle, C.POINTER(Params), c_double_p, c_double_p, c_double_p, c_double_p,
                                 C.c_int32, c_int32_p, C.POINTER(Profile)]),

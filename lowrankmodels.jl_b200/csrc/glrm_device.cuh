@@ -58,6 +58,12 @@ struct SweepArgs {
   double min_stepsize;
   double* obj_out;        // [units_total] recorded objective of the unit (obj_by_col, proxgrad.jl:178,190)
   unsigned long long* trial_counter;  // total line-search trials (profile)
+  // fused exchange (multi-GPU): replicas of `own` / `obj_out` on the peer GPUs, mapped through CUDA IPC.  The
+  // accepted column and the unit's objective are stored straight into every peer over NVLink from the update
+  // kernel, so the all-gather overlaps the sweep and only a barrier remains between half-iterations.
+  double* const* peer_own;   // [n_peers] or nullptr
+  double* const* peer_obj;   // [n_peers] or nullptr
+  int32_t n_peers;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -764,6 +770,14 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
         if (gid == 0 && crank == 0) {
 #pragma unroll
           for (int r = 0; r < R; ++r) *reinterpret_cast<double2*>(own + 2 * (lg + G * r)) = xn[r];   // :144
+          if (A.peer_own) {                                              // same column into every peer's replica
+            const int64_t off = own - A.own;
+            for (int p = 0; p < A.n_peers; ++p) {
+              double* po = A.peer_own[p] + off;
+#pragma unroll
+              for (int r = 0; r < R; ++r) *reinterpret_cast<double2*>(po + 2 * (lg + G * r)) = xn[r];
+            }
+          }
         }
         alpha *= 1.05;                                                   // :145
         obj_rec = obj_new;                                               // :190

@@ -49,6 +49,7 @@ struct NcclApi {
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId_t, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -65,6 +66,7 @@ static int load_nccl() {
   SYM(CommInitRank, "ncclCommInitRank");
   SYM(CommDestroy, "ncclCommDestroy");
   SYM(Broadcast, "ncclBroadcast");
+  SYM(AllReduce, "ncclAllReduce");
   SYM(GroupStart, "ncclGroupStart");
   SYM(GroupEnd, "ncclGroupEnd");
   SYM(GetErrorString, "ncclGetErrorString");
@@ -132,6 +134,13 @@ struct glrmb200_engine {
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   ncclComm_t comm = nullptr;
   bool factors_resident = false;
+  // fused exchange: peers' replicas opened through CUDA IPC (index = position among the other ranks)
+  bool peer_ready = false;
+  std::vector<void*> opened;                 // every pointer returned by cudaIpcOpenMemHandle
+  double** d_peer_X = nullptr;
+  double** d_peer_Y = nullptr;
+  double** d_peer_objc = nullptr;
+  double* d_barrier = nullptr;
 };
 
 static int g_device_checked = -1;
@@ -362,6 +371,9 @@ static SweepArgs make_args(const glrmb200_engine* E, bool x_side, int flags, dou
   A.min_stepsize = min_stepsize;
   A.obj_out = S.d_obj;
   A.trial_counter = E->d_trials + (x_side ? 0 : 1);
+  A.peer_own = E->peer_ready ? (x_side ? E->d_peer_X : E->d_peer_Y) : nullptr;
+  A.peer_obj = (E->peer_ready && !x_side) ? E->d_peer_objc : nullptr;
+  A.n_peers = E->peer_ready ? E->nranks - 1 : 0;
   return A;
 }
 
@@ -387,6 +399,8 @@ extern "C" int glrmb200_destroy(glrmb200_handle E) {
   cudaSetDevice(E->device);
   if (E->stream) cudaStreamSynchronize(E->stream);
   if (E->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(E->comm);
+  for (void* p : E->opened) cudaIpcCloseMemHandle(p);
+  cudaFree(E->d_peer_X); cudaFree(E->d_peer_Y); cudaFree(E->d_peer_objc); cudaFree(E->d_barrier);
   free_side(E->rows); free_side(E->cols);
   cudaFree(E->d_loss_code); cudaFree(E->d_loss_param); cudaFree(E->d_X); cudaFree(E->d_Y); cudaFree(E->d_ystart);
   cudaFree(E->d_scalars); cudaFree(E->d_trials);
@@ -491,6 +505,13 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   }
   R.begin = R.bounds[E->rank]; R.end = R.bounds[E->rank + 1];
   C.begin = C.bounds[E->rank]; C.end = C.bounds[E->rank + 1];
+  if (!getenv("GLRMB200_CLUSTER")) {
+    // a unit goes to the 8-CTA cluster tier only when one CTA working through it alone would outlast the whole
+    // shard's sweep (one CTA ~ half an SM, 148 SMs): degree >= nnz_shard / 256.  On one GPU that is rare by
+    // construction; on 8 GPUs it is what keeps the heaviest columns off the critical path.
+    const int64_t nnz_shard = E->nnz_rows_total / E->nranks;
+    E->cluster_threshold = std::max<int64_t>(8192, nnz_shard / 256);
+  }
 
   // ---- device ---------------------------------------------------------------------------------------
   int rc = check_device();
@@ -666,6 +687,63 @@ extern "C" int glrmb200_shard(glrmb200_handle E, int64_t* rb, int64_t* re, int64
   return 0;
 }
 
+static int comm_barrier(glrmb200_engine* E) {
+  if (E->nranks == 1) return 0;
+  if (!E->comm) return fail(GLRMB200_E_STATE, "glrmb200_comm_init was not called");
+  if (!E->d_barrier) {
+    CUDA_OK(cudaMalloc((void**)&E->d_barrier, sizeof(double)));
+    CUDA_OK(cudaMemset(E->d_barrier, 0, sizeof(double)));
+  }
+  NCCL_OK(g_nccl.AllReduce(E->d_barrier, E->d_barrier, 1, kNcclDouble, /*ncclSum*/ 0, E->comm, E->stream));
+  return 0;
+}
+
+extern "C" int glrmb200_comm_barrier(glrmb200_handle E) {
+  if (!E) return fail(GLRMB200_E_STATE, "null handle");
+  CUDA_OK(cudaSetDevice(E->device));
+  int rc = comm_barrier(E);
+  if (rc) return rc;
+  CUDA_OK(cudaStreamSynchronize(E->stream));
+  return 0;
+}
+
+extern "C" int glrmb200_ipc_export(glrmb200_handle E, uint8_t out[GLRMB200_IPC_BYTES]) {
+  if (!E || !out) return fail(GLRMB200_E_INVALID, "null argument");
+  CUDA_OK(cudaSetDevice(E->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h[3];
+  CUDA_OK(cudaIpcGetMemHandle(&h[0], E->d_X));
+  CUDA_OK(cudaIpcGetMemHandle(&h[1], E->d_Y));
+  CUDA_OK(cudaIpcGetMemHandle(&h[2], E->cols.d_obj));
+  memcpy(out, h, sizeof(h));
+  return 0;
+}
+
+extern "C" int glrmb200_ipc_open(glrmb200_handle E, const uint8_t* blobs) {
+  if (!E || !blobs) return fail(GLRMB200_E_INVALID, "null argument");
+  if (E->nranks == 1) return 0;
+  if (E->has_vec) return 0;   // block columns keep the NCCL exchange this round
+  CUDA_OK(cudaSetDevice(E->device));
+  std::vector<double*> px, py, po;
+  for (int r = 0; r < E->nranks; ++r) {
+    if (r == E->rank) continue;
+    cudaIpcMemHandle_t h[3];
+    memcpy(h, blobs + (size_t)r * GLRMB200_IPC_BYTES, sizeof(h));
+    void* p[3] = {nullptr, nullptr, nullptr};
+    for (int i = 0; i < 3; ++i) {
+      CUDA_OK(cudaIpcOpenMemHandle(&p[i], h[i], cudaIpcMemLazyEnablePeerAccess));
+      E->opened.push_back(p[i]);
+    }
+    px.push_back((double*)p[0]); py.push_back((double*)p[1]); po.push_back((double*)p[2]);
+  }
+  int rc;
+  if ((rc = upload(&E->d_peer_X, px.data(), px.size()))) return rc;
+  if ((rc = upload(&E->d_peer_Y, py.data(), py.size()))) return rc;
+  if ((rc = upload(&E->d_peer_objc, po.data(), po.size()))) return rc;
+  E->peer_ready = true;
+  return 0;
+}
+
 extern "C" int glrmb200_upload_factors(glrmb200_handle E, const double* X, const double* Y) {
   if (!E || !X || !Y) return fail(GLRMB200_E_INVALID, "null argument");
   CUDA_OK(cudaSetDevice(E->device));
@@ -725,7 +803,7 @@ static int objective_resident(glrmb200_engine* E, bool include_reg, double* out,
   cudaError_t ce = launch_sweep(E, A, E->cols, launches);
   if (ce == cudaSuccess) ce = launch_vec(E, A, false, E->cols, launches);
   if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "objective sweep launch: %s", cudaGetErrorString(ce));
-  int rc = allgather_units(E, E->cols.d_obj, E->cols, 1);
+  int rc = E->peer_ready ? comm_barrier(E) : allgather_units(E, E->cols.d_obj, E->cols, 1);
   if (rc) return rc;
   double total = 0.0;
   if ((rc = reduce_to_host(E, E->cols.d_obj, E->n, &total, launches))) return rc;
@@ -796,7 +874,8 @@ extern "C" int glrmb200_fit_resident(glrmb200_handle E, const glrmb200_params* p
       if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "update-X launch: %s", cudaGetErrorString(ce));
     }
     CUDA_OK(cudaEventRecord(E->ev[1], E->stream));
-    if ((rc = allgather_units(E, E->d_X, E->rows, E->stride))) return rc;
+    if (E->peer_ready) { if ((rc = comm_barrier(E))) return rc; }       // columns already stored into the peers
+    else if ((rc = allgather_units(E, E->d_X, E->rows, E->stride))) return rc;
     CUDA_OK(cudaEventRecord(E->ev[2], E->stream));
     for (int inner = 0; inner < prm->inner_iter_Y; ++inner) {                  // :160-203
       SweepArgs A = make_args(E, false, 0, prm->min_stepsize);
@@ -805,8 +884,11 @@ extern "C" int glrmb200_fit_resident(glrmb200_handle E, const glrmb200_params* p
       if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "update-Y launch: %s", cudaGetErrorString(ce));
     }
     CUDA_OK(cudaEventRecord(E->ev[3], E->stream));
-    if ((rc = allgather_units(E, E->d_Y, E->cols, E->stride, E->has_vec ? E->ystart.data() : nullptr))) return rc;
-    if ((rc = allgather_units(E, E->cols.d_obj, E->cols, 1))) return rc;
+    if (E->peer_ready) { if ((rc = comm_barrier(E))) return rc; }
+    else {
+      if ((rc = allgather_units(E, E->d_Y, E->cols, E->stride, E->has_vec ? E->ystart.data() : nullptr))) return rc;
+      if ((rc = allgather_units(E, E->cols.d_obj, E->cols, 1))) return rc;
+    }
     CUDA_OK(cudaEventRecord(E->ev[4], E->stream));
     double obj = 0.0;
     if ((rc = reduce_to_host(E, E->cols.d_obj, E->n, &obj, &prof.other_launches))) return rc;   // :205

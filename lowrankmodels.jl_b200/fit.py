@@ -40,6 +40,22 @@ class Engine:
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         _abi.check(_abi.lib().glrmb200_comm_init(self.h, buf))
 
+    def peer_init(self, dist):
+        """Fused exchange over NVLink peer memory: all-gather the CUDA IPC blobs (any torch.distributed backend)
+        and open the peers' factor replicas.  Call after comm_init on every rank."""
+        if self.nranks == 1:
+            return
+        buf = (C.c_uint8 * 192)()
+        _abi.check(_abi.lib().glrmb200_ipc_export(self.h, buf))
+        blobs = [None] * self.nranks
+        dist.all_gather_object(blobs, bytes(buf))
+        allb = (C.c_uint8 * (192 * self.nranks)).from_buffer_copy(b"".join(blobs))
+        _abi.check(_abi.lib().glrmb200_ipc_open(self.h, allb))
+        self._collective_close = True
+
+    def barrier(self):
+        _abi.check(_abi.lib().glrmb200_comm_barrier(self.h))
+
     def shard(self):
         v = [C.c_int64() for _ in range(4)]
         _abi.check(_abi.lib().glrmb200_shard(self.h, *[C.byref(x) for x in v]))
@@ -98,6 +114,12 @@ class Engine:
         return ar, ac
 
     def close(self):
+        if self.h and getattr(self, "_collective_close", False):
+            self._collective_close = False
+            try:
+                self.barrier()          # peers must be done storing into this rank's replicas
+            except Exception:
+                pass
         if self.h:
             _abi.lib().glrmb200_destroy(self.h)
             self.h = _abi.Handle()

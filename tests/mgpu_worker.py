@@ -28,14 +28,26 @@ def main():
         ep = lrm.encode_problem(g)
         p = lrm.ProxGradParams(max_iter=6, abs_tol=0, rel_tol=0)
         X, Y = g.X.copy(order="F"), g.Y.copy(order="F")
-        eng = lrm.Engine(ep, device=local, rank=rank, nranks=world)
-        eng.comm_init(D.broadcast_unique_id(dist, rank, lrm.Engine.unique_id))
-        rb, re_, cb, ce = eng.shard()
-        brow, bcol = D.shard_bounds(ep, world)
-        assert (rb, re_, cb, ce) == (brow[rank], brow[rank + 1], bcol[rank], bcol[rank + 1])
-        obj, _ = eng.fit(p, X, Y)
-        ar, ac = eng.stepsizes()
-        eng.close()
+        # two exchange paths: NCCL all-gather per half-iteration, and the fused peer-store epilogue (CUDA IPC)
+        results = []
+        for fused in (False, True):
+            Xf, Yf = g.X.copy(order="F"), g.Y.copy(order="F")
+            eng = lrm.Engine(ep, device=local, rank=rank, nranks=world)
+            eng.comm_init(D.broadcast_unique_id(dist, rank, lrm.Engine.unique_id))
+            if fused:
+                eng.peer_init(dist)
+            rb, re_, cb, ce = eng.shard()
+            brow, bcol = D.shard_bounds(ep, world)
+            assert (rb, re_, cb, ce) == (brow[rank], brow[rank + 1], bcol[rank], bcol[rank + 1])
+            objf, _ = eng.fit(p, Xf, Yf)
+            arf, acf = eng.stepsizes()
+            eng.close()
+            results.append((objf, Xf, Yf, arf, acf))
+        (obj, X, Y, ar, ac), (obj2, X2, Y2, ar2, ac2) = results
+        fused_same = (obj == obj2).all() and (X == X2).all() and (Y == Y2).all() and (ar == ar2).all() and (ac == ac2).all()
+        if rank == 0:
+            print(f"{name}: fused peer-store exchange identical to NCCL exchange = {fused_same}", flush=True)
+            ok = ok and bool(fused_same)
         if rank == 0:
             X1, Y1 = g.X.copy(order="F"), g.Y.copy(order="F")
             with lrm.Engine(ep, device=local) as e1:
