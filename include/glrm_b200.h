@@ -210,7 +210,7 @@ int glrmb200_plan_shards(const int64_t* ptr, int64_t count, int32_t nranks, int6
  * (rank order) and hands them to glrmb200_ipc_open; from then on the update kernels store every accepted factor
  * column (and the unit's objective) directly into all peers while the sweep runs, and the per-half-iteration NCCL
  * all-gather shrinks to a barrier.  glrmb200_comm_barrier must be called by all ranks before glrmb200_destroy. */
-#define GLRMB200_IPC_BYTES 192
+#define GLRMB200_IPC_BYTES 64
 int glrmb200_ipc_export(glrmb200_handle h, uint8_t out[GLRMB200_IPC_BYTES]);
 int glrmb200_ipc_open(glrmb200_handle h, const uint8_t* all_blobs /* nranks * GLRMB200_IPC_BYTES */);
 int glrmb200_comm_barrier(glrmb200_handle h);

@@ -123,6 +123,8 @@ struct glrmb200_engine {
   Side rows, cols;
   int32_t* d_loss_code = nullptr;
   double* d_loss_param = nullptr;
+  double* d_xchg = nullptr;                  // ONE allocation [X | Y | obj_by_col] (>= 2 MiB granule): one IPC handle
+  size_t xchg_bytes = 0;
   double* d_X = nullptr;
   double* d_Y = nullptr;
   double* d_scalars = nullptr;              // [4]
@@ -401,8 +403,9 @@ extern "C" int glrmb200_destroy(glrmb200_handle E) {
   if (E->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(E->comm);
   for (void* p : E->opened) cudaIpcCloseMemHandle(p);
   cudaFree(E->d_peer_X); cudaFree(E->d_peer_Y); cudaFree(E->d_peer_objc); cudaFree(E->d_barrier);
+  E->cols.d_obj = nullptr;   // lives inside d_xchg
   free_side(E->rows); free_side(E->cols);
-  cudaFree(E->d_loss_code); cudaFree(E->d_loss_param); cudaFree(E->d_X); cudaFree(E->d_Y); cudaFree(E->d_ystart);
+  cudaFree(E->d_loss_code); cudaFree(E->d_loss_param); cudaFree(E->d_xchg); cudaFree(E->d_ystart);
   cudaFree(E->d_scalars); cudaFree(E->d_trials);
   if (E->h_pinned) cudaFreeHost(E->h_pinned);
   for (auto& e : E->ev) if (e) cudaEventDestroy(e);
@@ -506,11 +509,13 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   R.begin = R.bounds[E->rank]; R.end = R.bounds[E->rank + 1];
   C.begin = C.bounds[E->rank]; C.end = C.bounds[E->rank + 1];
   if (!getenv("GLRMB200_CLUSTER")) {
-    // a unit goes to the 8-CTA cluster tier only when one CTA working through it alone would outlast the whole
-    // shard's sweep (one CTA ~ half an SM, 148 SMs): degree >= nnz_shard / 256.  On one GPU that is rare by
-    // construction; on 8 GPUs it is what keeps the heaviest columns off the critical path.
+    // a unit goes to the 8-CTA cluster tier when one CTA working through it alone (~half an SM) would take a sizeable
+    // part of the whole shard's sweep on 148 SMs: the whole sweep on one GPU (degree >= nnz/256, rare by
+    // construction — the cluster kernel is ~13 % less efficient per entry, measured), a quarter of it when sharded
+    // (degree >= nnz_shard/1184), where the heaviest columns otherwise become the critical path (measured at N=2, 8).
     const int64_t nnz_shard = E->nnz_rows_total / E->nranks;
-    E->cluster_threshold = std::max<int64_t>(8192, nnz_shard / 256);
+    E->cluster_threshold = E->nranks == 1 ? std::max<int64_t>(8192, nnz_shard / 256)
+                                          : std::max<int64_t>(4096, nnz_shard / 1184);
   }
 
   // ---- device ---------------------------------------------------------------------------------------
@@ -631,14 +636,22 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
     }
   }
 
-  CUDA_OK(cudaMalloc((void**)&E->d_X, (size_t)m * E->stride * sizeof(double)));
-  CUDA_OK(cudaMalloc((void**)&E->d_Y, (size_t)E->d * E->stride * sizeof(double)));
+  {
+    // factors and obj_by_col share one allocation rounded to the 2 MiB allocation granule, so that a single CUDA
+    // IPC handle maps exactly this memory in the peers (small cudaMallocs share granules; handles would alias)
+    const size_t nx = (size_t)m * E->stride, ny = (size_t)E->d * E->stride, no = (size_t)n;
+    const size_t granule = (size_t)2 << 20;
+    E->xchg_bytes = ((nx + ny + no) * sizeof(double) + granule - 1) / granule * granule;
+    CUDA_OK(cudaMalloc((void**)&E->d_xchg, E->xchg_bytes));
+    CUDA_OK(cudaMemset(E->d_xchg, 0, E->xchg_bytes));
+    E->d_X = E->d_xchg;
+    E->d_Y = E->d_X + nx;
+    C.d_obj = E->d_Y + ny;
+  }
   CUDA_OK(cudaMalloc((void**)&R.d_alpha, (size_t)m * sizeof(double)));
   CUDA_OK(cudaMalloc((void**)&C.d_alpha, (size_t)n * sizeof(double)));
   CUDA_OK(cudaMalloc((void**)&R.d_obj, (size_t)m * sizeof(double)));
-  CUDA_OK(cudaMalloc((void**)&C.d_obj, (size_t)n * sizeof(double)));
   CUDA_OK(cudaMemset(R.d_obj, 0, (size_t)m * sizeof(double)));
-  CUDA_OK(cudaMemset(C.d_obj, 0, (size_t)n * sizeof(double)));
   CUDA_OK(cudaMemset(R.d_alpha, 0, (size_t)m * sizeof(double)));
   CUDA_OK(cudaMemset(C.d_alpha, 0, (size_t)n * sizeof(double)));
   return 0;
@@ -711,11 +724,9 @@ extern "C" int glrmb200_ipc_export(glrmb200_handle E, uint8_t out[GLRMB200_IPC_B
   if (!E || !out) return fail(GLRMB200_E_INVALID, "null argument");
   CUDA_OK(cudaSetDevice(E->device));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  cudaIpcMemHandle_t h[3];
-  CUDA_OK(cudaIpcGetMemHandle(&h[0], E->d_X));
-  CUDA_OK(cudaIpcGetMemHandle(&h[1], E->d_Y));
-  CUDA_OK(cudaIpcGetMemHandle(&h[2], E->cols.d_obj));
-  memcpy(out, h, sizeof(h));
+  cudaIpcMemHandle_t h;
+  CUDA_OK(cudaIpcGetMemHandle(&h, E->d_xchg));
+  memcpy(out, &h, sizeof(h));
   return 0;
 }
 
@@ -727,14 +738,15 @@ extern "C" int glrmb200_ipc_open(glrmb200_handle E, const uint8_t* blobs) {
   std::vector<double*> px, py, po;
   for (int r = 0; r < E->nranks; ++r) {
     if (r == E->rank) continue;
-    cudaIpcMemHandle_t h[3];
-    memcpy(h, blobs + (size_t)r * GLRMB200_IPC_BYTES, sizeof(h));
-    void* p[3] = {nullptr, nullptr, nullptr};
-    for (int i = 0; i < 3; ++i) {
-      CUDA_OK(cudaIpcOpenMemHandle(&p[i], h[i], cudaIpcMemLazyEnablePeerAccess));
-      E->opened.push_back(p[i]);
-    }
-    px.push_back((double*)p[0]); py.push_back((double*)p[1]); po.push_back((double*)p[2]);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, blobs + (size_t)r * GLRMB200_IPC_BYTES, sizeof(h));
+    void* base = nullptr;
+    CUDA_OK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    E->opened.push_back(base);
+    double* bx = (double*)base;                       // same layout in every rank: [X | Y | obj_by_col]
+    px.push_back(bx);
+    py.push_back(bx + (E->d_Y - E->d_xchg));
+    po.push_back(bx + (E->cols.d_obj - E->d_xchg));
   }
   int rc;
   if ((rc = upload(&E->d_peer_X, px.data(), px.size()))) return rc;

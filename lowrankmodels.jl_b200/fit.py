@@ -45,11 +45,11 @@ class Engine:
         and open the peers' factor replicas.  Call after comm_init on every rank."""
         if self.nranks == 1:
             return
-        buf = (C.c_uint8 * 192)()
+        buf = (C.c_uint8 * 64)()
         _abi.check(_abi.lib().glrmb200_ipc_export(self.h, buf))
         blobs = [None] * self.nranks
         dist.all_gather_object(blobs, bytes(buf))
-        allb = (C.c_uint8 * (192 * self.nranks)).from_buffer_copy(b"".join(blobs))
+        allb = (C.c_uint8 * (64 * self.nranks)).from_buffer_copy(b"".join(blobs))
         _abi.check(_abi.lib().glrmb200_ipc_open(self.h, allb))
         self._collective_close = True
 
