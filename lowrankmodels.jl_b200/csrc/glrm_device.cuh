@@ -817,8 +817,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32, TileCfg<R>::HEAVY_CT
   process_unit<G, R, WARPS_PER_CTA_HEAVY, LOSS, TileCfg<R>::DEPTH>(A, A.order[blockIdx.x], red, part, xg);
 }
 
-// super-heavy units: a cluster of CLUSTER_CTAS CTAs (8 warps each) per unit
-constexpr int CLUSTER_CTAS = 8;
+// super-heavy units (>= 8192 observations): a cluster of CLUSTER_CTAS CTAs (8 warps each) per unit.  On one GPU this
+// tier costs a few % (per-pass pipeline start-up is amortised over fewer chunks per warp); sharded, it is what keeps
+// the heaviest columns from becoming the critical path of the sweep (measured at N=2 and N=8).
+constexpr int CLUSTER_CTAS = 4;
 template <int G, int R, int LOSS>
 __global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32, TileCfg<R>::HEAVY_CTAS) sweep_cluster_kernel(const SweepArgs A) {
   __shared__ double red[WARPS_PER_CTA_HEAVY * (G * 2 * R + 1)];

@@ -508,15 +508,8 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   }
   R.begin = R.bounds[E->rank]; R.end = R.bounds[E->rank + 1];
   C.begin = C.bounds[E->rank]; C.end = C.bounds[E->rank + 1];
-  if (!getenv("GLRMB200_CLUSTER")) {
-    // a unit goes to the 8-CTA cluster tier when one CTA working through it alone (~half an SM) would take a sizeable
-    // part of the whole shard's sweep on 148 SMs: the whole sweep on one GPU (degree >= nnz/256, rare by
-    // construction — the cluster kernel is ~13 % less efficient per entry, measured), a quarter of it when sharded
-    // (degree >= nnz_shard/1184), where the heaviest columns otherwise become the critical path (measured at N=2, 8).
-    const int64_t nnz_shard = E->nnz_rows_total / E->nranks;
-    E->cluster_threshold = E->nranks == 1 ? std::max<int64_t>(8192, nnz_shard / 256)
-                                          : std::max<int64_t>(4096, nnz_shard / 1184);
-  }
+  // NB: the tier of a unit (warp / CTA / cluster) fixes its reduction tree, so the thresholds are constants of the
+  // unit's degree — never of the rank count — or a sharded fit would stop being bit-identical to the 1-GPU fit.
 
   // ---- device ---------------------------------------------------------------------------------------
   int rc = check_device();

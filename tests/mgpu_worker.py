@@ -47,6 +47,8 @@ def main():
         fused_same = (obj == obj2).all() and (X == X2).all() and (Y == Y2).all() and (ar == ar2).all() and (ac == ac2).all()
         if rank == 0:
             print(f"{name}: fused peer-store exchange identical to NCCL exchange = {fused_same}", flush=True)
+            if not fused_same:
+                print("   obj", np.max(np.abs(obj - obj2)), "X", np.max(np.abs(X - X2)), "Y", np.max(np.abs(Y - Y2)), flush=True)
             ok = ok and bool(fused_same)
         if rank == 0:
             X1, Y1 = g.X.copy(order="F"), g.Y.copy(order="F")
@@ -55,6 +57,9 @@ def main():
                 ar1, ac1 = e1.stepsizes()
             same = (obj == obj1).all() and (X == X1).all() and (Y == Y1).all() and (ar == ar1).all() and (ac == ac1).all()
             print(f"{name}: {world}-GPU vs 1-GPU identical={same} obj_last={obj[-1]:.9e}", flush=True)
+            if not same:
+                print("   obj", np.max(np.abs(obj - obj1)), "X", np.max(np.abs(X - X1)), "Y", np.max(np.abs(Y - Y1)),
+                      "alpha", np.max(np.abs(ar - ar1)), np.max(np.abs(ac - ac1)), flush=True)
             ok = ok and bool(same)
     flag = torch.tensor([1.0 if ok else 0.0])
     dist.broadcast(flag, src=0)

@@ -30,6 +30,8 @@ def test_sharded_fit_is_bit_identical_to_single_gpu(world):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
                         os.path.join(ROOT, "tests", "mgpu_worker.py")], capture_output=True, text=True, timeout=900)
+    open(os.path.join(ROOT, "gpurun_out", f"mgpu_worker_{world}.log"), "w").write(r.stdout + "\n----\n" + r.stderr) \
+        if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("identical=True") == 3
