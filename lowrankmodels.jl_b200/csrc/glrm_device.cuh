@@ -791,8 +791,10 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
   if (gid == 0 && lg == 0 && crank == 0) {
     A.alpha[unit] = alpha;
     A.obj_out[unit] = obj_rec;
+    if (A.peer_obj) for (int p = 0; p < A.n_peers; ++p) A.peer_obj[p][unit] = obj_rec;
     if (ntrials && A.trial_counter) atomicAdd(A.trial_counter, (unsigned long long)ntrials);
   }
+  if (A.peer_own && gid == 0 && crank == 0) __threadfence_system();   // peer stores ordered before this kernel's completion
 }
 
 constexpr int WARPS_PER_CTA_LIGHT = 4;
