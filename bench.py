@@ -306,9 +306,7 @@ def run_ours(args):
     e0 = time.time()
     eng2 = lrm.Engine(ep, device=local, rank=rank, nranks=world, validate=False)
     if world > 1:
-        uid = [lrm.Engine.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        eng2.comm_init(uid[0])
+        eng2.comm_init(None)                # the per-process NCCL communicator is cached inside the library
         if not os.environ.get("GLRMB200_NO_PEER"):
             eng2.peer_init(dist)
     obj2, _ = eng2.fit(pk, Xh, Yh)

@@ -196,8 +196,9 @@ int glrmb200_create(glrmb200_handle* out, const glrmb200_problem* problem,
 
 /* Multi-GPU plumbing (one process per GPU).  Rank 0 calls glrmb200_comm_unique_id and the host
  * side (torch.distributed / Julia Distributed) broadcasts the 128 bytes; every rank then calls
- * glrmb200_comm_init.  The data-path exchange is one all-gather of the freshly updated factor per
- * half-iteration. */
+ * glrmb200_comm_init.  The communicator is cached per process: later handles of the same (rank, nranks, device)
+ * may pass id == NULL to reuse it.  The data-path exchange is one all-gather of the freshly updated factor per
+ * half-iteration, or the fused peer-store exchange below. */
 int glrmb200_comm_unique_id(uint8_t id[128]);
 int glrmb200_comm_init(glrmb200_handle h, const uint8_t id[128]);
 

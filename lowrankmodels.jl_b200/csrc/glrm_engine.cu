@@ -400,7 +400,7 @@ extern "C" int glrmb200_destroy(glrmb200_handle E) {
   if (!E) return 0;
   cudaSetDevice(E->device);
   if (E->stream) cudaStreamSynchronize(E->stream);
-  if (E->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(E->comm);
+  // E->comm is the process-wide cached communicator (glrmb200_comm_init): not destroyed with the handle
   for (void* p : E->opened) cudaIpcCloseMemHandle(p);
   cudaFree(E->d_peer_X); cudaFree(E->d_peer_Y); cudaFree(E->d_peer_objc); cudaFree(E->d_barrier);
   E->cols.d_obj = nullptr;   // lives inside d_xchg
@@ -672,15 +672,31 @@ extern "C" int glrmb200_comm_unique_id(uint8_t id[128]) {
   return 0;
 }
 
+// The communicator is created once per process and cached ("NCCL communicators are created
+// lazily and cached per process"): a second handle of the same (rank, nranks, device) may pass id == NULL to reuse it,
+// so re-fitting callers (cross-validation folds, bench.py's end-to-end leg) do not pay ncclCommInitRank again.
+static ncclComm_t g_comm = nullptr;
+static int g_comm_rank = -1, g_comm_nranks = 0, g_comm_device = -1;
+
 extern "C" int glrmb200_comm_init(glrmb200_handle E, const uint8_t id[128]) {
   if (!E) return fail(GLRMB200_E_STATE, "null handle");
   if (E->nranks == 1) return 0;
   int rc = load_nccl();
   if (rc) return rc;
   CUDA_OK(cudaSetDevice(E->device));
+  if (!id) {
+    if (!g_comm || g_comm_rank != E->rank || g_comm_nranks != E->nranks || g_comm_device != E->device)
+      return fail(GLRMB200_E_STATE, "no cached communicator for rank %d/%d on device %d", E->rank, E->nranks, E->device);
+    E->comm = g_comm;
+    return 0;
+  }
   ncclUniqueId_t u;
   memcpy(u.internal, id, 128);
-  NCCL_OK(g_nccl.CommInitRank(&E->comm, E->nranks, u, E->rank));
+  ncclComm_t c = nullptr;
+  NCCL_OK(g_nccl.CommInitRank(&c, E->nranks, u, E->rank));
+  if (g_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g_comm);
+  g_comm = c; g_comm_rank = E->rank; g_comm_nranks = E->nranks; g_comm_device = E->device;
+  E->comm = c;
   return 0;
 }
 

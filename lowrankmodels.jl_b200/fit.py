@@ -36,8 +36,9 @@ class Engine:
         _abi.check(_abi.lib().glrmb200_comm_unique_id(buf))
         return bytes(buf)
 
-    def comm_init(self, uid: bytes):
-        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+    def comm_init(self, uid: bytes = None):
+        """uid=None reuses the communicator this process created earlier (cached inside the library)."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid) if uid is not None else None
         _abi.check(_abi.lib().glrmb200_comm_init(self.h, buf))
 
     def peer_init(self, dist):
