@@ -262,6 +262,16 @@ def test_config2_and_3_scaled_twins(orc, cfgname):
     assert got["profile"]["x_trials"] >= cfg["m"] * 10 * 0.9
 
 
+def test_config5_scaled_twin_kmeans(orc):
+    """BASELINE config 5 (/64 twin: 156 250 x 128 dense, k=100): QuadLoss, rx = UnitOneSparseConstraint, ry = ZeroReg
+    (src/simple_glrms.jl:29-34).  Exercises the k<=128 tile, 128-entry rows and 156k-entry columns (cluster tier)."""
+    c = synth.config5(scale=64)
+    g = glrm_from_config(c, lrm.QuadLoss(), lrm.UnitOneSparseConstraint(), lrm.ZeroReg())
+    got, want = check(orc, g, lrm.ProxGradParams(max_iter=3, abs_tol=0, rel_tol=0), rtol=1e-6, factors=False)
+    assert_traj_close(got["objective"], want["objective"], SPEC)
+    assert np.isinf(got["objective"][0])                       # random start is infeasible for the one-hot constraint
+
+
 def test_objective_api_and_reg_scale(orc):
     A, obs, X0 = small_sparse(seed=30)
     g = lrm.GLRM(A, lrm.HuberLoss(), lrm.QuadReg(0.3), lrm.OneReg(0.2), 4, obs=obs, X=X0,
