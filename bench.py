@@ -114,7 +114,12 @@ def cpu_reference_run(config, steps, warmup, twin_scale=8, mode=0):
     g, cfg = build_problem(config, twin_scale)
     ep = lrm.encode_problem(g, validate=False)
     nnz = ep.nnz
-    threads = oracle_py.lib().oracle_num_threads()
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1: ignore it for the CPU arm)
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    oracle_py.lib()
     # thread count: the static row/column chunks of Threads.@threads stop scaling past the physical cores on
     # some hosts, so calibrate on one iteration (all threads vs half) and keep the faster setting
     p1 = lrm.ProxGradParams(max_iter=1, abs_tol=0, rel_tol=0)
@@ -305,14 +310,19 @@ def run_ours(args):
     barrier()
     e0 = time.time()
     eng2 = lrm.Engine(ep, device=local, rank=rank, nranks=world, validate=False)
+    e1 = time.time()
     if world > 1:
         eng2.comm_init(None)                # the per-process NCCL communicator is cached inside the library
         if not os.environ.get("GLRMB200_NO_PEER"):
             eng2.peer_init(dist)
+    e2 = time.time()
     obj2, _ = eng2.fit(pk, Xh, Yh)
+    e3 = time.time()
     eng2.close()
+    e4 = time.time()
     barrier()
     e2e_s = max_over_ranks(time.time() - e0)
+    log(f"[rank {rank}] e2e breakdown: create {e1 - e0:.3f}s, comm+peer {e2 - e1:.3f}s, fit {e3 - e2:.3f}s, close {e4 - e3:.3f}s")
     prob_bytes = sum(v.nbytes for name, v in ep.keep.items() if isinstance(v, np.ndarray))
     fac_bytes = (g.X.nbytes + g.Y.nbytes)
     e2e = {"value": nnz / (e2e_s / args.steps), "unit": UNIT,
