@@ -162,6 +162,15 @@ typedef struct glrmb200_params {
   double  min_stepsize;  /* line-search floor                     (default 0.01*stepsize)      */
 } glrmb200_params;
 
+/* ---- SparseProxGradParams (src/algorithms/sparse_proxgrad.jl:4-18), same five fields ------------- */
+typedef struct glrmb200_sparse_params {
+  double  stepsize;      /* initial (global) step size                  (default 1.0)              */
+  int32_t max_iter;      /* outer iterations                            (default 100)              */
+  int32_t inner_iter;    /* prox-grad steps on X, then on Y, per iter   (default 1)                */
+  double  abs_tol;       /* stop if decrease < abs_tol * |Omega|        (default 1e-5)             */
+  double  min_stepsize;  /* stop when the step size falls to this       (default 0.01*stepsize)    */
+} glrmb200_sparse_params;
+
 /* per-fit device timings (CUDA events on the engine's own stream), all in milliseconds         */
 typedef struct glrmb200_profile {
   double  setup_ms;        /* H2D of X,Y + initial objective                                   */
@@ -235,6 +244,17 @@ int glrmb200_fit(glrmb200_handle h, const glrmb200_params* params,
                  double* X, double* Y,
                  double* ch_objective, double* ch_seconds, int32_t cap, int32_t* n_recorded,
                  glrmb200_profile* profile);
+
+/* glrmb200_fit_sparse: fit!(glrm, ::SparseProxGradParams) of src/algorithms/sparse_proxgrad.jl:21-130 — what plain
+ * `fit!(glrm)` selects for a SparseMatrixCSC (src/fit.jl:13-15) — on the same kernels: unconditional prox-gradient
+ * sweeps with one global step size (:62-99), the full sparse objective (:102), accept (alpha*1.05, keep) or revert
+ * (alpha / max(1.5, -steps_in_a_row)) (:104-117), stop rule (:119).  Scalar-embedding losses only, as in the
+ * reference.  X, Y in/out: on return they hold the best model found (glrm.X / glrm.Y).  ch_* as the reference
+ * records them: entry 0 the initial objective, one entry per ACCEPTED iteration, and the final duplicate (:126);
+ * cap >= max_iter + 2. */
+int glrmb200_fit_sparse(glrmb200_handle h, const glrmb200_sparse_params* params, double* X, double* Y,
+                        double* ch_objective, double* ch_seconds, int32_t cap, int32_t* n_recorded,
+                        glrmb200_profile* profile);
 
 /* glrmb200_objective: objective(glrm, X, Y; include_regularization) of src/evaluate_fit.jl:57-83
  * (loss summed over observed_examples, then calc_penalty :91-104), evaluated on observed entries

@@ -11,13 +11,13 @@ from .losses import (BvSLoss, ClassificationLoss, DiffLoss, HingeLoss, HuberLoss
                      Loss, MultinomialLoss, MultinomialOrdinalLoss, OrdinalHingeLoss, OrdisticLoss,
                      OvALoss, PeriodicLoss, PoissonLoss, QuadLoss, QuantileLoss, WeightedHingeLoss,
                      embedding_dim, get_yidxs)
-from .params import AbstractParams, B200ProxGradParams, Params, ProxGradParams
+from .params import AbstractParams, B200ProxGradParams, Params, ProxGradParams, SparseProxGradParams
 from .regularizers import (KSparseConstraint, MNLOrdinalReg, NonNegConstraint, NonNegOneReg, OneReg,
                            OneSparseConstraint, OrdinalReg, QuadConstraint, QuadReg, Regularizer,
                            RemQuadReg, SimplexConstraint, UnitOneSparseConstraint, ZeroReg,
                            fixed_last_latent_features, fixed_latent_features, lastentry1,
                            lastentry_unpenalized)
-from .encode import encode_params, encode_problem
+from .encode import encode_params, encode_problem, encode_sparse_params
 from . import _abi, distributed, synth
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -34,6 +34,11 @@ class Params(C.Structure):
     ]
 
 
+class SparseParams(C.Structure):
+    _fields_ = [("stepsize", C.c_double), ("max_iter", C.c_int32), ("inner_iter", C.c_int32),
+                ("abs_tol", C.c_double), ("min_stepsize", C.c_double)]
+
+
 class Profile(C.Structure):
     _fields_ = [
         ("setup_ms", C.c_double), ("update_x_ms", C.c_double), ("update_y_ms", C.c_double),
@@ -63,6 +68,8 @@ SYMBOLS = [
     ("glrmb200_shard", C.c_int, [Handle, c_int64_p, c_int64_p, c_int64_p, c_int64_p]),
     ("glrmb200_fit", C.c_int, [Handle, C.POINTER(Params), c_double_p, c_double_p, c_double_p, c_double_p,
                                 C.c_int32, c_int32_p, C.POINTER(Profile)]),
+    ("glrmb200_fit_sparse", C.c_int, [Handle, C.POINTER(SparseParams), c_double_p, c_double_p, c_double_p, c_double_p,
+                                       C.c_int32, c_int32_p, C.POINTER(Profile)]),
     ("glrmb200_objective", C.c_int, [Handle, c_double_p, c_double_p, C.c_int32, c_double_p]),
     ("glrmb200_set_reg_scale", C.c_int, [Handle, C.c_double]),
     ("glrmb200_upload_factors", C.c_int, [Handle, c_double_p, c_double_p]),

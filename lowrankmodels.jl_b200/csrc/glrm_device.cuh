@@ -29,7 +29,7 @@ namespace glrm {
 
 constexpr unsigned FULLMASK = 0xffffffffu;
 #define TRIAL_TILE_DOUBLES(G) ((G) <= 8 ? 2 * 32 * ((G) + 1) : 1)   /* two [32][G+1] partial-dot tiles per warp (narrow groups only) */
-enum : int { FLAG_EVAL_ONLY = 1, FLAG_NO_REG = 2, FLAG_LOSS_BY_ENTRY = 4 };
+enum : int { FLAG_EVAL_ONLY = 1, FLAG_NO_REG = 2, FLAG_LOSS_BY_ENTRY = 4, FLAG_UNCONDITIONAL = 8 };
 
 struct SweepArgs {
   // observation lists of this side (shard-local), see glrm_b200.h
@@ -56,6 +56,8 @@ struct SweepArgs {
   int32_t flags;
   double* alpha;          // [units_total] step sizes (alpharow / alphacol, proxgrad.jl:69-70)
   double min_stepsize;
+  double global_alpha;    // FLAG_UNCONDITIONAL (SparseProxGradParams, sparse_proxgrad.jl:62-99): one shared step size,
+                          // the prox-gradient step is taken without a line search
   double* obj_out;        // [units_total] recorded objective of the unit (obj_by_col, proxgrad.jl:178,190)
   unsigned long long* trial_counter;  // total line-search trials (profile)
   // fused exchange (multi-GPU): replicas of `own` / `obj_out` on the peer GPUs, mapped through CUDA IPC.  The
@@ -726,10 +728,11 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
   cluster_sum_g<G, R, CS>(g, reinterpret_cast<double2*>(clbuf + 2), gid, lg);
   if (use_reg) obj_old += reg_eval<G, R>(rcode, rp, x, lg, k);
 
-  double alpha = A.alpha[unit];
+  const bool uncond = A.flags & FLAG_UNCONDITIONAL;
+  double alpha = uncond ? A.global_alpha : A.alpha[unit];
   double obj_rec = obj_old;
   int ntrials = 0;
-  if (!(A.flags & FLAG_EVAL_ONLY) && alpha > A.min_stepsize) {
+  if (!(A.flags & FLAG_EVAL_ONLY) && (uncond || alpha > A.min_stepsize)) {
     // x and g are only needed to form trial points: park them in shared memory so the trial passes can
     // spend the registers on a deeper gather pipeline
     double2* xs = reinterpret_cast<double2*>(xg);
@@ -742,7 +745,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
     }
     if (W > 1) __syncthreads(); else __syncwarp();
     const double l1 = (double)(len + 1);                                 // proxgrad.jl:134
-    while (alpha > A.min_stepsize) {                                     // :136
+    while (uncond || alpha > A.min_stepsize) {                           // :136
       const double stepsize = alpha / l1;                                // :137
       double2 xn[R];
 #pragma unroll
@@ -751,6 +754,21 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
         xn[r].x = fma(-stepsize, gr.x, xr.x); xn[r].y = fma(-stepsize, gr.y, xr.y);                   // :140
       }
       reg_prox<G, R>(rcode, rp, xn, lg, k, stepsize);                    // :142
+      if (uncond) {                                                      // sparse_proxgrad.jl:73-78 / :93-98: no trial
+        if (gid == 0 && crank == 0) {
+          const int64_t off = own - A.own;
+#pragma unroll
+          for (int r = 0; r < R; ++r) *reinterpret_cast<double2*>(own + 2 * (lg + G * r)) = xn[r];
+          if (A.peer_own) {
+            for (int p = 0; p < A.n_peers; ++p) {
+              double* po = A.peer_own[p] + off;
+#pragma unroll
+              for (int r = 0; r < R; ++r) *reinterpret_cast<double2*>(po + 2 * (lg + G * r)) = xn[r];
+            }
+          }
+        }
+        break;
+      }
       double obj_new;
       if constexpr (G <= 8) {                       // shared-memory transposed reduction (k <= 64)
         obj_new = trial_pass<G, R, WT, LOSS, TileCfg<R>::TRIAL_DEPTH>(
@@ -789,7 +807,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
     }
   }
   if (gid == 0 && lg == 0 && crank == 0) {
-    A.alpha[unit] = alpha;
+    if (!uncond) A.alpha[unit] = alpha;
     A.obj_out[unit] = obj_rec;
     if (A.peer_obj) for (int p = 0; p < A.n_peers; ++p) A.peer_obj[p][unit] = obj_rec;
     if (ntrials && A.trial_counter) atomicAdd(A.trial_counter, (unsigned long long)ntrials);

@@ -372,6 +372,7 @@ static SweepArgs make_args(const glrmb200_engine* E, bool x_side, int flags, dou
   A.flags = flags | ((x_side && E->loss_template == 0) ? FLAG_LOSS_BY_ENTRY : 0);
   A.alpha = S.d_alpha;
   A.min_stepsize = min_stepsize;
+  A.global_alpha = 0.0;
   A.obj_out = S.d_obj;
   A.trial_counter = E->d_trials + (x_side ? 0 : 1);
   A.peer_own = E->peer_ready ? (x_side ? E->d_peer_X : E->d_peer_Y) : nullptr;
@@ -996,6 +997,87 @@ extern "C" int glrmb200_fit(glrmb200_handle E, const glrmb200_params* prm, doubl
   int rc = glrmb200_upload_factors(E, X, Y);
   if (rc) return rc;
   if ((rc = glrmb200_fit_resident(E, prm, ch_objective, ch_seconds, cap, n_recorded, profile))) return rc;
+  return glrmb200_download_factors(E, X, Y);
+}
+
+extern "C" int glrmb200_fit_sparse(glrmb200_handle E, const glrmb200_sparse_params* prm, double* X, double* Y,
+                                   double* ch_objective, double* ch_seconds, int32_t cap, int32_t* n_recorded,
+                                   glrmb200_profile* profile) {
+  if (!E || !prm || !X || !Y || !ch_objective || !ch_seconds || !n_recorded) return fail(GLRMB200_E_INVALID, "null argument");
+  if (E->has_vec) return fail(GLRMB200_E_UNSUPPORTED, "SparseProxGradParams handles scalar-embedding losses only (sparse_proxgrad.jl:70 uses dot(x_e, y_f))");
+  if (cap < prm->max_iter + 2) return fail(GLRMB200_E_INVALID, "cap %d < max_iter+2", cap);
+  if (prm->inner_iter < 1) return fail(GLRMB200_E_INVALID, "inner_iter must be >= 1");
+  bool allzero = true;
+  for (int64_t i = 0; i < E->k * E->d && allzero; ++i) allzero = (Y[i] == 0.0);
+  if (allzero) return fail(GLRMB200_E_INVALID, "norm(Y) == 0: the solver would never move (sparse_proxgrad.jl:37-40)");
+  int rc = glrmb200_upload_factors(E, X, Y);                      // working copies X, Y (:33)
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(E->device));
+  using clk = std::chrono::steady_clock;
+  glrmb200_profile prof;
+  memset(&prof, 0, sizeof(prof));
+  // best-so-far factors (glrm.X / glrm.Y in the reference) live next to the working copies on the device
+  const size_t fac_doubles = (size_t)(E->m + E->d) * E->stride;   // X and Y are contiguous inside d_xchg
+  double* d_best = nullptr;
+  CUDA_OK(cudaMalloc((void**)&d_best, fac_doubles * sizeof(double)));
+  CUDA_OK(cudaMemcpyAsync(d_best, E->d_X, fac_doubles * sizeof(double), cudaMemcpyDeviceToDevice, E->stream));
+  auto cleanup = [&]() { cudaStreamSynchronize(E->stream); cudaFree(d_best); };
+
+  double alpha = prm->stepsize;                                                   // :44
+  const double tol = prm->abs_tol * (double)E->nnz_rows_total;                    // :46
+  int nrec = 0;
+  double obj0 = 0.0;
+  if ((rc = objective_resident(E, true, &obj0, &prof.other_launches))) { cleanup(); return rc; }   // :50
+  ch_objective[nrec] = obj0; ch_seconds[nrec++] = 0.0;
+  auto t = clk::now();
+  const auto t_loop = t;
+  int steps_in_a_row = 0;
+  for (int it = 1; it <= prm->max_iter; ++it) {                                   // :60
+    for (int side = 0; side < 2; ++side) {                                        // X update :62-79, Y update :83-99
+      const bool xs = side == 0;
+      Side& S = xs ? E->rows : E->cols;
+      for (int inner = 0; inner < prm->inner_iter; ++inner) {
+        SweepArgs A = make_args(E, xs, FLAG_UNCONDITIONAL, 0.0);
+        A.global_alpha = alpha;
+        cudaError_t ce = launch_sweep(E, A, S, xs ? &prof.x_launches : &prof.y_launches);
+        if (ce != cudaSuccess) { cleanup(); return fail(GLRMB200_E_CUDA, "sparse sweep launch: %s", cudaGetErrorString(ce)); }
+      }
+      if (E->peer_ready) rc = comm_barrier(E);
+      else rc = allgather_units(E, xs ? E->d_X : E->d_Y, S, E->stride);
+      if (rc) { cleanup(); return rc; }
+    }
+    double obj = 0.0;
+    if ((rc = objective_resident(E, true, &obj, &prof.other_launches))) { cleanup(); return rc; }   // :102
+    prof.iterations = it;
+    if (obj < ch_objective[nrec - 1]) {                                           // :104
+      const auto now = clk::now();
+      ch_objective[nrec] = obj;
+      ch_seconds[nrec++] = std::chrono::duration<double>(now - t).count();        // :105-106
+      CUDA_OK(cudaMemcpyAsync(d_best, E->d_X, fac_doubles * sizeof(double), cudaMemcpyDeviceToDevice, E->stream));   // :107
+      alpha = alpha * 1.05;                                                       // :108
+      steps_in_a_row = std::max(1, steps_in_a_row + 1);                           // :109
+      t = clk::now();
+    } else {
+      alpha = alpha / std::max(1.5, (double)(-steps_in_a_row));                   // :113
+      CUDA_OK(cudaMemcpyAsync(E->d_X, d_best, fac_doubles * sizeof(double), cudaMemcpyDeviceToDevice, E->stream));   // :115
+      // with the fused exchange the peers store into this replica during their next sweep: they must not start
+      // before the revert has landed
+      if (E->peer_ready && (rc = comm_barrier(E))) { cleanup(); return rc; }
+      steps_in_a_row = std::min(0, steps_in_a_row - 1);                           // :116
+    }
+    // :119  i>10 && (steps_in_a_row > 3 && ch.objective[end-1] - obj < tol) || alpha <= min_stepsize
+    const double prev = nrec >= 2 ? ch_objective[nrec - 2] : INFINITY;
+    if ((it > 10 && (steps_in_a_row > 3 && prev - obj < tol)) || alpha <= prm->min_stepsize) break;
+  }
+  ch_objective[nrec] = ch_objective[nrec - 1];                                    // :125-126
+  ch_seconds[nrec] = std::chrono::duration<double>(clk::now() - t).count();
+  ++nrec;
+  prof.loop_ms = std::chrono::duration<double, std::milli>(clk::now() - t_loop).count();
+  // hand back the best model: working copies <- best, then the usual download
+  CUDA_OK(cudaMemcpyAsync(E->d_X, d_best, fac_doubles * sizeof(double), cudaMemcpyDeviceToDevice, E->stream));
+  cleanup();
+  *n_recorded = nrec;
+  if (profile) *profile = prof;
   return glrmb200_download_factors(E, X, Y);
 }
 

@@ -127,3 +127,7 @@ def encode_problem(glrm: GLRM, validate=True) -> EncodedProblem:
 def encode_params(p) -> _abi.Params:
     return _abi.Params(p.stepsize, p.max_iter, p.inner_iter_X, p.inner_iter_Y, p.abs_tol, p.rel_tol,
                        p.min_stepsize)
+
+
+def encode_sparse_params(p) -> _abi.SparseParams:
+    return _abi.SparseParams(p.stepsize, p.max_iter, p.inner_iter, p.abs_tol, p.min_stepsize)

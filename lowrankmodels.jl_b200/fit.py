@@ -12,9 +12,9 @@ import numpy as np
 
 from . import _abi
 from .convergence import ConvergenceHistory, update_ch
-from .encode import EncodedProblem, encode_params, encode_problem
+from .encode import EncodedProblem, encode_params, encode_problem, encode_sparse_params
 from .glrm import GLRM
-from .params import ProxGradParams
+from .params import ProxGradParams, SparseProxGradParams
 
 
 class Engine:
@@ -87,6 +87,20 @@ class Engine:
         assert X.shape == (self.k, self.m) and Y.shape == (self.k, self.d)
         return self._run(params, X, Y, resident=False)
 
+    def fit_sparse(self, params, X, Y):
+        """fit!(glrm, ::SparseProxGradParams) on the engine: X, Y in/out (best model found).  Returns (objective, seconds)
+        exactly as the reference records them (initial, one per accepted iteration, final duplicate)."""
+        assert X.flags.f_contiguous and Y.flags.f_contiguous and X.dtype == np.float64 == Y.dtype
+        cap = params.max_iter + 2
+        obj, sec = np.zeros(cap), np.zeros(cap)
+        nrec = C.c_int32(0)
+        prof = _abi.Profile()
+        prm = encode_sparse_params(params)
+        _abi.check(_abi.lib().glrmb200_fit_sparse(self.h, C.byref(prm), _abi.dptr(X), _abi.dptr(Y), _abi.dptr(obj),
+                                                  _abi.dptr(sec), cap, C.byref(nrec), C.byref(prof)))
+        self.last_profile = prof.as_dict()
+        return obj[:nrec.value], sec[:nrec.value]
+
     def upload(self, X, Y):
         assert X.flags.f_contiguous and Y.flags.f_contiguous
         _abi.check(_abi.lib().glrmb200_upload_factors(self.h, _abi.dptr(X), _abi.dptr(Y)))
@@ -143,8 +157,8 @@ def fit_inplace(glrm: GLRM, params: ProxGradParams = None, *, ch: ConvergenceHis
     """`fit!(glrm, params; ch, verbose)`: mutates glrm.X / glrm.Y in place and returns
     (glrm.X, glrm.Y, ch) (proxgrad.jl:34-37,43,219); appends to a caller-supplied `ch`
     (cross_validate.jl:174); warm-starts from the current factors."""
-    if params is None:
-        params = ProxGradParams()                                               # fit.jl:17-18
+    if params is None:                                                          # fit.jl:13-19
+        params = SparseProxGradParams() if glrm._sparse else ProxGradParams()
     if ch is None:
         ch = ConvergenceHistory("B200ProxGradGLRM")
     own = engine is None
@@ -153,7 +167,10 @@ def fit_inplace(glrm: GLRM, params: ProxGradParams = None, *, ch: ConvergenceHis
     try:
         if verbose:
             print("Fitting GLRM")                                              # proxgrad.jl:75
-        obj, sec = engine.fit(params, glrm.X, glrm.Y)
+        if isinstance(params, SparseProxGradParams):
+            obj, sec = engine.fit_sparse(params, glrm.X, glrm.Y)
+        else:
+            obj, sec = engine.fit(params, glrm.X, glrm.Y)
         for i, (o, s) in enumerate(zip(obj, sec)):
             update_ch(ch, s, o)                                                # proxgrad.jl:76,207
             if verbose and i > 0 and i % 10 == 0:

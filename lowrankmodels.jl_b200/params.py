@@ -39,3 +39,16 @@ class B200ProxGradParams(ProxGradParams):
 
 def Params(*args, **kwargs):  # fit.jl:5
     return ProxGradParams(*args, **kwargs)
+
+
+class SparseProxGradParams(AbstractParams):
+    """Mirror of /root/reference/src/algorithms/sparse_proxgrad.jl:4-18 (five fields, same defaults)."""
+
+    def __init__(self, stepsize=1.0, *, max_iter=100, inner_iter=1, abs_tol=0.00001, min_stepsize=None, device=0):
+        stepsize = float(stepsize)
+        self.stepsize = stepsize
+        self.max_iter = int(max_iter)
+        self.inner_iter = int(inner_iter)
+        self.abs_tol = float(abs_tol)
+        self.min_stepsize = float(0.01 * stepsize if min_stepsize is None else min_stepsize)
+        self.device = int(device)

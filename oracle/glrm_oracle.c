@@ -947,6 +947,97 @@ int oracle_half_sweep(const glrmb200_problem* P, const glrmb200_params* prm, dou
   return err;
 }
 
+/* fit!(glrm, ::SparseProxGradParams) — /root/reference/src/algorithms/sparse_proxgrad.jl:21-130.
+ * sp = {stepsize, max_iter, inner_iter, abs_tol, min_stepsize} (the struct of include/glrm_b200.h).
+ * X, Y in/out (the best model, like glrm.X / glrm.Y); scalar-embedding losses only (the reference uses dot(x_e,y_f)).
+ * cap >= max_iter + 2.  returns 0 or an error code as oracle_fit. */
+int oracle_fit_sparse(const glrmb200_problem* P, const glrmb200_sparse_params* sp, double* Xbest, double* Ybest,
+                      double* ch_objective, double* ch_seconds, int32_t cap, int32_t* n_recorded, double* alpha_out) {
+  view_t V;
+  if (view_init(&V, P)) return 4;
+  if (cap < sp->max_iter + 2 || V.d != V.n) { view_free(&V); return 5; }
+  const int64_t m = V.m, n = V.n, k = V.k;
+  int err = 0;
+  double* X = (double*)malloc(sizeof(double) * (size_t)(k * m));
+  double* Y = (double*)malloc(sizeof(double) * (size_t)(k * n));
+  memcpy(X, Xbest, sizeof(double) * (size_t)(k * m));                          /* :33 */
+  memcpy(Y, Ybest, sizeof(double) * (size_t)(k * n));
+  double alpha = sp->stepsize;                                                 /* :44 */
+  const double tol = sp->abs_tol * (double)V.nnz_rows;                         /* :46 */
+  int nrec = 0;
+  ch_objective[nrec] = full_objective(&V, Xbest, Ybest, 1, &err);             /* :50 */
+  ch_seconds[nrec++] = 0.0;
+  double t = now_s();
+  int steps_in_a_row = 0;
+  double* g = (double*)malloc(sizeof(double) * (size_t)k);
+  for (int i = 1; i <= sp->max_iter; ++i) {                                    /* :60 */
+    for (int inner = 0; inner < sp->inner_iter; ++inner) {                     /* :62 */
+      for (int64_t e = 0; e < m; ++e) {                                        /* :63 */
+        double* xe = X + e * k;
+        for (int64_t r = 0; r < k; ++r) g[r] *= 0;                             /* :64 */
+        for (int64_t r = 0; r < k; ++r) g[r] = 0.0;
+        const int64_t len = row_len(&V, e);
+        for (int64_t q = 0; q < len; ++q) {                                    /* :67-72 */
+          int64_t f; double a;
+          row_entry(&V, e, q, &f, &a);
+          const double* yf = Y + f * k;
+          const double c = sl_grad(P->loss_code[f], P->loss_param + f * GLRMB200_LOSS_NPARAM, dotk(xe, yf, k), a, &err);
+          for (int64_t r = 0; r < k; ++r) g[r] += c * yf[r];
+        }
+        const double l = (double)(len + 1);                                    /* :74 */
+        for (int64_t r = 0; r < k; ++r) g[r] *= -alpha / l;                    /* :75 */
+        for (int64_t r = 0; r < k; ++r) xe[r] += g[r];                         /* :77 */
+        reg_prox(*rx_code(&V, e), rx_par(&V, e), xe, k, 1, alpha / l);         /* :79 */
+      }
+    }
+    for (int inner = 0; inner < sp->inner_iter; ++inner) {                     /* :83 */
+      for (int64_t f = 0; f < n; ++f) {                                        /* :84 */
+        double* yf = Y + f * k;
+        for (int64_t r = 0; r < k; ++r) g[r] = 0.0;                            /* :85 */
+        const int64_t len = col_len(&V, f);
+        for (int64_t q = 0; q < len; ++q) {                                    /* :88-92 */
+          int64_t e; double a;
+          col_entry(&V, f, q, &e, &a);
+          const double* xe = X + e * k;
+          const double c = sl_grad(P->loss_code[f], P->loss_param + f * GLRMB200_LOSS_NPARAM, dotk(xe, yf, k), a, &err);
+          for (int64_t r = 0; r < k; ++r) g[r] += c * xe[r];
+        }
+        const double l = (double)(len + 1);                                    /* :94 */
+        for (int64_t r = 0; r < k; ++r) g[r] *= -alpha / l;                    /* :95 */
+        for (int64_t r = 0; r < k; ++r) yf[r] += g[r];                         /* :97 */
+        reg_prox(*ry_code(&V, f), ry_par(&V, f), yf, k, 1, alpha / l);         /* :99 */
+      }
+    }
+    const double obj = full_objective(&V, X, Y, 1, &err);                      /* :102 */
+    if (obj < ch_objective[nrec - 1]) {                                        /* :104 */
+      const double now = now_s();
+      ch_objective[nrec] = obj;
+      ch_seconds[nrec++] = now - t;                                            /* :105-106 */
+      memcpy(Xbest, X, sizeof(double) * (size_t)(k * m));                      /* :107 */
+      memcpy(Ybest, Y, sizeof(double) * (size_t)(k * n));
+      alpha = alpha * 1.05;                                                    /* :108 */
+      steps_in_a_row = steps_in_a_row + 1 > 1 ? steps_in_a_row + 1 : 1;        /* :109 */
+      t = now_s();
+    } else {
+      const double div = (double)(-steps_in_a_row) > 1.5 ? (double)(-steps_in_a_row) : 1.5;
+      alpha = alpha / div;                                                     /* :113 */
+      memcpy(X, Xbest, sizeof(double) * (size_t)(k * m));                      /* :115 */
+      memcpy(Y, Ybest, sizeof(double) * (size_t)(k * n));
+      steps_in_a_row = steps_in_a_row - 1 < 0 ? steps_in_a_row - 1 : 0;        /* :116 */
+    }
+    const double prev = nrec >= 2 ? ch_objective[nrec - 2] : INFINITY;
+    if ((i > 10 && (steps_in_a_row > 3 && prev - obj < tol)) || alpha <= sp->min_stepsize) break;   /* :119 */
+  }
+  ch_objective[nrec] = ch_objective[nrec - 1];                                 /* :125-126 */
+  ch_seconds[nrec] = now_s() - t;
+  ++nrec;
+  *n_recorded = nrec;
+  if (alpha_out) *alpha_out = alpha;
+  free(g); free(X); free(Y);
+  view_free(&V);
+  return err;
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

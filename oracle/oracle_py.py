@@ -40,6 +40,8 @@ def lib():
                                  C.POINTER(C.c_int32), C.c_int32, C.c_int32, _dp, _dp,
                                  C.POINTER(C.c_int64)]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_fit_sparse.restype = C.c_int
+        L.oracle_fit_sparse.argtypes = [C.c_void_p, C.c_void_p, _dp, _dp, _dp, _dp, C.c_int32, C.POINTER(C.c_int32), _dp]
         L.oracle_half_sweep.restype = C.c_int
         L.oracle_half_sweep.argtypes = [C.c_void_p, C.c_void_p, _dp, _dp, _dp, C.c_int32, C.c_int64, C.c_int64, _dp]
         _lib = L
@@ -122,3 +124,17 @@ def half_sweep(ep, params_struct, X, Y, alpha, which, begin, end, obj_by_unit):
                                  which, begin, end, _d(obj_by_unit))
     if rc:
         raise ValueError(f"oracle_half_sweep error {rc}")
+
+
+def fit_sparse(ep, sparse_params_struct, X, Y):
+    """Restated fit!(glrm, ::SparseProxGradParams); X, Y in/out (best model).  Returns dict(objective, seconds, alpha)."""
+    assert X.flags.f_contiguous and Y.flags.f_contiguous
+    cap = sparse_params_struct.max_iter + 2
+    obj, sec = np.zeros(cap), np.zeros(cap)
+    nrec = C.c_int32(0)
+    alpha = np.zeros(1)
+    rc = lib().oracle_fit_sparse(C.addressof(ep.struct), C.addressof(sparse_params_struct), _d(X), _d(Y), _d(obj), _d(sec),
+                                 cap, C.byref(nrec), _d(alpha))
+    if rc:
+        raise ValueError(f"oracle_fit_sparse error {rc}")
+    return dict(objective=obj[:nrec.value].copy(), seconds=sec[:nrec.value].copy(), alpha=float(alpha[0]))

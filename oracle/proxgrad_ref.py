@@ -465,3 +465,57 @@ def fit_reference(glrm, params, X=None, Y=None):
         if i > 10 and (obj_decrease < scaled_abs_tol or obj_decrease / obj < params.rel_tol):  # :211
             break
     return X, Y, ch, alpharow, alphacol
+
+
+# ---------------------------------------------------------------------------------- sparse_proxgrad.jl
+def fit_sparse_reference(glrm, params):
+    """Restatement of fit!(glrm, params::SparseProxGradParams) (sparse_proxgrad.jl:21-130).  Returns
+    (Xbest, Ybest, objective list, alpha)."""
+    from lowrankmodels_b200 import get_yidxs
+
+    A = glrm.A
+    losses, rx, ry = glrm.losses, glrm.rx, glrm.ry
+    Xb, Yb = glrm.X.copy(), glrm.Y.copy()                                         # glrm.X / glrm.Y: best model yet
+    X, Y = Xb.copy(), Yb.copy()                                                   # :33 working variables
+    k = glrm.k
+    m, n = A.shape
+    ystart = get_yidxs(losses)
+    alpha = params.stepsize                                                       # :44
+    tol = params.abs_tol * sum(len(glrm.observed_features[i]) for i in range(m))  # :46
+    ch = [objective(glrm, Xb, Yb, ystart)]                                        # :50
+    steps_in_a_row = 0
+    for i in range(1, params.max_iter + 1):                                       # :60
+        for _ in range(params.inner_iter):                                        # :62
+            for e in range(m):                                                    # :63
+                g = np.zeros(k)                                                   # :64
+                for f in glrm.observed_features[e]:                               # :67-72
+                    g += grad(losses[f], float(X[:, e] @ Y[:, f]), A[e, f]) * Y[:, f]
+                l = len(glrm.observed_features[e]) + 1                            # :74
+                g *= -alpha / l                                                   # :75
+                X[:, e] = X[:, e] + g                                             # :77
+                X[:, e] = prox(rx[e], X[:, e], alpha / l)                         # :79
+        for _ in range(params.inner_iter):                                        # :83
+            for f in range(n):                                                    # :84
+                g = np.zeros(k)                                                   # :85
+                for e in glrm.observed_examples[f]:                               # :88-92
+                    g += grad(losses[f], float(X[:, e] @ Y[:, f]), A[e, f]) * X[:, e]
+                l = len(glrm.observed_examples[f]) + 1                            # :94
+                g *= -alpha / l                                                   # :95
+                Y[:, f] = Y[:, f] + g                                             # :97
+                Y[:, f] = prox(ry[f], Y[:, f], alpha / l)                         # :99
+        obj = objective(glrm, X, Y, ystart)                                       # :102
+        if obj < ch[-1]:                                                          # :104
+            ch.append(obj)                                                        # :106
+            Xb[...] = X                                                           # :107
+            Yb[...] = Y
+            alpha = alpha * 1.05                                                  # :108
+            steps_in_a_row = max(1, steps_in_a_row + 1)                           # :109
+        else:
+            alpha = alpha / max(1.5, -steps_in_a_row)                             # :113
+            X[...] = Xb                                                           # :115
+            Y[...] = Yb
+            steps_in_a_row = min(0, steps_in_a_row - 1)                           # :116
+        if (i > 10 and (steps_in_a_row > 3 and ch[-2] - obj < tol)) or alpha <= params.min_stepsize:   # :119
+            break
+    ch.append(ch[-1])                                                             # :126
+    return Xb, Yb, ch, alpha

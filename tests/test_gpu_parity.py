@@ -272,6 +272,30 @@ def test_config5_scaled_twin_kmeans(orc):
     assert np.isinf(got["objective"][0])                       # random start is infeasible for the one-hot constraint
 
 
+@pytest.mark.parametrize("stepsize", [1.0, 12.0])
+def test_sparse_proxgrad_params_semantics(orc, stepsize):
+    """fit!(glrm, SparseProxGradParams()) (sparse_proxgrad.jl:21-130) on the engine: unconditional sweeps with one global
+    step size, global accept / revert; stepsize 12 forces rejected iterations.  Series recorded as the reference does."""
+    from test_oracle_sparse_params import problems
+    for name, g in problems():
+        p = lrm.SparseProxGradParams(stepsize, max_iter=14, abs_tol=1e-6)
+        ep = lrm.encode_problem(g)
+        Xo, Yo = g.X.copy(order="F"), g.Y.copy(order="F")
+        want = orc.fit_sparse(ep, lrm.encode_sparse_params(p), Xo, Yo)
+        X, Y = g.X.copy(order="F"), g.Y.copy(order="F")
+        with lrm.Engine(ep) as eng:
+            obj, sec = eng.fit_sparse(p, X, Y)
+        assert_traj_close(obj, want["objective"], 1e-7, name)
+        np.testing.assert_allclose(X, Xo, rtol=1e-5, atol=1e-8)
+        np.testing.assert_allclose(Y, Yo, rtol=1e-5, atol=1e-8)
+        assert obj[-1] == obj[-2] and len(sec) == len(obj)
+    cfg = synth.config2(scale=16)
+    g = glrm_from_config(cfg, lrm.QuadLoss(), lrm.QuadReg(0.1), lrm.QuadReg(0.1))
+    X0, Y0 = g.X.copy(), g.Y.copy()
+    _, _, ch = lrm.fit_inplace(g, verbose=False)                       # sparse A -> SparseProxGradParams by default (fit.jl:13-15)
+    assert ch.objective[-1] < ch.objective[0] and not (g.X == X0).all()
+
+
 def test_objective_api_and_reg_scale(orc):
     A, obs, X0 = small_sparse(seed=30)
     g = lrm.GLRM(A, lrm.HuberLoss(), lrm.QuadReg(0.3), lrm.OneReg(0.2), 4, obs=obs, X=X0,
