@@ -26,7 +26,7 @@ import LowRankModels: fit!, AbstractParams, GLRM, ConvergenceHistory, update_ch!
                       OneSparseConstraint, KSparseConstraint, UnitOneSparseConstraint, SimplexConstraint,
                       lastentry1, lastentry_unpenalized
 
-export B200ProxGradParams
+export B200ProxGradParams, B200SparseProxGradParams
 
 const LIB = get(ENV, "GLRMB200_LIB", joinpath(@__DIR__, "..", "csrc", "libglrm_b200.so"))
 
@@ -142,6 +142,17 @@ check(rc) = rc == 0 ? nothing : error("glrmb200 error $rc: $(lasterr())")
 function fit!(glrm::GLRM, params::B200ProxGradParams;
               ch::ConvergenceHistory=ConvergenceHistory("B200ProxGradGLRM"),
               verbose=true, kwargs...)
+    return _fit_with(glrm, params, ch, verbose) do handle, X, Y, obj, sec, cap, nrec
+        cp = Ref(CParams(params.stepsize, params.max_iter, params.inner_iter_X, params.inner_iter_Y,
+                         params.abs_tol, params.rel_tol, params.min_stepsize))
+        ccall((:glrmb200_fit, LIB), Cint,
+              (Ptr{Cvoid}, Ref{CParams}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Int32, Ref{Int32}, Ptr{Cvoid}),
+              handle, cp, X, Y, obj, sec, cap, nrec, C_NULL)
+    end
+end
+
+# encode the GLRM, create the handle, run `call(handle, X, Y, obj, sec, cap, nrec)`, feed `ch`, destroy the handle
+function _fit_with(call::Function, glrm::GLRM, params::B200ProxGradParams, ch::ConvergenceHistory, verbose)
     A = glrm.A
     m, n = size(A)
     k = glrm.k
@@ -170,8 +181,6 @@ function fit!(glrm::GLRM, params::B200ProxGradParams;
 
     cap = params.max_iter + 1
     obj = zeros(Cdouble, cap); sec = zeros(Cdouble, cap); nrec = Ref{Int32}(0)
-    cp = Ref(CParams(params.stepsize, params.max_iter, params.inner_iter_X, params.inner_iter_Y,
-                     params.abs_tol, params.rel_tol, params.min_stepsize))
     handle = Ref{Ptr{Cvoid}}(C_NULL)
     if verbose println("Fitting GLRM") end                                      # proxgrad.jl:75
     GC.@preserve lcode lparam rxc rxp ryc ryp dense rptr ridx rval cptr cidx cval X Y obj sec begin
@@ -183,10 +192,7 @@ function fit!(glrm::GLRM, params::B200ProxGradParams;
         check(ccall((:glrmb200_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{CProblem}, Int32, Int32, Int32),
                     handle, prob, params.device, 0, 1))
         try
-            check(ccall((:glrmb200_fit, LIB), Cint,
-                        (Ptr{Cvoid}, Ref{CParams}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Int32,
-                         Ref{Int32}, Ptr{Cvoid}),
-                        handle[], cp, X, Y, obj, sec, cap, nrec, C_NULL))
+            check(call(handle[], X, Y, obj, sec, Int32(cap), nrec))
         finally
             ccall((:glrmb200_destroy, LIB), Cint, (Ptr{Cvoid},), handle[])
         end
@@ -198,6 +204,40 @@ function fit!(glrm::GLRM, params::B200ProxGradParams;
         end
     end
     return glrm.X, glrm.Y, ch                                                   # proxgrad.jl:219
+end
+
+# ---- SparseProxGradParams' five fields (src/algorithms/sparse_proxgrad.jl:4-18) + the device -------------------
+mutable struct B200SparseProxGradParams <: AbstractParams
+    stepsize::Float64
+    max_iter::Int
+    inner_iter::Int
+    abs_tol::Float64
+    min_stepsize::Float64
+    device::Int
+end
+B200SparseProxGradParams(stepsize::Number=1.0; max_iter::Int=100, inner_iter::Int=1, abs_tol::Float64=0.00001,
+                         min_stepsize::Float64=0.01*stepsize, device::Int=0) =
+    B200SparseProxGradParams(Float64(stepsize), max_iter, inner_iter, abs_tol, min_stepsize, device)
+
+struct CSparseParams      # glrmb200_sparse_params
+    stepsize::Cdouble
+    max_iter::Int32
+    inner_iter::Int32
+    abs_tol::Cdouble
+    min_stepsize::Cdouble
+end
+
+# Same encoding as above, then glrmb200_fit_sparse instead of glrmb200_fit; the recorded series is the reference's
+# (initial objective, one entry per accepted iteration, final duplicate — sparse_proxgrad.jl:50,106,126).
+function fit!(glrm::GLRM, params::B200SparseProxGradParams;
+              ch::ConvergenceHistory=ConvergenceHistory("B200SparseProxGradGLRM"), verbose=true, kwargs...)
+    pg = B200ProxGradParams(params.stepsize; max_iter=params.max_iter + 1, device=params.device)
+    return _fit_with(glrm, pg, ch, verbose) do handle, X, Y, obj, sec, cap, nrec
+        cp = Ref(CSparseParams(params.stepsize, params.max_iter, params.inner_iter, params.abs_tol, params.min_stepsize))
+        ccall((:glrmb200_fit_sparse, LIB), Cint,
+              (Ptr{Cvoid}, Ref{CSparseParams}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Int32, Ref{Int32}, Ptr{Cvoid}),
+              handle, cp, X, Y, obj, sec, cap, nrec, C_NULL)
+    end
 end
 
 end # module

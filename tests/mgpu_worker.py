@@ -61,6 +61,28 @@ def main():
                 print("   obj", np.max(np.abs(obj - obj1)), "X", np.max(np.abs(X - X1)), "Y", np.max(np.abs(Y - Y1)),
                       "alpha", np.max(np.abs(ar - ar1)), np.max(np.abs(ac - ac1)), flush=True)
             ok = ok and bool(same)
+    # SparseProxGradParams path (unconditional sweeps, global accept / revert incl. rejected iterations), both exchanges
+    cfg = synth.config2(scale=16)
+    g = glrm_from_config(cfg, lrm.QuadLoss(), lrm.QuadReg(0.1), lrm.QuadReg(0.1))
+    ep = lrm.encode_problem(g)
+    sp = lrm.SparseProxGradParams(12.0, max_iter=12, abs_tol=1e-6)
+    outs = []
+    for fused in (False, True):
+        Xf, Yf = g.X.copy(order="F"), g.Y.copy(order="F")
+        eng = lrm.Engine(ep, device=local, rank=rank, nranks=world)
+        eng.comm_init(D.broadcast_unique_id(dist, rank, lrm.Engine.unique_id))
+        if fused:
+            eng.peer_init(dist)
+        objf, _ = eng.fit_sparse(sp, Xf, Yf)
+        eng.close()
+        outs.append((objf, Xf, Yf))
+    if rank == 0:
+        X1, Y1 = g.X.copy(order="F"), g.Y.copy(order="F")
+        with lrm.Engine(ep, device=local) as e1:
+            obj1, _ = e1.fit_sparse(sp, X1, Y1)
+        same = all(len(o) == len(obj1) and (o == obj1).all() and (x == X1).all() and (y == Y1).all() for o, x, y in outs)
+        print(f"sparse-params C2/16: {world}-GPU (NCCL and fused) vs 1-GPU identical={same} recorded={len(obj1)}", flush=True)
+        ok = ok and bool(same)
     flag = torch.tensor([1.0 if ok else 0.0])
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()
