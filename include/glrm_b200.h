@@ -263,8 +263,13 @@ int glrmb200_objective(glrmb200_handle h, const double* X, const double* Y,
                        int32_t include_regularization, double* out);
 
 /* Residency helpers for the callers that refit the same data (src/cross_validate.jl:141-240):
- * rescale all regularizers (scale_regularizer!, src/glrm.jl:84-88) without re-uploading A. */
+ * rescale all regularizers (scale_regularizer!, src/glrm.jl:84-88) without re-uploading A ... */
 int glrmb200_set_reg_scale(glrmb200_handle h, double newscale);
+/* ... and swap the observation lists of a live handle (a training fold: cross_validate.jl:31-33 replaces
+ * glrm.observed_features / observed_examples and refits): same array meaning as in glrmb200_problem; losses,
+ * regularizers, shapes and the device-resident factors are kept.  A fully observed handle becomes list mode. */
+int glrmb200_set_obs(glrmb200_handle h, const int64_t* row_ptr, const int32_t* row_idx, const double* row_val,
+                     const int64_t* col_ptr, const int32_t* col_idx, const double* col_val);
 
 /* Device-resident benchmarking hooks: keep factors on the device between calls so the timed
  * region of bench.py's `value` leg contains no host<->device copies.

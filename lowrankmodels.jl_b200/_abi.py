@@ -72,6 +72,7 @@ SYMBOLS = [
                                        C.c_int32, c_int32_p, C.POINTER(Profile)]),
     ("glrmb200_objective", C.c_int, [Handle, c_double_p, c_double_p, C.c_int32, c_double_p]),
     ("glrmb200_set_reg_scale", C.c_int, [Handle, C.c_double]),
+    ("glrmb200_set_obs", C.c_int, [Handle, c_int64_p, c_int32_p, c_double_p, c_int64_p, c_int32_p, c_double_p]),
     ("glrmb200_upload_factors", C.c_int, [Handle, c_double_p, c_double_p]),
     ("glrmb200_fit_resident", C.c_int, [Handle, C.POINTER(Params), c_double_p, c_double_p, C.c_int32,
                                          c_int32_p, C.POINTER(Profile)]),

@@ -120,6 +120,8 @@ struct glrmb200_engine {
   bool has_vec = false;              // some column has a vector-valued loss
   int64_t* d_ystart = nullptr;       // [n+1]
   std::vector<int64_t> ystart;
+  std::vector<char> col_is_vec, all_rows_vec;   // schedule routing (vector-loss units)
+  std::vector<int32_t> h_loss_code;             // host copy (error messages)
   Side rows, cols;
   int32_t* d_loss_code = nullptr;
   double* d_loss_param = nullptr;
@@ -449,6 +451,78 @@ extern "C" int glrmb200_destroy(glrmb200_handle E) {
   return 0;
 }
 
+// Observation lists (list mode): host checks, nnz-balanced shards, upload of this rank's shard, device-side
+// validation (index bounds, NaN, label domains), degree-sorted schedules.  Used by glrmb200_create and by
+// glrmb200_set_obs (new lists on a live handle: cross-validation folds, src/cross_validate.jl:31-33).
+static int load_lists(glrmb200_engine* E, const int64_t* row_ptr, const int32_t* row_idx, const double* row_val,
+                      const int64_t* col_ptr, const int32_t* col_idx, const double* col_val) {
+  const int64_t m = E->m, n = E->n;
+  Side& R = E->rows;
+  Side& C = E->cols;
+  if (!row_ptr || !col_ptr) return fail(GLRMB200_E_INVALID, "observation lists missing");
+  const int64_t nr = row_ptr[m], nc = col_ptr[n];
+  if (row_ptr[0] != 0 || col_ptr[0] != 0) return fail(GLRMB200_E_INVALID, "ptr arrays must start at 0");
+  if ((nr && (!row_idx || !row_val)) || (nc && (!col_idx || !col_val))) return fail(GLRMB200_E_INVALID, "observation arrays missing");
+  for (int64_t e = 0; e < m; ++e)
+    if (row_ptr[e + 1] < row_ptr[e]) return fail(GLRMB200_E_INVALID, "row_ptr not monotone");
+  for (int64_t f = 0; f < n; ++f)
+    if (col_ptr[f + 1] < col_ptr[f]) return fail(GLRMB200_E_INVALID, "col_ptr not monotone");
+  E->obs_full = false;
+  R.full_len = C.full_len = 0;
+  E->nnz_rows_total = nr;
+  R.bounds.assign((size_t)E->nranks + 1, 0);
+  C.bounds.assign((size_t)E->nranks + 1, 0);
+  glrmb200_plan_shards(row_ptr, m, E->nranks, R.bounds.data());
+  glrmb200_plan_shards(col_ptr, n, E->nranks, C.bounds.data());
+  R.begin = R.bounds[E->rank]; R.end = R.bounds[E->rank + 1];
+  C.begin = C.bounds[E->rank]; C.end = C.bounds[E->rank + 1];
+  for (Side* S : {&R, &C}) {
+    cudaFree(S->d_ptr); cudaFree(S->d_idx); cudaFree(S->d_val); cudaFree(S->d_order); cudaFree(S->d_order_vec);
+    S->d_ptr = nullptr; S->d_idx = nullptr; S->d_val = nullptr; S->d_order = nullptr; S->d_order_vec = nullptr;
+  }
+  int rc;
+  auto up_side = [&](Side& S, const int64_t* ptr, const int32_t* idx, const double* val, const std::vector<char>* vecflags) -> int {
+    const int64_t cnt = S.end - S.begin, q0 = ptr[S.begin], q1 = ptr[S.end];
+    S.nnz_local = q1 - q0;
+    std::vector<int64_t> local((size_t)cnt + 1);
+    for (int64_t i = 0; i <= cnt; ++i) local[(size_t)i] = ptr[S.begin + i] - q0;
+    int r2 = upload(&S.d_ptr, local.data(), local.size());
+    if (r2) return r2;
+    if ((r2 = upload(&S.d_idx, idx ? idx + q0 : nullptr, (size_t)S.nnz_local))) return r2;
+    if ((r2 = upload(&S.d_val, val ? val + q0 : nullptr, (size_t)S.nnz_local))) return r2;
+    return build_schedule(S, ptr, E->heavy_threshold, E->cluster_threshold, E->has_vec ? vecflags : nullptr);
+  };
+  if ((rc = up_side(R, row_ptr, row_idx, row_val, &E->all_rows_vec))) return rc;
+  if ((rc = up_side(C, col_ptr, col_idx, col_val, &E->col_is_vec))) return rc;
+  unsigned long long* d_bad = nullptr;
+  CUDA_OK(cudaMalloc((void**)&d_bad, 2 * sizeof(unsigned long long)));
+  CUDA_OK(cudaMemset(d_bad, 0xff, 2 * sizeof(unsigned long long)));
+  if (R.nnz_local > 0)
+    validate_rows_kernel<<<(unsigned)((R.nnz_local + 255) / 256), 256, 0, E->stream>>>(R.d_idx, R.d_val, R.nnz_local, n, E->d_loss_code, E->d_loss_param, d_bad);
+  if (C.end > C.begin)
+    validate_cols_kernel<<<(unsigned)((C.end - C.begin + 7) / 8), 256, 0, E->stream>>>(C.d_ptr, C.d_idx, C.d_val, C.end - C.begin, C.begin, m, E->d_loss_code, E->d_loss_param, d_bad + 1);
+  CUDA_OK(cudaGetLastError());
+  unsigned long long bad[2] = {0, 0};
+  CUDA_OK(cudaMemcpyAsync(bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
+  CUDA_OK(cudaStreamSynchronize(E->stream));
+  cudaFree(d_bad);
+  for (int side = 0; side < 2; ++side) {
+    if (bad[side] == ~0ULL) continue;
+    const int kind = -(int)(bad[side] & 15ULL);
+    const Side& S = side == 0 ? R : C;
+    const int64_t* ptr = side == 0 ? row_ptr : col_ptr;
+    const int64_t q = ptr[S.begin] + (int64_t)(bad[side] >> 4);
+    const int64_t unit = (std::upper_bound(ptr, ptr + (side == 0 ? m : n) + 1, q) - ptr) - 1;
+    const int64_t other = side == 0 ? row_idx[q] : col_idx[q];
+    const int64_t e = side == 0 ? unit : other, f = side == 0 ? other : unit;
+    const double v = side == 0 ? row_val[q] : col_val[q];
+    if (kind == GLRMB200_E_INVALID) return fail(kind, "%s[%lld] = %lld out of range", side == 0 ? "row_idx" : "col_idx", (long long)q, (long long)other);
+    if (kind == GLRMB200_E_NAN) return fail(kind, "Observed value in entry (%lld, %lld) is NaN.", (long long)e + 1, (long long)f + 1);
+    return fail(kind, "entry (%lld, %lld): label %g is outside the domain of loss code %d", (long long)e + 1, (long long)f + 1, v, (int)E->h_loss_code[(size_t)f]);
+  }
+  return 0;
+}
+
 static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   const int64_t m = P->m, n = P->n, k = P->k;
   if (m <= 0 || n <= 0 || k <= 0) return fail(GLRMB200_E_INVALID, "m, n, k must be positive");
@@ -461,7 +535,9 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   int64_t dsum = 0;
   bool uniform = true;
   E->ystart.assign((size_t)n + 1, 0);
-  std::vector<char> col_is_vec((size_t)n, 0);
+  E->col_is_vec.assign((size_t)n, 0);
+  E->h_loss_code.assign(P->loss_code, P->loss_code + n);
+  std::vector<char>& col_is_vec = E->col_is_vec;
   for (int64_t f = 0; f < n; ++f) {
     const int code = P->loss_code[f];
     const double* p = P->loss_param + f * GLRMB200_LOSS_NPARAM;
@@ -524,20 +600,7 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
     E->nnz_rows_total = m * n;
     glrmb200_plan_shards(nullptr, m, E->nranks, R.bounds.data());
     glrmb200_plan_shards(nullptr, n, E->nranks, C.bounds.data());
-  } else {
-    if (!P->row_ptr || !P->col_ptr) return fail(GLRMB200_E_INVALID, "observation lists missing");
-    const int64_t nr = P->row_ptr[m], nc = P->col_ptr[n];
-    if (P->row_ptr[0] != 0 || P->col_ptr[0] != 0) return fail(GLRMB200_E_INVALID, "ptr arrays must start at 0");
-    if ((nr && (!P->row_idx || !P->row_val)) || (nc && (!P->col_idx || !P->col_val))) return fail(GLRMB200_E_INVALID, "observation arrays missing");
-    for (int64_t e = 0; e < m; ++e)
-      if (P->row_ptr[e + 1] < P->row_ptr[e]) return fail(GLRMB200_E_INVALID, "row_ptr not monotone");
-    for (int64_t f = 0; f < n; ++f)
-      if (P->col_ptr[f + 1] < P->col_ptr[f]) return fail(GLRMB200_E_INVALID, "col_ptr not monotone");
-    // index bounds, NaN and label domains are checked on the device after the upload (validate_*_kernel)
-    E->nnz_rows_total = nr;
-    glrmb200_plan_shards(P->row_ptr, m, E->nranks, R.bounds.data());
-    glrmb200_plan_shards(P->col_ptr, n, E->nranks, C.bounds.data());
-  }
+  }   // (observation lists: checked, sharded and uploaded by load_lists below)
   R.begin = R.bounds[E->rank]; R.end = R.bounds[E->rank + 1];
   C.begin = C.bounds[E->rank]; C.end = C.bounds[E->rank + 1];
   // NB: the tier of a unit (warp / CTA / cluster) fixes its reduction tree, so the thresholds are constants of the
@@ -562,7 +625,8 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   if ((rc = upload(&E->d_loss_param, P->loss_param, (size_t)n * GLRMB200_LOSS_NPARAM))) return rc;
   if ((rc = setup_regs(R, P->rx_count, P->rx_code, P->rx_param))) return rc;
   if ((rc = setup_regs(C, P->ry_count, P->ry_code, P->ry_param))) return rc;
-  std::vector<char> all_rows_vec(E->has_vec ? (size_t)m : 0, 1);   // with block columns every row takes the vector path
+  E->all_rows_vec.assign(E->has_vec ? (size_t)m : 0, 1);   // with block columns every row takes the vector path
+  std::vector<char>& all_rows_vec = E->all_rows_vec;
   if (E->has_vec) {
     if ((rc = upload(&E->d_ystart, E->ystart.data(), E->ystart.size()))) return rc;
     for (int64_t f = 0; f < n; ++f) {
@@ -620,45 +684,7 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
       }
     }
   } else {
-    auto up_side = [&](Side& S, const int64_t* ptr, const int32_t* idx, const double* val, const std::vector<char>* vecflags) -> int {
-      const int64_t cnt = S.end - S.begin, q0 = ptr[S.begin], q1 = ptr[S.end];
-      S.nnz_local = q1 - q0;
-      std::vector<int64_t> local((size_t)cnt + 1);
-      for (int64_t i = 0; i <= cnt; ++i) local[(size_t)i] = ptr[S.begin + i] - q0;
-      int r2 = upload(&S.d_ptr, local.data(), local.size());
-      if (r2) return r2;
-      if ((r2 = upload(&S.d_idx, idx ? idx + q0 : nullptr, (size_t)S.nnz_local))) return r2;
-      if ((r2 = upload(&S.d_val, val ? val + q0 : nullptr, (size_t)S.nnz_local))) return r2;
-      return build_schedule(S, ptr, E->heavy_threshold, E->cluster_threshold, E->has_vec ? vecflags : nullptr);
-    };
-    if ((rc = up_side(R, P->row_ptr, P->row_idx, P->row_val, &all_rows_vec))) return rc;
-    if ((rc = up_side(C, P->col_ptr, P->col_idx, P->col_val, &col_is_vec))) return rc;
-    unsigned long long* d_bad = nullptr;
-    CUDA_OK(cudaMalloc((void**)&d_bad, 2 * sizeof(unsigned long long)));
-    CUDA_OK(cudaMemset(d_bad, 0xff, 2 * sizeof(unsigned long long)));
-    if (R.nnz_local > 0)
-      validate_rows_kernel<<<(unsigned)((R.nnz_local + 255) / 256), 256, 0, E->stream>>>(R.d_idx, R.d_val, R.nnz_local, n, E->d_loss_code, E->d_loss_param, d_bad);
-    if (C.end > C.begin)
-      validate_cols_kernel<<<(unsigned)((C.end - C.begin + 7) / 8), 256, 0, E->stream>>>(C.d_ptr, C.d_idx, C.d_val, C.end - C.begin, C.begin, m, E->d_loss_code, E->d_loss_param, d_bad + 1);
-    CUDA_OK(cudaGetLastError());
-    unsigned long long bad[2] = {0, 0};
-    CUDA_OK(cudaMemcpyAsync(bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
-    CUDA_OK(cudaStreamSynchronize(E->stream));
-    cudaFree(d_bad);
-    for (int side = 0; side < 2; ++side) {
-      if (bad[side] == ~0ULL) continue;
-      const int kind = -(int)(bad[side] & 15ULL);
-      const Side& S = side == 0 ? R : C;
-      const int64_t* ptr = side == 0 ? P->row_ptr : P->col_ptr;
-      const int64_t q = ptr[S.begin] + (int64_t)(bad[side] >> 4);
-      const int64_t unit = (std::upper_bound(ptr, ptr + (side == 0 ? m : n) + 1, q) - ptr) - 1;
-      const int64_t other = side == 0 ? P->row_idx[q] : P->col_idx[q];
-      const int64_t e = side == 0 ? unit : other, f = side == 0 ? other : unit;
-      const double v = side == 0 ? P->row_val[q] : P->col_val[q];
-      if (kind == GLRMB200_E_INVALID) return fail(kind, "%s[%lld] = %lld out of range", side == 0 ? "row_idx" : "col_idx", (long long)q, (long long)other);
-      if (kind == GLRMB200_E_NAN) return fail(kind, "Observed value in entry (%lld, %lld) is NaN.", (long long)e + 1, (long long)f + 1);
-      return fail(kind, "entry (%lld, %lld): label %g is outside the domain of loss code %d", (long long)e + 1, (long long)f + 1, v, P->loss_code[f]);
-    }
+    if ((rc = load_lists(E, P->row_ptr, P->row_idx, P->row_val, P->col_ptr, P->col_idx, P->col_val))) return rc;
   }
 
   {
@@ -699,6 +725,14 @@ extern "C" int glrmb200_create(glrmb200_handle* out, const glrmb200_problem* pro
   if (rc) { glrmb200_destroy(E); return rc; }
   *out = E;
   return 0;
+}
+
+extern "C" int glrmb200_set_obs(glrmb200_handle E, const int64_t* row_ptr, const int32_t* row_idx, const double* row_val,
+                                const int64_t* col_ptr, const int32_t* col_idx, const double* col_val) {
+  if (!E) return fail(GLRMB200_E_STATE, "null handle");
+  CUDA_OK(cudaSetDevice(E->device));
+  CUDA_OK(cudaStreamSynchronize(E->stream));
+  return load_lists(E, row_ptr, row_idx, row_val, col_ptr, col_idx, col_val);
 }
 
 extern "C" int glrmb200_comm_unique_id(uint8_t id[128]) {

@@ -123,6 +123,15 @@ class Engine:
     def set_reg_scale(self, newscale):
         _abi.check(_abi.lib().glrmb200_set_reg_scale(self.h, float(newscale)))
 
+    def set_obs(self, ep):
+        """Swap in the observation lists of another EncodedProblem (same A shape / losses / regularizers): the
+        training fold of cross_validate (src/cross_validate.jl:31-33) without re-creating the handle."""
+        k_ = ep.keep
+        _abi.check(_abi.lib().glrmb200_set_obs(self.h, _abi.i64ptr(k_["row_ptr"]), _abi.i32ptr(k_["row_idx"]),
+                                               _abi.dptr(k_["row_val"]), _abi.i64ptr(k_["col_ptr"]),
+                                               _abi.i32ptr(k_["col_idx"]), _abi.dptr(k_["col_val"])))
+        self.ep = ep
+
     def stepsizes(self):
         ar, ac = np.zeros(self.m), np.zeros(self.n)
         _abi.check(_abi.lib().glrmb200_get_stepsizes(self.h, _abi.dptr(ar), _abi.dptr(ac)))

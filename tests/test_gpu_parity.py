@@ -310,6 +310,41 @@ def test_objective_api_and_reg_scale(orc):
         assert eng.objective(g.X, g.Y, True) == pytest.approx(orc.objective(ep2, g.X, g.Y, True), rel=1e-12)
 
 
+def test_set_obs_swaps_lists_on_a_live_handle(orc):
+    """cross_validate.jl:31-33 replaces the observation lists of a copy of the model and refits: glrmb200_set_obs does
+    that on a live handle.  The result must equal a handle created from scratch on the training fold."""
+    A, obs, X0 = small_sparse(seed=50, m=80, n=50, density=0.4)
+    k = 4
+    Y0 = synth.normal_matrix(51, 1, k, A.shape[1])
+    full = lrm.GLRM(A, lrm.HuberLoss(), lrm.QuadReg(0.1), lrm.QuadReg(0.1), k, obs=obs, X=X0, Y=Y0)
+    fold = synth.uniform(52, 1, np.arange(len(obs))) < 0.8
+    train = lrm.GLRM(A, lrm.HuberLoss(), lrm.QuadReg(0.1), lrm.QuadReg(0.1), k, obs=obs[fold], X=X0, Y=Y0)
+    p = lrm.ProxGradParams(max_iter=8)
+    want = run_oracle(orc, train, p)
+    Xa, Ya = train.X.copy(order="F"), train.Y.copy(order="F")
+    with lrm.Engine(full) as eng:
+        eng.fit(lrm.ProxGradParams(max_iter=2), full.X.copy(order="F"), full.Y.copy(order="F"))   # handle in use on all obs
+        eng.set_obs(lrm.encode_problem(train))
+        obj, _ = eng.fit(p, Xa, Ya)
+    Xb, Yb = train.X.copy(order="F"), train.Y.copy(order="F")
+    with lrm.Engine(train) as eng:
+        obj2, _ = eng.fit(p, Xb, Yb)
+    assert (obj == obj2).all() and (Xa == Xb).all() and (Ya == Yb).all()
+    assert_traj_close(obj, want["objective"], TIGHT)
+    # a fully observed handle switches to list mode
+    c = synth.config1()
+    gfull = glrm_from_config(c, lrm.QuadLoss(), lrm.QuadReg(0.1), lrm.QuadReg(0.1))
+    ii, jj = np.nonzero(synth.uniform(53, 1, np.arange(100 * 100)).reshape(100, 100) < 0.5)
+    gsub = lrm.GLRM(c["A"], lrm.QuadLoss(), lrm.QuadReg(0.1), lrm.QuadReg(0.1), 5, obs=np.stack([ii, jj], axis=1),
+                    X=c["X0"], Y=c["Y0"])
+    wsub = run_oracle(orc, gsub, p)
+    Xc, Yc = gsub.X.copy(order="F"), gsub.Y.copy(order="F")
+    with lrm.Engine(gfull) as eng:
+        eng.set_obs(lrm.encode_problem(gsub))
+        objc, _ = eng.fit(p, Xc, Yc)
+    assert_traj_close(objc, wsub["objective"], TIGHT)
+
+
 def test_fit_mutates_in_place_warm_starts_and_appends_ch(orc):
     g = glrm_from_config(synth.config1(), lrm.QuadLoss(), lrm.QuadReg(0.1), lrm.QuadReg(0.1))
     X_id, Y_id = id(g.X), id(g.Y)
