@@ -97,6 +97,10 @@ enum {
  * wrappers (the offset path, src/modify_glrm.jl:21-24):
  *   LASTENTRY1            regularizers.jl:163-174   last factor entry pinned to 1
  *   LASTENTRY_UNPENALIZED regularizers.jl:178-189   last factor entry skipped by the inner reg
+ * block regularizers of the ordinal losses (ry only; applied to the whole k x d_f block of a column):
+ *   ORDINAL_REG           regularizers.jl:356-380   first k-1 rows: mean over the block's columns, inner prox, copied
+ *                                                    back to every column; evaluate = inner reg on a[1:k-1, 1]
+ *   MNL_ORDINAL_REG       regularizers.jl:385-407   the same + last row made negative and decreasing (TOL 1e-3)
  */
 enum {
   GLRMB200_REG_ZERO = 0,
@@ -111,7 +115,9 @@ enum {
   GLRMB200_REG_SIMPLEX = 9,
   GLRMB200_REG_BASE_MASK = 0xff,
   GLRMB200_REG_LASTENTRY1 = 0x100,
-  GLRMB200_REG_LASTENTRY_UNPENALIZED = 0x200
+  GLRMB200_REG_LASTENTRY_UNPENALIZED = 0x200,
+  GLRMB200_REG_ORDINAL = 0x400,
+  GLRMB200_REG_MNL_ORDINAL = 0x800
 };
 
 /* ---- the problem: what `GLRM(A, losses, rx, ry, k; ...)` holds (src/glrm.jl:12-22) ---------- *

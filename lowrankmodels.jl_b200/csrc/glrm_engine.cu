@@ -225,14 +225,17 @@ static int build_schedule(Side& S, const int64_t* ptr_global, int64_t heavy_thre
   return upload(&S.d_order_vec, vec.data(), vec.size());
 }
 
-static int setup_regs(Side& S, int64_t count, const int32_t* code, const double* param) {
+static int setup_regs(Side& S, int64_t count, const int32_t* code, const double* param, bool allow_ordinal) {
   if (count != 1 && count != S.units) return fail(GLRMB200_E_INVALID, "regularizer count must be 1 or the number of columns");
   S.reg_uniform = (count == 1);
   S.h_reg_code.assign(code, code + count);
   S.h_reg_param.assign(param, param + count * GLRMB200_REG_NPARAM);
   for (int64_t i = 0; i < count; ++i) {
     const int base = code[i] & GLRMB200_REG_BASE_MASK;
-    if (base > GLRMB200_REG_SIMPLEX || (code[i] & ~(GLRMB200_REG_BASE_MASK | GLRMB200_REG_LASTENTRY1 | GLRMB200_REG_LASTENTRY_UNPENALIZED)))
+    const int ord = code[i] & (GLRMB200_REG_ORDINAL | GLRMB200_REG_MNL_ORDINAL);
+    if (ord && (!allow_ordinal || (code[i] & (GLRMB200_REG_LASTENTRY1 | GLRMB200_REG_LASTENTRY_UNPENALIZED))))
+      return fail(GLRMB200_E_UNSUPPORTED, "OrdinalReg / MNLOrdinalReg are column (ry) regularizers and are not combined with the offset wrappers");
+    if (base > GLRMB200_REG_SIMPLEX || (code[i] & ~(GLRMB200_REG_BASE_MASK | GLRMB200_REG_LASTENTRY1 | GLRMB200_REG_LASTENTRY_UNPENALIZED | GLRMB200_REG_ORDINAL | GLRMB200_REG_MNL_ORDINAL)))
       return fail(GLRMB200_E_UNSUPPORTED, "regularizer code %d has no device implementation", code[i]);
   }
   int rc = upload(&S.d_reg_code, code, (size_t)count);
@@ -558,6 +561,9 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
     if (code != P->loss_code[0] || memcmp(p, P->loss_param, 3 * sizeof(double)) != 0) uniform = false;
   }
   E->ystart[(size_t)n] = dsum;
+  for (int64_t f = 0; f < n; ++f) {          // OrdinalReg / MNLOrdinalReg columns take the block path whatever their width
+    if (P->ry_code[P->ry_count == 1 ? 0 : f] & (GLRMB200_REG_ORDINAL | GLRMB200_REG_MNL_ORDINAL)) { col_is_vec[(size_t)f] = 1; E->has_vec = true; }
+  }
   if (dsum != P->d) return fail(GLRMB200_E_INVALID, "d = %lld but the losses' embedding dimensions sum to %lld (proxgrad.jl:55-63)", (long long)P->d, (long long)dsum);
   E->loss_template = 0;
   if (uniform && !E->has_vec && (P->loss_code[0] == GLRMB200_LOSS_QUAD || P->loss_code[0] == GLRMB200_LOSS_LOGISTIC)) {
@@ -623,15 +629,17 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
 
   if ((rc = upload(&E->d_loss_code, P->loss_code, (size_t)n))) return rc;
   if ((rc = upload(&E->d_loss_param, P->loss_param, (size_t)n * GLRMB200_LOSS_NPARAM))) return rc;
-  if ((rc = setup_regs(R, P->rx_count, P->rx_code, P->rx_param))) return rc;
-  if ((rc = setup_regs(C, P->ry_count, P->ry_code, P->ry_param))) return rc;
+  if ((rc = setup_regs(R, P->rx_count, P->rx_code, P->rx_param, false))) return rc;
+  if ((rc = setup_regs(C, P->ry_count, P->ry_code, P->ry_param, true))) return rc;
   E->all_rows_vec.assign(E->has_vec ? (size_t)m : 0, 1);   // with block columns every row takes the vector path
   std::vector<char>& all_rows_vec = E->all_rows_vec;
   if (E->has_vec) {
     if ((rc = upload(&E->d_ystart, E->ystart.data(), E->ystart.size()))) return rc;
     for (int64_t f = 0; f < n; ++f) {
       if (!col_is_vec[(size_t)f]) continue;
-      const int base = P->ry_code[P->ry_count == 1 ? 0 : f] & GLRMB200_REG_BASE_MASK;
+      const int rcf = P->ry_code[P->ry_count == 1 ? 0 : f];
+      const int base = rcf & GLRMB200_REG_BASE_MASK;
+      if (rcf & (GLRMB200_REG_ORDINAL | GLRMB200_REG_MNL_ORDINAL)) continue;   // inner prox acts on one (k-1)-vector: any base
       if (!(base == GLRMB200_REG_ZERO || base == GLRMB200_REG_QUAD || base == GLRMB200_REG_ONE ||
             base == GLRMB200_REG_NONNEG || base == GLRMB200_REG_NONNEG_ONE))
         return fail(GLRMB200_E_UNSUPPORTED, "column %lld: regularizer code %d on a block column (only element-wise regularizers decompose over the k x d_f block)", (long long)f, base);

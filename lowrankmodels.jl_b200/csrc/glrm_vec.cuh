@@ -204,8 +204,52 @@ __device__ __forceinline__ double vec_pass(const VecArgs& V, int64_t unit, int64
 
 // separable regularizers on a k x D block: evaluate / prox column by column (regularizers.jl: Quad, One, NonNeg,
 // NonNegOne, Zero and the offset wrappers act element- or row-wise, so the block forms decompose exactly)
+constexpr int ORDINAL_FLAGS = GLRMB200_REG_ORDINAL | GLRMB200_REG_MNL_ORDINAL;
+
+// OrdinalReg / MNLOrdinalReg (regularizers.jl:356-407): the first k-1 rows of the block's columns are forced equal —
+// mean over the columns, inner prox on that (k-1)-vector, copied back — and MNL additionally makes the last row
+// negative and strictly decreasing across the columns.
+template <int G, int R, int DB>
+__device__ __forceinline__ void block_ordinal_prox(int code, const double* rp, double2 (&v)[DB][R], int D, int lg, int k, double alpha) {
+  double2 um[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    double sx = 0.0, sy = 0.0;
+#pragma unroll
+    for (int c = 0; c < DB; ++c) if (c < D) { sx += v[c][r].x; sy += v[c][r].y; }
+    um[r] = make_double2(sx / (double)D, sy / (double)D);
+  }
+  // inner prox sees rows 0..k-2 (the last-row slot of `um` is scratch and is not copied back)
+  reg_prox<G, R>((code & GLRMB200_REG_BASE_MASK) | GLRMB200_REG_LASTENTRY_UNPENALIZED, rp, um, lg, k, alpha);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i0 = 2 * (lg + G * r);
+#pragma unroll
+    for (int c = 0; c < DB; ++c) if (c < D) {
+      if (i0 < k - 1) v[c][r].x = um[r].x;
+      if (i0 + 1 < k - 1) v[c][r].y = um[r].y;
+    }
+    if (code & GLRMB200_REG_MNL_ORDINAL) {                       // :399-402, the lane that owns row k-1 walks the columns
+      if (i0 == k - 1) {
+        double prev = jl_mind(-1e-3, v[0][r].x);
+        v[0][r].x = prev;
+#pragma unroll
+        for (int c = 1; c < DB; ++c) if (c < D) { prev = jl_mind(v[c][r].x, prev - 1e-3); v[c][r].x = prev; }
+      }
+      if (i0 + 1 == k - 1) {
+        double prev = jl_mind(-1e-3, v[0][r].y);
+        v[0][r].y = prev;
+#pragma unroll
+        for (int c = 1; c < DB; ++c) if (c < D) { prev = jl_mind(v[c][r].y, prev - 1e-3); v[c][r].y = prev; }
+      }
+    }
+  }
+}
+
 template <int G, int R, int DB>
 __device__ __forceinline__ double block_reg_eval(int code, const double* rp, const double2 (&v)[DB][R], int D, int lg, int k) {
+  if (code & ORDINAL_FLAGS)                                      // evaluate(r.r, a[1:end-1, 1])  (:378,405)
+    return reg_eval<G, R>((code & GLRMB200_REG_BASE_MASK) | GLRMB200_REG_LASTENTRY_UNPENALIZED, rp, v[0], lg, k);
   double t = 0.0;
 #pragma unroll
   for (int c = 0; c < DB; ++c) if (c < D) t += reg_eval<G, R>(code, rp, v[c], lg, k);
@@ -250,8 +294,9 @@ __global__ void __launch_bounds__(128) vec_sweep_kernel(const VecArgs V) {
       for (int c = 0; c < DB; ++c) {
 #pragma unroll
         for (int r = 0; r < R; ++r) { nw[c][r].x = fma(-stepsize, grad[c][r].x, own[c][r].x); nw[c][r].y = fma(-stepsize, grad[c][r].y, own[c][r].y); }
-        if (c < D) reg_prox<G, R>(rcode, rp, nw[c], lg, k, stepsize);
+        if (c < D && !(rcode & ORDINAL_FLAGS)) reg_prox<G, R>(rcode, rp, nw[c], lg, k, stepsize);
       }
+      if (rcode & ORDINAL_FLAGS) block_ordinal_prox<G, R, DB>(rcode, rp, nw, D, lg, k, stepsize);
       double obj_new = vec_pass<G, R, DB, false>(V, unit, start, len, lane, nw, D, dummy);
       obj_new += block_reg_eval<G, R, DB>(rcode, rp, nw, D, lg, k);
       ++ntrials;

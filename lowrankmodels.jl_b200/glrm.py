@@ -217,9 +217,11 @@ class GLRM:
 def add_offset(glrm: GLRM):
     """add_offset! (modify_glrm.jl:21-24)."""
     def wrap(regs, w):
+        # lastentry_unpenalized(r::OrdinalReg) = r, same for MNLOrdinalReg (regularizers.jl:383,409)
+        keep = lambda r: r if type(r).__name__ in ("OrdinalReg", "MNLOrdinalReg") and w is lastentry_unpenalized else w(r)
         if isinstance(regs, Repeated):
-            return Repeated(w(regs.item), regs.count)
-        return [w(r) for r in regs]
+            return Repeated(keep(regs.item), regs.count)
+        return [keep(r) for r in regs]
     glrm.rx, glrm.ry = wrap(glrm.rx, lastentry1), wrap(glrm.ry, lastentry_unpenalized)
     return glrm
 

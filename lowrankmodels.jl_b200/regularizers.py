@@ -14,6 +14,7 @@ import numpy as np
 REG_ZERO, REG_QUAD, REG_QUAD_CONSTRAINT, REG_ONE, REG_NONNEG, REG_NONNEG_ONE = 0, 1, 2, 3, 4, 5
 REG_ONE_SPARSE, REG_KSPARSE, REG_UNIT_ONE_SPARSE, REG_SIMPLEX = 6, 7, 8, 9
 REG_LASTENTRY1, REG_LASTENTRY_UNPENALIZED = 0x100, 0x200
+REG_ORDINAL, REG_MNL_ORDINAL = 0x400, 0x800
 REG_NPARAM = 4
 
 
@@ -160,12 +161,12 @@ class fixed_last_latent_features(_Unsupported):  # regularizers.jl:214-231
     pass
 
 
-class OrdinalReg(_Unsupported):  # regularizers.jl:356-380
-    pass
+class OrdinalReg(_Wrapper):  # regularizers.jl:356-380 (block regularizer of the ordinal losses; ry only)
+    flag = REG_ORDINAL
 
 
-class MNLOrdinalReg(_Unsupported):  # regularizers.jl:385-407
-    pass
+class MNLOrdinalReg(_Wrapper):  # regularizers.jl:385-407
+    flag = REG_MNL_ORDINAL
 
 
 class RemQuadReg(_Unsupported):  # regularizers.jl:412-423

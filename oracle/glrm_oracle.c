@@ -462,6 +462,8 @@ static void base_reg_prox(int base, const double* p, double* v, int64_t L, doubl
  * sees rows 1..k-1 of every column of the block. */
 static double reg_eval(int code, const double* p, const double* v, int64_t k, int64_t D) {
   const int base = code & GLRMB200_REG_BASE_MASK;
+  if (code & (GLRMB200_REG_ORDINAL | GLRMB200_REG_MNL_ORDINAL))                 /* regularizers.jl:378,405 */
+    return base_reg_eval(base, p, v, k - 1);                                    /* evaluate(r.r, a[1:end-1,1]) */
   if (code & (GLRMB200_REG_LASTENTRY1 | GLRMB200_REG_LASTENTRY_UNPENALIZED)) {
     if (code & GLRMB200_REG_LASTENTRY1)
       for (int64_t c = 0; c < D; ++c) if (v[c * k + k - 1] != 1) return INFINITY;      /* :171-172 */
@@ -476,6 +478,24 @@ static double reg_eval(int code, const double* p, const double* v, int64_t k, in
 
 static void reg_prox(int code, const double* p, double* v, int64_t k, int64_t D, double alpha) {
   const int base = code & GLRMB200_REG_BASE_MASK;
+  if (code & (GLRMB200_REG_ORDINAL | GLRMB200_REG_MNL_ORDINAL)) {               /* regularizers.jl:361-377,390-404 */
+    double* um = (double*)malloc(sizeof(double) * (size_t)k);
+    for (int64_t i = 0; i < k - 1; ++i) {                                       /* um = mean(u[1:end-1,:], dims=2) */
+      double acc = 0.0;
+      for (int64_t c = 0; c < D; ++c) acc += v[c * k + i];
+      um[i] = acc / (double)D;
+    }
+    base_reg_prox(base, p, um, k - 1, alpha);                                   /* prox!(r.r, um, alpha) */
+    for (int64_t i = 0; i < k - 1; ++i)
+      for (int64_t c = 0; c < D; ++c) v[c * k + i] = um[i];
+    free(um);
+    if (code & GLRMB200_REG_MNL_ORDINAL) {                                      /* :399-402 */
+      const double TOL = 1e-3;
+      v[k - 1] = jl_min(-TOL, v[k - 1]);
+      for (int64_t c = 1; c < D; ++c) v[c * k + k - 1] = jl_min(v[c * k + k - 1], v[(c - 1) * k + k - 1] - TOL);
+    }
+    return;
+  }
   if (code & (GLRMB200_REG_LASTENTRY1 | GLRMB200_REG_LASTENTRY_UNPENALIZED)) {
     double* tmp = (double*)malloc(sizeof(double) * (size_t)((k - 1) * D + 1));
     for (int64_t c = 0; c < D; ++c) memcpy(tmp + c * (k - 1), v + c * k, sizeof(double) * (size_t)(k - 1));

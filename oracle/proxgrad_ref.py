@@ -252,6 +252,8 @@ def reg_evaluate(r, a):
         if abs(np.sum(a) - 1) > TOL:
             return math.inf
         return math.inf if (a < 0).any() else 0
+    if name in ("OrdinalReg", "MNLOrdinalReg"):                                  # :378,405
+        return reg_evaluate(r.r, a[:-1] if a.ndim == 1 else a[:-1, 0])
     if name == "lastentry1":                                                     # :171-172
         if a.ndim == 1:
             return reg_evaluate(r.r, a[:-1]) if a[-1] == 1 else math.inf
@@ -306,6 +308,16 @@ def prox(r, u, alpha):
                 t = (ysum[i] - 1) / (i + 1)
                 break
         return np.maximum(u - t, 0)
+    if name in ("OrdinalReg", "MNLOrdinalReg"):                                  # :361-377 / :390-404
+        u2 = u.reshape(-1, 1) if u.ndim == 1 else u.copy()
+        um = np.mean(u2[:-1, :], axis=1)
+        um = prox(r.r, um, alpha)
+        u2[:-1, :] = um[:, None]
+        if name == "MNLOrdinalReg":
+            u2[-1, 0] = min(-1e-3, u2[-1, 0])
+            for j in range(1, u2.shape[1]):
+                u2[-1, j] = min(u2[-1, j], u2[-1, j - 1] - 1e-3)
+        return u2[:, 0] if u.ndim == 1 else u2
     if name == "lastentry1":                                                     # :167,169
         if u.ndim == 1:
             return np.concatenate([prox(r.r, u[:-1], alpha), [1.0]])

@@ -95,5 +95,5 @@ def test_host_mirror_constructor_checks():
     p = lrm.ProxGradParams(2.0, inner_iter=3)
     assert (p.inner_iter_X, p.inner_iter_Y, p.min_stepsize, p.max_iter) == (3, 3, 0.02, 100)
     with pytest.raises(ValueError):
-        lrm.GLRM(A, lrm.QuadLoss(), lrm.OrdinalReg(), lrm.ZeroReg(), 2) and lrm.encode_problem(
-            lrm.GLRM(A, lrm.QuadLoss(), lrm.OrdinalReg(), lrm.ZeroReg(), 2))
+        lrm.GLRM(A, lrm.QuadLoss(), lrm.RemQuadReg(), lrm.ZeroReg(), 2) and lrm.encode_problem(
+            lrm.GLRM(A, lrm.QuadLoss(), lrm.RemQuadReg(), lrm.ZeroReg(), 2))

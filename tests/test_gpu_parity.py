@@ -184,6 +184,13 @@ def test_vector_valued_losses_mixed_columns(orc):
     check(orc, g, lrm.ProxGradParams(max_iter=6, inner_iter=2), rtol=1e-6, factors=False)
 
 
+def test_ordinal_block_regularizers(orc):
+    """OrdinalReg / MNLOrdinalReg on block columns with the offset wrappers on the rest (fit_dataframe.jl defaults)."""
+    from test_oracle_trajectory import ordinal_problem
+    check(orc, ordinal_problem(), lrm.ProxGradParams(max_iter=10), rtol=1e-6, factors=False)
+    check(orc, ordinal_problem(m=60, k=7, seed=9), lrm.ProxGradParams(max_iter=6), rtol=1e-6, factors=False)
+
+
 def test_config4_scaled_twin(orc):
     """BASELINE config 4 (/16 twin: 62 500 x 62, fully observed): 50 % QuadLoss, 30 % HingeLoss, 20 % MultinomialLoss(5), k=20."""
     c = synth.config4(scale=16)

@@ -105,7 +105,9 @@ def test_c_oracle_matches_python_restatement_on_every_loss(orc):
 ALL_REGS = [lrm.ZeroReg(), lrm.QuadReg(0.3), lrm.QuadConstraint(1.5), lrm.OneReg(0.4), lrm.NonNegConstraint(),
             lrm.NonNegOneReg(0.2), lrm.OneSparseConstraint(), lrm.KSparseConstraint(2), lrm.UnitOneSparseConstraint(),
             lrm.SimplexConstraint(), lrm.lastentry1(lrm.QuadReg(0.3)), lrm.lastentry_unpenalized(lrm.OneReg(0.2)),
-            lrm.lastentry1(lrm.NonNegConstraint()), lrm.lastentry_unpenalized(lrm.QuadReg(0.5))]
+            lrm.lastentry1(lrm.NonNegConstraint()), lrm.lastentry_unpenalized(lrm.QuadReg(0.5)),
+            lrm.OrdinalReg(lrm.QuadReg(0.3)), lrm.MNLOrdinalReg(lrm.QuadReg(0.2)), lrm.OrdinalReg(lrm.OneReg(0.1)),
+            lrm.MNLOrdinalReg(lrm.ZeroReg())]
 
 
 def test_c_oracle_matches_python_restatement_on_every_regularizer(orc):

@@ -113,6 +113,35 @@ def test_offset_wrappers_and_inner_iters(orc):
     check_all_forms(orc, g, lrm.ProxGradParams(max_iter=6, inner_iter=2))
 
 
+def ordinal_problem(m=35, k=4, seed=5):
+    """The DataFrame front-end's default for ordinal columns (fit_dataframe.jl:13-18,64-72): MultinomialOrdinalLoss with
+    MNLOrdinalReg on the column block, offset on (rows lastentry1), next to real-valued columns; plus BvS + OrdinalReg."""
+    n = 5
+    u = synth.uniform(seed, 71, np.arange(m * n)).reshape(m, n)
+    z = synth.normal_matrix(seed, 72, m, n)
+    A = z.copy()
+    A[:, 1] = np.floor(u[:, 1] * 5) + 1          # MultinomialOrdinal levels 1..5 (embedding 4)
+    A[:, 2] = np.floor(u[:, 2] * 2) + 1          # MultinomialOrdinal levels 1..2 (embedding 1, still a block column)
+    A[:, 3] = np.floor(u[:, 3] * 4) + 1          # BvS levels 1..4 (embedding 3)
+    losses = [lrm.QuadLoss(), lrm.MultinomialOrdinalLoss(5), lrm.MultinomialOrdinalLoss(2), lrm.BvSLoss(4), lrm.HuberLoss()]
+    ry = [lrm.QuadReg(0.1), lrm.MNLOrdinalReg(lrm.QuadReg(0.1)), lrm.MNLOrdinalReg(lrm.QuadReg(0.2)),
+          lrm.OrdinalReg(lrm.OneReg(0.05)), lrm.QuadReg(0.1)]
+    d = lrm.embedding_dim(losses)
+    ii, jj = np.nonzero(u < 0.8)
+    X0 = 0.3 * synth.normal_matrix(seed, 73, k, m)
+    X0[-1, :] = 1.0
+    Y0 = 0.3 * synth.normal_matrix(seed, 74, k, d)
+    Y0[-1, :] = -0.3 - 0.2 * np.arange(d)        # decreasing negative last row: feasible for the ordinal rules
+    return lrm.GLRM(A, losses, lrm.QuadReg(0.1), ry, k, obs=np.stack([ii, jj], axis=1), X=X0, Y=Y0, offset=True)
+
+
+def test_ordinal_block_regularizers(orc):
+    g = ordinal_problem()
+    assert type(g.rx[0]).__name__ == "lastentry1" and type(g.ry[1]).__name__ == "MNLOrdinalReg"   # not re-wrapped (:409)
+    assert type(g.ry[0]).__name__ == "lastentry_unpenalized"
+    check_all_forms(orc, g, lrm.ProxGradParams(max_iter=8), rtol=1e-8)
+
+
 def test_stopping_rule_fires_after_ten(orc):
     g = glrm_from_config(synth.config1(), lrm.QuadLoss(), lrm.QuadReg(0.1), lrm.QuadReg(0.1))
     res = run_oracle(orc, g, lrm.ProxGradParams(max_iter=100, rel_tol=1e-2))
