@@ -24,7 +24,7 @@ import LowRankModels: fit!, AbstractParams, GLRM, ConvergenceHistory, update_ch!
                       MultinomialOrdinalLoss,
                       ZeroReg, QuadReg, QuadConstraint, OneReg, NonNegConstraint, NonNegOneReg,
                       OneSparseConstraint, KSparseConstraint, UnitOneSparseConstraint, SimplexConstraint,
-                      lastentry1, lastentry_unpenalized
+                      lastentry1, lastentry_unpenalized, OrdinalReg, MNLOrdinalReg
 
 export B200ProxGradParams, B200SparseProxGradParams
 
@@ -103,6 +103,8 @@ regrow(r::UnitOneSparseConstraint) = (8, 0.0)
 regrow(r::SimplexConstraint)       = (9, 0.0)
 regrow(r::lastentry1)              = ((c, p) = regrow(r.r); (c | 0x100, p))
 regrow(r::lastentry_unpenalized)   = ((c, p) = regrow(r.r); (c | 0x200, p))
+regrow(r::OrdinalReg)              = ((c, p) = regrow(r.r); (c | 0x400, p))   # block regularizers (ry only)
+regrow(r::MNLOrdinalReg)           = ((c, p) = regrow(r.r); (c | 0x800, p))
 regrow(r::Regularizer) = throw(ArgumentError("$(typeof(r)) has no B200 device implementation (no CPU fallback)"))
 
 function regtable(rs)
