@@ -91,20 +91,25 @@ class GLRMB200Error(RuntimeError):
         self.code = code
 
 
+def load(path):
+    """dlopen a build of the engine and type every symbol of include/glrm_b200.h."""
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build the CUDA engine first "
+            "(python -c 'import __graft_entry__ as g; g.build()').  There is no CPU fallback.")
+    L = C.CDLL(path)
+    for name, res, args in SYMBOLS:
+        fn = getattr(L, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return L
+
+
 def lib():
     """Load csrc/libglrm_b200.so (built by __graft_entry__.build() / csrc/build.sh)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(
-                f"{LIB_PATH} is missing: build the CUDA engine first "
-                "(python -c 'import __graft_entry__ as g; g.build()').  There is no CPU fallback.")
-        L = C.CDLL(LIB_PATH)
-        for name, res, args in SYMBOLS:
-            fn = getattr(L, name)          # AttributeError if the symbol is not exported
-            fn.restype = res
-            fn.argtypes = args
-        _lib = L
+        _lib = load(LIB_PATH)
     return _lib
 
 

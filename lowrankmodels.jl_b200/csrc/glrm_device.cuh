@@ -672,10 +672,13 @@ __device__ __forceinline__ void cluster_sum_g(double2 (&g)[R], double2* buf, int
 #ifndef GLRM_TRIAL_DEPTH
 #define GLRM_TRIAL_DEPTH 4
 #endif
+#ifndef GLRM_LIGHT_CTAS
+#define GLRM_LIGHT_CTAS 4      /* resident 4-warp CTAs per SM the warp-tier kernel is compiled for (register cap) */
+#endif
 template <int R> struct TileCfg {
   static constexpr int DEPTH = GLRM_PIPE_DEPTH;
   static constexpr int TRIAL_DEPTH = GLRM_TRIAL_DEPTH;
-  static constexpr int LIGHT_CTAS = 4;
+  static constexpr int LIGHT_CTAS = GLRM_LIGHT_CTAS;
   static constexpr int HEAVY_CTAS = 2;
 };
 

@@ -21,6 +21,9 @@ for v in variants:
     keys = []
     for kv in v.split():
         k_, val = kv.split("=")
+        if k_ == "LIB":                      # a differently compiled engine build, loaded side by side
+            lrm._abi._lib = lrm._abi.load(os.path.join(ROOT, val))
+            continue
         os.environ[k_] = val
         keys.append(k_)
     eng = lrm.Engine(ep, validate=False)
