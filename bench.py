@@ -87,7 +87,9 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        # samples inside the timed region; the region is tens of ms, so fall back to the closest samples around it
         rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 9] or \
+               [r for t, r in self.rows if t0 - 0.30 <= t <= t1 + 0.30 and len(r) >= 9] or \
                [r for _, r in self.rows if len(r) >= 9]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
