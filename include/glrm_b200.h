@@ -49,7 +49,7 @@ enum {
 };
 
 /* ---- loss codes (src/losses.jl) ----------------------------------------------------------- *
- * loss_param[f*8 + ...]:  [0]=scale  [1]=p1  [2]=p2  [3]=bin_loss code  [4]=bin scale  [5]=bin p1
+ * loss_param[f*8 + ...]:  [0]=scale  [1]=p1  [2]=p2  [3]=bin_loss code  [4]=bin scale  [5]=bin p1  [6]=bin p2
  *   QUAD           losses.jl:138-146   -
  *   L1             losses.jl:152-160   -
  *   HUBER          losses.jl:166-177   p1=crossover

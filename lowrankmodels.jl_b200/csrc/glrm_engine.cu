@@ -17,7 +17,8 @@
 #include <string>
 #include <vector>
 
-#include "glrm_device.cuh"
+#include "glrm_launch.cuh"
+#include "glrm_small.cuh"
 #include "glrm_vec.cuh"
 
 using namespace glrm;
@@ -92,7 +93,7 @@ struct Side {
   int32_t* d_idx = nullptr;
   double* d_val = nullptr;
   int32_t* d_order = nullptr;
-  int64_t n_cluster = 0, n_heavy = 0, n_light = 0;   // schedule = [cluster tier | CTA tier | warp tier]
+  int64_t n_cluster16 = 0, n_cluster = 0, n_heavy = 0, n_light = 0;   // schedule = [16-CTA clusters | 4-CTA clusters | CTA tier | warp tier]
   int32_t* d_order_vec = nullptr;   // units that go through vec_sweep_kernel (block columns / all rows of a problem with them)
   int64_t n_vec = 0;
   int32_t* d_reg_code = nullptr;
@@ -115,6 +116,7 @@ struct glrmb200_engine {
   double uparam[3] = {1, 0, 0};
   int64_t heavy_threshold = 1024;
   int64_t cluster_threshold = 8192;
+  int64_t cluster16_threshold = 32768;
   int64_t nnz_rows_total = 0;
   bool obs_full = false;
   bool has_vec = false;              // some column has a vector-valued loss
@@ -191,18 +193,23 @@ extern "C" int glrmb200_plan_shards(const int64_t* ptr, int64_t count, int32_t n
   return 0;
 }
 
+// `pad` extra zeroed elements follow the payload: the entry passes read idx[start] / val[start] of a unit even when it
+// is empty, and an empty unit at the end of a shard has start == nnz_local
 template <class T>
-static int upload(T** dst, const T* src, size_t count) {
+static int upload(T** dst, const T* src, size_t count, size_t pad = 0) {
   *dst = nullptr;
-  if (count == 0) count = 1, src = nullptr;
-  CUDA_OK(cudaMalloc((void**)dst, count * sizeof(T)));
+  if (count == 0) src = nullptr;
+  const size_t alloc = std::max<size_t>(1, count + pad);
+  CUDA_OK(cudaMalloc((void**)dst, alloc * sizeof(T)));
+  if (alloc > count) CUDA_OK(cudaMemset(*dst + count, 0, (alloc - count) * sizeof(T)));
   if (src) CUDA_OK(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
   return 0;
 }
 
 // degree-sorted schedule (heaviest first): LPT order for the tail, and neighbouring warps of a CTA get
 // units of similar length.  `is_vec` (optional) routes units to the vector-loss kernel instead.
-static int build_schedule(Side& S, const int64_t* ptr_global, int64_t heavy_threshold, int64_t cluster_threshold, const std::vector<char>* is_vec = nullptr) {
+static int build_schedule(Side& S, const int64_t* ptr_global, const glrmb200_engine* E, const std::vector<char>* is_vec = nullptr) {
+  const int64_t heavy_threshold = E->heavy_threshold, cluster_threshold = E->cluster_threshold, cluster16_threshold = E->cluster16_threshold;
   const int64_t cnt = S.end - S.begin;
   std::vector<int32_t> order, vec;
   order.reserve((size_t)cnt);
@@ -214,11 +221,13 @@ static int build_schedule(Side& S, const int64_t* ptr_global, int64_t heavy_thre
     std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return deg(a) > deg(b); });
     std::stable_sort(vec.begin(), vec.end(), [&](int32_t a, int32_t b) { return deg(a) > deg(b); });
   }
-  S.n_cluster = 0;
-  while (S.n_cluster < (int64_t)order.size() && deg(order[(size_t)S.n_cluster]) >= cluster_threshold) S.n_cluster++;
-  S.n_heavy = 0;
-  while (S.n_cluster + S.n_heavy < (int64_t)order.size() && deg(order[(size_t)(S.n_cluster + S.n_heavy)]) >= heavy_threshold) S.n_heavy++;
-  S.n_light = (int64_t)order.size() - S.n_heavy - S.n_cluster;
+  int64_t pos = 0;
+  const int64_t total = (int64_t)order.size();
+  auto take = [&](int64_t threshold) { const int64_t p0 = pos; while (pos < total && deg(order[(size_t)pos]) >= threshold) ++pos; return pos - p0; };
+  S.n_cluster16 = take(cluster16_threshold);
+  S.n_cluster = take(cluster_threshold);
+  S.n_heavy = take(heavy_threshold);
+  S.n_light = total - pos;
   S.n_vec = (int64_t)vec.size();
   int rc = upload(&S.d_order, order.data(), order.size());
   if (rc) return rc;
@@ -244,81 +253,25 @@ static int setup_regs(Side& S, int64_t count, const int32_t* code, const double*
 }
 
 // ------------------------------------------------------------------------------------------------
-// kernel dispatch over the (G, R) tile and the loss template
+// kernel dispatch over the (G, R) tile and the loss template: the instantiations live in sweep_inst.cu, compiled once
+// per (loss template, tile half) so the build parallelises (csrc/Makefile)
 struct Tile { int g, r; };
 static const Tile kTiles[] = {{4, 1}, {8, 1}, {8, 2}, {8, 3}, {8, 4}, {16, 2}, {16, 3}, {16, 4}, {32, 2}, {32, 3}, {32, 4}};
 
-struct Streams { cudaStream_t main, side; cudaEvent_t fork, join; };
-
-// the two tiers of a sweep touch disjoint units: the warp tier is forked onto the side stream so it fills the
-// SMs the CTA tier leaves idle in its tail, and joined back before anything else is enqueued
-template <int G, int R, int LOSS>
-static cudaError_t launch_tile(const SweepArgs& A0, int64_t n_cluster, int64_t n_heavy, int64_t n_light, const Streams& st, int64_t* launches) {
-  const bool both = (n_heavy > 0 || n_cluster > 0) && n_light > 0 && st.side;
-  SweepArgs A = A0;
-  A.order = A0.order + n_cluster;
-  if (both) {
-    cudaEventRecord(st.fork, st.main);
-    cudaStreamWaitEvent(st.side, st.fork, 0);
-  }
-  if (n_cluster > 0) {                       // super-heavy units first (LPT): a cluster of CTAs per unit
-    SweepArgs K = A0;
-    K.n_units = n_cluster;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(n_cluster * CLUSTER_CTAS), 1, 1);
-    cfg.blockDim = dim3(WARPS_PER_CTA_HEAVY * 32, 1, 1);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = st.main;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CLUSTER_CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t ce = cudaLaunchKernelEx(&cfg, sweep_cluster_kernel<G, R, LOSS>, K);
-    if (ce != cudaSuccess) return ce;
-    ++*launches;
-  }
-  if (n_heavy > 0) {
-    SweepArgs H = A;
-    H.n_units = n_heavy;
-    sweep_cta_kernel<G, R, LOSS><<<(unsigned)n_heavy, WARPS_PER_CTA_HEAVY * 32, 0, st.main>>>(H);
-    ++*launches;
-  }
-  if (n_light > 0) {
-    SweepArgs L = A;
-    L.order = A.order + n_heavy;
-    L.n_units = n_light;
-    const int64_t grid = (n_light + WARPS_PER_CTA_LIGHT - 1) / WARPS_PER_CTA_LIGHT;
-    sweep_warp_kernel<G, R, LOSS><<<(unsigned)grid, WARPS_PER_CTA_LIGHT * 32, 0, both ? st.side : st.main>>>(L);
-    ++*launches;
-  }
-  if (both) {
-    cudaEventRecord(st.join, st.side);
-    cudaStreamWaitEvent(st.main, st.join, 0);
-  }
-  return cudaGetLastError();
-}
-
-template <int LOSS>
-static cudaError_t launch_loss(int g, int r, const SweepArgs& A, int64_t nc, int64_t nh, int64_t nl, const Streams& st, int64_t* launches) {
-#define T(GG, RR) if (g == GG && r == RR) return launch_tile<GG, RR, LOSS>(A, nc, nh, nl, st, launches)
-  T(4, 1); T(8, 1); T(8, 2); T(8, 3); T(8, 4); T(16, 2); T(16, 3); T(16, 4); T(32, 2); T(32, 3); T(32, 4);
-#undef T
-  return cudaErrorInvalidValue;
-}
-
 static cudaError_t launch_sweep(const glrmb200_engine* E, const SweepArgs& A, const Side& S, int64_t* launches) {
-  const int64_t nc = S.n_cluster, nh = S.n_heavy, nl = S.n_light;
+  const TierCounts tc{S.n_cluster16, S.n_cluster, S.n_heavy, S.n_light};
   static const bool two_streams = !(getenv("GLRMB200_ONE_STREAM") && atoi(getenv("GLRMB200_ONE_STREAM")));
   const Streams st{E->stream, two_streams ? E->stream2 : nullptr, E->ev_fork, E->ev_join};
+  const bool wide = E->tile_g >= 16;
   switch (E->loss_template) {
-    case GLRMB200_LOSS_QUAD: return launch_loss<GLRMB200_LOSS_QUAD>(E->tile_g, E->tile_r, A, nc, nh, nl, st, launches);
-    case GLRMB200_LOSS_LOGISTIC: return launch_loss<GLRMB200_LOSS_LOGISTIC>(E->tile_g, E->tile_r, A, nc, nh, nl, st, launches);
-    default: return launch_loss<0>(E->tile_g, E->tile_r, A, nc, nh, nl, st, launches);
+    case GLRMB200_LOSS_QUAD: return (wide ? launch_quad_wide : launch_quad_narrow)(E->tile_g, E->tile_r, A, tc, st, launches);
+    case GLRMB200_LOSS_LOGISTIC: return (wide ? launch_logistic_wide : launch_logistic_narrow)(E->tile_g, E->tile_r, A, tc, st, launches);
+    default: return (wide ? launch_generic_wide : launch_generic_narrow)(E->tile_g, E->tile_r, A, tc, st, launches);
   }
 }
 
-// units that involve vector-valued losses (csrc/glrm_vec.cuh): one warp per unit
+// units that involve vector-valued losses (csrc/glrm_vec.cuh, instantiated in vec_inst.cu): one warp per unit
+namespace glrm { cudaError_t launch_vec_inst(int g, int r, const VecArgs& V, bool x_side, int64_t n_vec, cudaStream_t stream, int64_t* launches); }
 static cudaError_t launch_vec(const glrmb200_engine* E, const SweepArgs& A, bool x_side, const Side& S, int64_t* launches) {
   if (S.n_vec == 0) return cudaSuccess;
   VecArgs V;
@@ -328,18 +281,7 @@ static cudaError_t launch_vec(const glrmb200_engine* E, const SweepArgs& A, bool
   V.s.own_col = nullptr;
   V.ystart = E->d_ystart;
   V.x_side = x_side ? 1 : 0;
-  const unsigned grid = (unsigned)((S.n_vec + 3) / 4);
-  const int g = E->tile_g, r = E->tile_r;
-#define T(GG, RR)                                                                                    \
-  if (g == GG && r == RR) {                                                                          \
-    if (x_side) vec_sweep_kernel<GG, RR, 1><<<grid, 128, 0, E->stream>>>(V);                          \
-    else vec_sweep_kernel<GG, RR, VEC_DMAX><<<grid, 128, 0, E->stream>>>(V);                          \
-    ++*launches;                                                                                     \
-    return cudaGetLastError();                                                                       \
-  }
-  T(4, 1) T(8, 1) T(8, 2)
-#undef T
-  return cudaErrorInvalidValue;
+  return launch_vec_inst(E->tile_g, E->tile_r, V, x_side, S.n_vec, E->stream, launches);
 }
 
 static cudaError_t launch_reg_eval(const glrmb200_engine* E, const double* own, const Side& S, double* out) {
@@ -491,9 +433,9 @@ static int load_lists(glrmb200_engine* E, const int64_t* row_ptr, const int32_t*
     for (int64_t i = 0; i <= cnt; ++i) local[(size_t)i] = ptr[S.begin + i] - q0;
     int r2 = upload(&S.d_ptr, local.data(), local.size());
     if (r2) return r2;
-    if ((r2 = upload(&S.d_idx, idx ? idx + q0 : nullptr, (size_t)S.nnz_local))) return r2;
-    if ((r2 = upload(&S.d_val, val ? val + q0 : nullptr, (size_t)S.nnz_local))) return r2;
-    return build_schedule(S, ptr, E->heavy_threshold, E->cluster_threshold, E->has_vec ? vecflags : nullptr);
+    if ((r2 = upload(&S.d_idx, idx ? idx + q0 : nullptr, (size_t)S.nnz_local, 32))) return r2;
+    if ((r2 = upload(&S.d_val, val ? val + q0 : nullptr, (size_t)S.nnz_local, 32))) return r2;
+    return build_schedule(S, ptr, E, E->has_vec ? vecflags : nullptr);
   };
   if ((rc = up_side(R, row_ptr, row_idx, row_val, &E->all_rows_vec))) return rc;
   if ((rc = up_side(C, col_ptr, col_idx, col_val, &E->col_is_vec))) return rc;
@@ -592,7 +534,9 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
     return fail(GLRMB200_E_UNSUPPORTED, "vector-valued losses are supported on the device for k <= 32 this round (k = %lld)", (long long)k);
   if (const char* t = getenv("GLRMB200_HEAVY")) E->heavy_threshold = std::max<long long>(1, atoll(t));
   if (const char* t = getenv("GLRMB200_CLUSTER")) E->cluster_threshold = std::max<long long>(1, atoll(t));
+  if (const char* t = getenv("GLRMB200_CLUSTER16")) E->cluster16_threshold = std::max<long long>(1, atoll(t));
   if (E->cluster_threshold < E->heavy_threshold) E->cluster_threshold = E->heavy_threshold;
+  if (E->cluster16_threshold < E->cluster_threshold) E->cluster16_threshold = E->cluster_threshold;
 
   // ---- observation lists: validation (glrm.jl:63-71, losses.jl:104) ----------------------------
   Side& R = E->rows;
@@ -670,8 +614,8 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
       cudaFree(d_rowmajor);
       cudaFree(d_full);
     }
-    if ((rc = build_schedule(R, nullptr, E->heavy_threshold, E->cluster_threshold, E->has_vec ? &all_rows_vec : nullptr))) return rc;
-    if ((rc = build_schedule(C, nullptr, E->heavy_threshold, E->cluster_threshold, E->has_vec ? &col_is_vec : nullptr))) return rc;
+    if ((rc = build_schedule(R, nullptr, E, E->has_vec ? &all_rows_vec : nullptr))) return rc;
+    if ((rc = build_schedule(C, nullptr, E, E->has_vec ? &col_is_vec : nullptr))) return rc;
     {
       unsigned long long* d_bad = nullptr;
       CUDA_OK(cudaMalloc((void**)&d_bad, sizeof(unsigned long long)));

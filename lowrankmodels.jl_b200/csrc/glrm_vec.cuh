@@ -21,8 +21,8 @@ struct VecArgs {
 
 // ---- vector losses: value and gradient (scaled), u[0..D) -------------------------------------------------------
 // bin-loss dispatch for OvA / BvS (losses.jl:419,456: any scalar loss; default LogisticLoss(scale))
-__device__ __forceinline__ void bin_eval(int bcode, double bs, double bp1, double u, bool label, double& l, double& c) {
-  loss_eval<0, true>(bcode, bs, bp1, 0.0, u, label ? 1.0 : 0.0, l, c);
+__device__ __forceinline__ void bin_eval(int bcode, double bs, double bp1, double bp2, double u, bool label, double& l, double& c) {
+  loss_eval<0, true>(bcode, bs, bp1, bp2, u, label ? 1.0 : 0.0, l, c);
 }
 
 template <bool WANT_GRAD>
@@ -50,11 +50,11 @@ __device__ __forceinline__ double vec_loss(int code, const double* __restrict__ 
     case GLRMB200_LOSS_OVA:            // :424-438   (scale applied on top of the bin loss's own scale, as in the reference)
     case GLRMB200_LOSS_BVS: {          // :461-475
       const int bcode = (int)lp[3];
-      const double bs = lp[4], bp1 = lp[5];
+      const double bs = lp[4], bp1 = lp[5], bp2 = lp[6];
 #pragma unroll
       for (int j = 0; j < VEC_DMAX; ++j) if (j < D) {
         double l, c;
-        bin_eval(bcode, bs, bp1, u[j], code == GLRMB200_LOSS_OVA ? (a == j + 1) : (a > j + 1), l, c);
+        bin_eval(bcode, bs, bp1, bp2, u[j], code == GLRMB200_LOSS_OVA ? (a == j + 1) : (a > j + 1), l, c);
         loss += l;
         gc[j] = s * c;
       }

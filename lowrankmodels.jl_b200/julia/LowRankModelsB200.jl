@@ -85,7 +85,8 @@ lossrow(l::WeightedHingeLoss) = (9, (l.scale, l.case_weight_ratio))
 lossrow(l::MultinomialLoss)   = (10, (l.scale, 0.0, Float64(l.max)))
 function lossrow(l::Union{OvALoss,BvSLoss})
     bc, bp = lossrow(l.bin_loss)
-    (l isa OvALoss ? 11 : 12, (l.scale, 0.0, Float64(l.max), Float64(bc), bp[1], length(bp) > 1 ? bp[2] : 0.0))
+    (l isa OvALoss ? 11 : 12, (l.scale, 0.0, Float64(l.max), Float64(bc), bp[1], length(bp) > 1 ? bp[2] : 0.0,
+                                 length(bp) > 2 ? bp[3] : 0.0))
 end
 lossrow(l::OrdisticLoss)           = (13, (l.scale, 0.0, Float64(l.max)))
 lossrow(l::MultinomialOrdinalLoss) = (14, (l.scale, 0.0, Float64(l.max)))

@@ -155,7 +155,7 @@ class _LevelLoss(Loss):
             if b.embedding_dim() != 1 or isinstance(b, _LevelLoss):
                 raise ValueError("bin_loss must be a scalar loss")
             bcode, bp = b.encode()
-            out += [(3, bcode), (4, bp[0]), (5, bp[1])]
+            out += [(3, bcode), (4, bp[0]), (5, bp[1]), (6, bp[2])]
         return tuple(out)
 
 

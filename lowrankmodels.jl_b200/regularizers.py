@@ -90,6 +90,12 @@ class NonNegOneReg(Regularizer):  # regularizers.jl:118-138
     def _p0(self):
         return self.scale
 
+    def get_scale(self):        # scale(r::NonNegOneReg) = 1 (regularizers.jl:137)
+        return 1.0
+
+    def mul(self, newscale):    # mul!(r::NonNegOneReg, newscale) = 1: a no-op (regularizers.jl:138)
+        return self
+
 
 @dataclass
 class OneSparseConstraint(Regularizer):  # regularizers.jl:235-255

@@ -196,14 +196,14 @@ static double vl_eval(int code, const double* p, const double* uin, int D, doubl
     }
     case GLRMB200_LOSS_OVA: {                                                  /* :424-430 */
       const int bcode = (int)p[3];
-      const double bp[GLRMB200_LOSS_NPARAM] = {p[4], p[5], 0, 0, 0, 0, 0, 0};
+      const double bp[GLRMB200_LOSS_NPARAM] = {p[4], p[5], p[6], 0, 0, 0, 0, 0};
       double loss = 0;
       for (int j = 0; j < D; ++j) loss += sl_eval(bcode, bp, u[j], (a == j + 1) ? 1.0 : 0.0, err);
       return s * loss;
     }
     case GLRMB200_LOSS_BVS: {                                                  /* :461-467 */
       const int bcode = (int)p[3];
-      const double bp[GLRMB200_LOSS_NPARAM] = {p[4], p[5], 0, 0, 0, 0, 0, 0};
+      const double bp[GLRMB200_LOSS_NPARAM] = {p[4], p[5], p[6], 0, 0, 0, 0, 0};
       double loss = 0;
       for (int j = 0; j < D; ++j) loss += sl_eval(bcode, bp, u[j], (a > j + 1) ? 1.0 : 0.0, err);
       return s * loss;
@@ -252,13 +252,13 @@ static void vl_grad(int code, const double* p, const double* uin, int D, double 
     }
     case GLRMB200_LOSS_OVA: {                                                  /* :432-438 */
       const int bcode = (int)p[3];
-      const double bp[GLRMB200_LOSS_NPARAM] = {p[4], p[5], 0, 0, 0, 0, 0, 0};
+      const double bp[GLRMB200_LOSS_NPARAM] = {p[4], p[5], p[6], 0, 0, 0, 0, 0};
       for (int j = 0; j < D; ++j) g[j] = s * sl_grad(bcode, bp, u[j], (a == j + 1) ? 1.0 : 0.0, err);
       return;
     }
     case GLRMB200_LOSS_BVS: {                                                  /* :469-475 */
       const int bcode = (int)p[3];
-      const double bp[GLRMB200_LOSS_NPARAM] = {p[4], p[5], 0, 0, 0, 0, 0, 0};
+      const double bp[GLRMB200_LOSS_NPARAM] = {p[4], p[5], p[6], 0, 0, 0, 0, 0};
       for (int j = 0; j < D; ++j) g[j] = s * sl_grad(bcode, bp, u[j], (a > j + 1) ? 1.0 : 0.0, err);
       return;
     }

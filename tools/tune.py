@@ -9,8 +9,10 @@ from bench import build_problem
 
 config = sys.argv[1] if len(sys.argv) > 1 else "C2"
 scale = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-variants = sys.argv[3:] or ["", "GLRMB200_PACKED=1", "GLRMB200_TILE=16,2", "GLRMB200_TILE=16,4", "GLRMB200_HEAVY=512",
-                            "GLRMB200_HEAVY=2048", "GLRMB200_HEAVY=4096"]
+variants = sys.argv[3:] or ["", "GLRMB200_HEAVY=512", "GLRMB200_HEAVY=512 GLRMB200_CLUSTER=4096",
+                            "GLRMB200_HEAVY=512 GLRMB200_CLUSTER=4096 GLRMB200_CLUSTER16=16384",
+                            "GLRMB200_HEAVY=256 GLRMB200_CLUSTER=2048 GLRMB200_CLUSTER16=16384",
+                            "GLRMB200_HEAVY=1024 GLRMB200_CLUSTER=4096 GLRMB200_CLUSTER16=16384"]
 g, cfg = build_problem(config, scale)
 ep = lrm.encode_problem(g, validate=False)
 nnz = ep.nnz
