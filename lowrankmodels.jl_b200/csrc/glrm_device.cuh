@@ -66,7 +66,12 @@ struct SweepArgs {
   double* const* peer_own;   // [n_peers] or nullptr
   double* const* peer_obj;   // [n_peers] or nullptr
   int32_t n_peers;
+  const int* stop;           // device flag set by record_kernel when the stopping rule fired (proxgrad.jl:209-213): the host
+                             // enqueues iterations ahead of the device, launches after the stop are no-ops
 };
+__device__ __forceinline__ bool sweep_stopped(const SweepArgs& A) {
+  return A.stop != nullptr && *reinterpret_cast<const volatile int*>(A.stop) != 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -828,7 +833,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA_LIGHT * 32, TileCfg<R>::LIGHT_CT
   const int64_t slot = (int64_t)blockIdx.x * WARPS_PER_CTA_LIGHT + (threadIdx.x >> 5);
   __shared__ double part[WARPS_PER_CTA_LIGHT * TRIAL_TILE_DOUBLES(G)];
   __shared__ __align__(16) double xg[WARPS_PER_CTA_LIGHT * 4 * G * R];
-  if (slot >= A.n_units) return;
+  if (slot >= A.n_units || sweep_stopped(A)) return;
   process_unit<G, R, 1, LOSS, TileCfg<R>::DEPTH>(A, A.order[slot], nullptr, part, xg + (threadIdx.x >> 5) * 4 * G * R);
 }
 
@@ -838,6 +843,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32, TileCfg<R>::HEAVY_CT
   __shared__ double red[WARPS_PER_CTA_HEAVY * (G * 2 * R + 1)];
   __shared__ double part[WARPS_PER_CTA_HEAVY * TRIAL_TILE_DOUBLES(G)];
   __shared__ __align__(16) double xg[4 * G * R];
+  if (sweep_stopped(A)) return;
   process_unit<G, R, WARPS_PER_CTA_HEAVY, LOSS, TileCfg<R>::DEPTH>(A, A.order[blockIdx.x], red, part, xg);
 }
 
@@ -853,6 +859,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32, TileCfg<R>::HEAVY_CT
   __shared__ double part[WARPS_PER_CTA_HEAVY * TRIAL_TILE_DOUBLES(G)];
   __shared__ __align__(16) double xg[4 * G * R];
   __shared__ __align__(16) double clbuf[2 + 2 * G * R];
+  if (sweep_stopped(A)) return;                // the same value in every CTA of the cluster: the flag only changes between kernels
   process_unit<G, R, WARPS_PER_CTA_HEAVY, LOSS, TileCfg<R>::DEPTH, CS>(A, A.order[blockIdx.x / CS], red, part, xg, clbuf);
 }
 

@@ -106,6 +106,9 @@ struct Side {
   std::vector<int64_t> bounds;  // [nranks+1] shard boundaries (all ranks)
 };
 
+constexpr int EVENT_CHUNK = 64;   // iterations whose timing events are in flight before the host harvests them
+constexpr int MAX_RANKS = 64;     // slots of the peer flag array
+
 struct glrmb200_engine {
   int device = 0, rank = 0, nranks = 1;
   int64_t m = 0, n = 0, k = 0, d = 0;
@@ -116,7 +119,7 @@ struct glrmb200_engine {
   double uparam[3] = {1, 0, 0};
   int64_t heavy_threshold = 1024;
   int64_t cluster_threshold = 8192;
-  int64_t cluster16_threshold = 32768;
+  int64_t cluster16_threshold = 16384;
   int64_t nnz_rows_total = 0;
   bool obs_full = false;
   bool has_vec = false;              // some column has a vector-valued loss
@@ -127,17 +130,24 @@ struct glrmb200_engine {
   Side rows, cols;
   int32_t* d_loss_code = nullptr;
   double* d_loss_param = nullptr;
-  double* d_xchg = nullptr;                  // ONE allocation [X | Y | obj_by_col] (>= 2 MiB granule): one IPC handle
+  double* d_xchg = nullptr;                  // ONE allocation [X | Y | obj_by_col | peer flags] (2 MiB granules): one IPC handle
   size_t xchg_bytes = 0;
   double* d_X = nullptr;
   double* d_Y = nullptr;
+  unsigned long long* d_flags = nullptr;     // [MAX_RANKS] epochs published by the peers (inside d_xchg)
   double* d_scalars = nullptr;              // [4]
   unsigned long long* d_trials = nullptr;   // [2]
-  double* h_pinned = nullptr;               // [8]
+  int* d_stop = nullptr;                    // [2]: stop iteration (0 = running), barrier time-out flag
+  double* d_objs = nullptr;                 // [objs_cap] objective record of the running fit
+  int64_t objs_cap = 0;
+  double* d_stage = nullptr;                // staging buffer for contiguous factor transfers [(m + d) * k]
+  double* h_pinned = nullptr;               // [8] process-level pinned scratch (not owned)
+  volatile int* h_stop = nullptr;           // mapped pinned flag written by record_kernel (not owned)
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;            // the warp-tier launch of a sweep runs here, concurrently with the CTA tier
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_base = nullptr, ev_aux = nullptr;
+  std::vector<cudaEvent_t> evpool;           // EVENT_CHUNK x 5 per-iteration timing events
   ncclComm_t comm = nullptr;
   bool factors_resident = false;
   // fused exchange: peers' replicas opened through CUDA IPC (index = position among the other ranks)
@@ -147,6 +157,9 @@ struct glrmb200_engine {
   double** d_peer_X = nullptr;
   double** d_peer_Y = nullptr;
   double** d_peer_objc = nullptr;
+  unsigned long long** d_peer_flags = nullptr;
+  int* d_peer_rank = nullptr;
+  unsigned long long epoch = 0;              // barriers executed since the flags were last zeroed (glrmb200_ipc_export)
   double* d_barrier = nullptr;
 };
 
@@ -164,6 +177,15 @@ static int check_device() {
   return 0;
 }
 
+// process-level pinned scratch: [0..7] doubles for scalar read-backs, then the mapped stop flag
+static double* g_pinned = nullptr;
+static int pinned_setup() {
+  if (g_pinned) return 0;
+  CUDA_OK(cudaHostAlloc((void**)&g_pinned, 16 * sizeof(double), cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(g_pinned, 0, 16 * sizeof(double));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-side helpers
 static int loss_dim(int code, const double* p) {
@@ -174,18 +196,28 @@ static int loss_dim(int code, const double* p) {
   }
 }
 
+// Predicted cost of updating one unit, in entry slots: a pass walks the list in chunks of 32 entries (a partial chunk
+// costs a whole one) and every unit pays a fixed overhead (pipeline start-up, line search, write-back) of about one chunk.
+static inline int64_t unit_cost(int64_t deg) { return ((deg + 31) / 32) * 32 + 32; }
+
 extern "C" int glrmb200_plan_shards(const int64_t* ptr, int64_t count, int32_t nranks, int64_t* bounds) {
-  // contiguous shards balanced by observation count (ptr == NULL: by unit count)
+  // contiguous shards balanced by predicted cost (ptr == NULL: by unit count)
   if (nranks < 1 || count < 0 || !bounds) return fail(GLRMB200_E_INVALID, "plan_shards: bad arguments");
   bounds[0] = 0;
   bounds[nranks] = count;
-  const int64_t total = ptr ? ptr[count] - ptr[0] : count;
+  if (!ptr || ptr[count] - ptr[0] == 0) {
+    for (int r = 1; r < nranks; ++r) bounds[r] = count * r / nranks;
+    return 0;
+  }
+  std::vector<int64_t> cum((size_t)count + 1);
+  cum[0] = 0;
+  for (int64_t u = 0; u < count; ++u) cum[(size_t)u + 1] = cum[(size_t)u] + unit_cost(ptr[u + 1] - ptr[u]);
+  const int64_t total = cum[(size_t)count];
   for (int r = 1; r < nranks; ++r) {
-    if (!ptr || total == 0) { bounds[r] = count * r / nranks; continue; }
-    const int64_t target = ptr[0] + (total / nranks) * r + std::min<int64_t>(r, total % nranks);
-    const int64_t* it = std::lower_bound(ptr, ptr + count + 1, target);
-    if (it > ptr && it <= ptr + count && target - *(it - 1) < *it - target) --it;   // nearest boundary
-    int64_t b = it - ptr;
+    const int64_t target = (total / nranks) * r + std::min<int64_t>(r, total % nranks);
+    auto it = std::lower_bound(cum.begin(), cum.end(), target);
+    if (it != cum.begin() && it != cum.end() && target - *(it - 1) < *it - target) --it;   // nearest boundary
+    int64_t b = it - cum.begin();
     if (b > count) b = count;
     if (b < bounds[r - 1]) b = bounds[r - 1];
     bounds[r] = b;
@@ -193,23 +225,54 @@ extern "C" int glrmb200_plan_shards(const int64_t* ptr, int64_t count, int32_t n
   return 0;
 }
 
-// `pad` extra zeroed elements follow the payload: the entry passes read idx[start] / val[start] of a unit even when it
-// is empty, and an empty unit at the end of a shard has start == nnz_local
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync, release threshold = keep everything):
+// allocation and free cost microseconds instead of the 0.1-1 ms of cudaMalloc / cudaFree — and pool memory is not
+// mapped into the peers, so freeing it does not pay the cross-device unmap that made destroy cost 0.22 s at 8 GPUs
+// once CUDA IPC had enabled peer access (round-1 SCALE record).  Only the exchange allocation, which must be
+// exportable through CUDA IPC, is a plain cudaMalloc (and is cached per process, see XchgCache).
+static int pool_setup(int device) {
+  static std::vector<char> done;
+  if ((int)done.size() <= device) done.resize((size_t)device + 1, 0);
+  if (done[(size_t)device]) return 0;
+  cudaMemPool_t pool;
+  CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t keep = UINT64_MAX;
+  CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  done[(size_t)device] = 1;
+  return 0;
+}
 template <class T>
-static int upload(T** dst, const T* src, size_t count, size_t pad = 0) {
+static int dalloc(T** dst, size_t count, cudaStream_t st) {
   *dst = nullptr;
+  CUDA_OK(cudaMallocAsync((void**)dst, std::max<size_t>(1, count) * sizeof(T), st));
+  return 0;
+}
+template <class T>
+static void dfree(T*& p, cudaStream_t st) {
+  if (p) cudaFreeAsync((void*)p, st);
+  p = nullptr;
+}
+
+// `pad` extra zeroed elements follow the payload: the entry passes read idx[start] / val[start] of a unit even when it
+// is empty, and an empty unit at the end of a shard has start == nnz_local.  The copy is stream-ordered: from pinned
+// host memory it is a true asynchronous DMA (the caller synchronises before handing the host buffer back), from
+// pageable memory cudaMemcpyAsync returns once the source has been staged.
+template <class T>
+static int upload(T** dst, const T* src, size_t count, cudaStream_t st, size_t pad = 0) {
   if (count == 0) src = nullptr;
   const size_t alloc = std::max<size_t>(1, count + pad);
-  CUDA_OK(cudaMalloc((void**)dst, alloc * sizeof(T)));
-  if (alloc > count) CUDA_OK(cudaMemset(*dst + count, 0, (alloc - count) * sizeof(T)));
-  if (src) CUDA_OK(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+  int rc = dalloc(dst, alloc, st);
+  if (rc) return rc;
+  if (alloc > count) CUDA_OK(cudaMemsetAsync(*dst + count, 0, (alloc - count) * sizeof(T), st));
+  if (src) CUDA_OK(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
   return 0;
 }
 
 // degree-sorted schedule (heaviest first): LPT order for the tail, and neighbouring warps of a CTA get
 // units of similar length.  `is_vec` (optional) routes units to the vector-loss kernel instead.
-static int build_schedule(Side& S, const int64_t* ptr_global, const glrmb200_engine* E, const std::vector<char>* is_vec = nullptr) {
-  const int64_t heavy_threshold = E->heavy_threshold, cluster_threshold = E->cluster_threshold, cluster16_threshold = E->cluster16_threshold;
+// NB: the tier of a unit (warp / CTA / cluster) fixes its reduction tree, so the thresholds are constants of the
+// unit's degree — never of the rank count — or a sharded fit would stop being bit-identical to the 1-GPU fit.
+static int build_schedule(glrmb200_engine* E, Side& S, const int64_t* ptr_global, const std::vector<char>* is_vec = nullptr) {
   const int64_t cnt = S.end - S.begin;
   std::vector<int32_t> order, vec;
   order.reserve((size_t)cnt);
@@ -224,17 +287,17 @@ static int build_schedule(Side& S, const int64_t* ptr_global, const glrmb200_eng
   int64_t pos = 0;
   const int64_t total = (int64_t)order.size();
   auto take = [&](int64_t threshold) { const int64_t p0 = pos; while (pos < total && deg(order[(size_t)pos]) >= threshold) ++pos; return pos - p0; };
-  S.n_cluster16 = take(cluster16_threshold);
-  S.n_cluster = take(cluster_threshold);
-  S.n_heavy = take(heavy_threshold);
+  S.n_cluster16 = take(E->cluster16_threshold);
+  S.n_cluster = take(E->cluster_threshold);
+  S.n_heavy = take(E->heavy_threshold);
   S.n_light = total - pos;
   S.n_vec = (int64_t)vec.size();
-  int rc = upload(&S.d_order, order.data(), order.size());
+  int rc = upload(&S.d_order, order.data(), order.size(), E->stream);
   if (rc) return rc;
-  return upload(&S.d_order_vec, vec.data(), vec.size());
+  return upload(&S.d_order_vec, vec.data(), vec.size(), E->stream);
 }
 
-static int setup_regs(Side& S, int64_t count, const int32_t* code, const double* param, bool allow_ordinal) {
+static int setup_regs(glrmb200_engine* E, Side& S, int64_t count, const int32_t* code, const double* param, bool allow_ordinal) {
   if (count != 1 && count != S.units) return fail(GLRMB200_E_INVALID, "regularizer count must be 1 or the number of columns");
   S.reg_uniform = (count == 1);
   S.h_reg_code.assign(code, code + count);
@@ -247,9 +310,9 @@ static int setup_regs(Side& S, int64_t count, const int32_t* code, const double*
     if (base > GLRMB200_REG_SIMPLEX || (code[i] & ~(GLRMB200_REG_BASE_MASK | GLRMB200_REG_LASTENTRY1 | GLRMB200_REG_LASTENTRY_UNPENALIZED | GLRMB200_REG_ORDINAL | GLRMB200_REG_MNL_ORDINAL)))
       return fail(GLRMB200_E_UNSUPPORTED, "regularizer code %d has no device implementation", code[i]);
   }
-  int rc = upload(&S.d_reg_code, code, (size_t)count);
+  int rc = upload(&S.d_reg_code, code, (size_t)count, E->stream);
   if (rc) return rc;
-  return upload(&S.d_reg_param, param, (size_t)count * GLRMB200_REG_NPARAM);
+  return upload(&S.d_reg_param, param, (size_t)count * GLRMB200_REG_NPARAM, E->stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -294,7 +357,7 @@ static cudaError_t launch_reg_eval(const glrmb200_engine* E, const double* own, 
   return cudaErrorInvalidValue;
 }
 
-static SweepArgs make_args(const glrmb200_engine* E, bool x_side, int flags, double min_stepsize) {
+static SweepArgs make_args(const glrmb200_engine* E, bool x_side, int flags, double min_stepsize, bool honour_stop = false) {
   const Side& S = x_side ? E->rows : E->cols;
   SweepArgs A;
   A.ptr = S.d_ptr;
@@ -325,6 +388,7 @@ static SweepArgs make_args(const glrmb200_engine* E, bool x_side, int flags, dou
   A.peer_own = E->peer_ready ? (x_side ? E->d_peer_X : E->d_peer_Y) : nullptr;
   A.peer_obj = (E->peer_ready && !x_side) ? E->d_peer_objc : nullptr;
   A.n_peers = E->peer_ready ? E->nranks - 1 : 0;
+  A.stop = honour_stop ? E->d_stop : nullptr;
   return A;
 }
 
@@ -340,9 +404,13 @@ extern "C" int glrmb200_device_count(int32_t* count) {
   return 0;
 }
 
-static void free_side(Side& S) {
-  cudaFree(S.d_ptr); cudaFree(S.d_idx); cudaFree(S.d_val); cudaFree(S.d_order); cudaFree(S.d_order_vec);
-  cudaFree(S.d_reg_code); cudaFree(S.d_reg_param); cudaFree(S.d_alpha); cudaFree(S.d_obj);
+static void free_lists(glrmb200_engine* E, Side& S) {
+  dfree(S.d_ptr, E->stream); dfree(S.d_idx, E->stream); dfree(S.d_val, E->stream);
+  dfree(S.d_order, E->stream); dfree(S.d_order_vec, E->stream);
+}
+static void free_side(glrmb200_engine* E, Side& S) {
+  free_lists(E, S);
+  dfree(S.d_reg_code, E->stream); dfree(S.d_reg_param, E->stream); dfree(S.d_alpha, E->stream); dfree(S.d_obj, E->stream);
 }
 
 // Process-level cache of the exchange allocation and its peer mappings.  cudaIpcCloseMemHandle + cudaFree of an
@@ -356,13 +424,14 @@ struct XchgCache {
   std::vector<uint8_t> blobs;
   std::vector<void*> opened;
   double** dpx = nullptr; double** dpy = nullptr; double** dpo = nullptr;
+  unsigned long long** dpf = nullptr; int* dpr = nullptr;
 };
 static XchgCache g_xc;
 static void xc_release(XchgCache& c) {
   if (!c.d_xchg) return;
   cudaSetDevice(c.device);
   for (void* p : c.opened) cudaIpcCloseMemHandle(p);
-  cudaFree(c.dpx); cudaFree(c.dpy); cudaFree(c.dpo);
+  cudaFree(c.dpx); cudaFree(c.dpy); cudaFree(c.dpo); cudaFree(c.dpf); cudaFree(c.dpr);
   cudaFree(c.d_xchg);
   c = XchgCache();
 }
@@ -372,33 +441,36 @@ extern "C" int glrmb200_destroy(glrmb200_handle E) {
   cudaSetDevice(E->device);
   if (E->stream) cudaStreamSynchronize(E->stream);
   // E->comm is the process-wide cached communicator (glrmb200_comm_init): not destroyed with the handle
-  if (E->d_xchg && !E->opened.empty()) {      // park the exchange allocation with its peer mappings
+  if (E->d_xchg) {                            // park the exchange allocation (with its peer mappings, if any)
     xc_release(g_xc);
     g_xc.device = E->device; g_xc.rank = E->rank; g_xc.nranks = E->nranks; g_xc.bytes = E->xchg_bytes;
     g_xc.d_xchg = E->d_xchg; g_xc.blobs = E->peer_blobs; g_xc.opened = E->opened;
-    g_xc.dpx = E->d_peer_X; g_xc.dpy = E->d_peer_Y; g_xc.dpo = E->d_peer_objc;
+    g_xc.dpx = E->d_peer_X; g_xc.dpy = E->d_peer_Y; g_xc.dpo = E->d_peer_objc; g_xc.dpf = E->d_peer_flags; g_xc.dpr = E->d_peer_rank;
     E->d_xchg = nullptr;
-  } else {
-    cudaFree(E->d_peer_X); cudaFree(E->d_peer_Y); cudaFree(E->d_peer_objc);
   }
-  cudaFree(E->d_barrier);
-  E->cols.d_obj = nullptr;   // lives inside d_xchg
-  free_side(E->rows); free_side(E->cols);
-  cudaFree(E->d_loss_code); cudaFree(E->d_loss_param); cudaFree(E->d_xchg); cudaFree(E->d_ystart);
-  cudaFree(E->d_scalars); cudaFree(E->d_trials);
-  if (E->h_pinned) cudaFreeHost(E->h_pinned);
-  for (auto& e : E->ev) if (e) cudaEventDestroy(e);
+  if (E->stream) {
+    E->cols.d_obj = nullptr;   // lives inside d_xchg
+    free_side(E, E->rows); free_side(E, E->cols);
+    dfree(E->d_loss_code, E->stream); dfree(E->d_loss_param, E->stream); dfree(E->d_ystart, E->stream);
+    dfree(E->d_scalars, E->stream); dfree(E->d_trials, E->stream); dfree(E->d_stop, E->stream);
+    dfree(E->d_objs, E->stream); dfree(E->d_stage, E->stream); dfree(E->d_barrier, E->stream);
+  }
+  for (auto& e : E->evpool) if (e) cudaEventDestroy(e);
+  if (E->ev_base) cudaEventDestroy(E->ev_base);
+  if (E->ev_aux) cudaEventDestroy(E->ev_aux);
   if (E->ev_fork) cudaEventDestroy(E->ev_fork);
   if (E->ev_join) cudaEventDestroy(E->ev_join);
   if (E->stream2) cudaStreamDestroy(E->stream2);
-  if (E->stream) cudaStreamDestroy(E->stream);
+  if (E->stream) cudaStreamDestroy(E->stream);   // work already enqueued (the frees) still completes
   delete E;
   return 0;
 }
 
-// Observation lists (list mode): host checks, nnz-balanced shards, upload of this rank's shard, device-side
+// Observation lists (list mode): host checks, cost-balanced shards, upload of this rank's shard, device-side
 // validation (index bounds, NaN, label domains), degree-sorted schedules.  Used by glrmb200_create and by
 // glrmb200_set_obs (new lists on a live handle: cross-validation folds, src/cross_validate.jl:31-33).
+// The four big copies are enqueued first; the host-side work (monotonicity checks, local ptr arrays, the two degree
+// sorts) runs while they are in flight, and one synchronisation at the end hands the host buffers back.
 static int load_lists(glrmb200_engine* E, const int64_t* row_ptr, const int32_t* row_idx, const double* row_val,
                       const int64_t* col_ptr, const int32_t* col_idx, const double* col_val) {
   const int64_t m = E->m, n = E->n;
@@ -421,27 +493,34 @@ static int load_lists(glrmb200_engine* E, const int64_t* row_ptr, const int32_t*
   glrmb200_plan_shards(col_ptr, n, E->nranks, C.bounds.data());
   R.begin = R.bounds[E->rank]; R.end = R.bounds[E->rank + 1];
   C.begin = C.bounds[E->rank]; C.end = C.bounds[E->rank + 1];
-  for (Side* S : {&R, &C}) {
-    cudaFree(S->d_ptr); cudaFree(S->d_idx); cudaFree(S->d_val); cudaFree(S->d_order); cudaFree(S->d_order_vec);
-    S->d_ptr = nullptr; S->d_idx = nullptr; S->d_val = nullptr; S->d_order = nullptr; S->d_order_vec = nullptr;
-  }
+  free_lists(E, R);
+  free_lists(E, C);
   int rc;
-  auto up_side = [&](Side& S, const int64_t* ptr, const int32_t* idx, const double* val, const std::vector<char>* vecflags) -> int {
-    const int64_t cnt = S.end - S.begin, q0 = ptr[S.begin], q1 = ptr[S.end];
+  // 1. the big streams first (asynchronous from pinned memory)
+  auto up_lists = [&](Side& S, const int64_t* ptr, const int32_t* idx, const double* val) -> int {
+    const int64_t q0 = ptr[S.begin], q1 = ptr[S.end];
     S.nnz_local = q1 - q0;
+    int r2;
+    if ((r2 = upload(&S.d_idx, idx ? idx + q0 : nullptr, (size_t)S.nnz_local, E->stream, 32))) return r2;
+    return upload(&S.d_val, val ? val + q0 : nullptr, (size_t)S.nnz_local, E->stream, 32);
+  };
+  if ((rc = up_lists(R, row_ptr, row_idx, row_val))) return rc;
+  if ((rc = up_lists(C, col_ptr, col_idx, col_val))) return rc;
+  // 2. host work under the copies: shard-local ptr arrays and the degree-sorted schedules
+  auto up_sched = [&](Side& S, const int64_t* ptr, const std::vector<char>* vecflags) -> int {
+    const int64_t cnt = S.end - S.begin, q0 = ptr[S.begin];
     std::vector<int64_t> local((size_t)cnt + 1);
     for (int64_t i = 0; i <= cnt; ++i) local[(size_t)i] = ptr[S.begin + i] - q0;
-    int r2 = upload(&S.d_ptr, local.data(), local.size());
+    int r2 = upload(&S.d_ptr, local.data(), local.size(), E->stream);
     if (r2) return r2;
-    if ((r2 = upload(&S.d_idx, idx ? idx + q0 : nullptr, (size_t)S.nnz_local, 32))) return r2;
-    if ((r2 = upload(&S.d_val, val ? val + q0 : nullptr, (size_t)S.nnz_local, 32))) return r2;
-    return build_schedule(S, ptr, E, E->has_vec ? vecflags : nullptr);
+    return build_schedule(E, S, ptr, E->has_vec ? vecflags : nullptr);
   };
-  if ((rc = up_side(R, row_ptr, row_idx, row_val, &E->all_rows_vec))) return rc;
-  if ((rc = up_side(C, col_ptr, col_idx, col_val, &E->col_is_vec))) return rc;
+  if ((rc = up_sched(R, row_ptr, &E->all_rows_vec))) return rc;
+  if ((rc = up_sched(C, col_ptr, &E->col_is_vec))) return rc;
+  // 3. validation on the device
   unsigned long long* d_bad = nullptr;
-  CUDA_OK(cudaMalloc((void**)&d_bad, 2 * sizeof(unsigned long long)));
-  CUDA_OK(cudaMemset(d_bad, 0xff, 2 * sizeof(unsigned long long)));
+  if ((rc = dalloc(&d_bad, 2, E->stream))) return rc;
+  CUDA_OK(cudaMemsetAsync(d_bad, 0xff, 2 * sizeof(unsigned long long), E->stream));
   if (R.nnz_local > 0)
     validate_rows_kernel<<<(unsigned)((R.nnz_local + 255) / 256), 256, 0, E->stream>>>(R.d_idx, R.d_val, R.nnz_local, n, E->d_loss_code, E->d_loss_param, d_bad);
   if (C.end > C.begin)
@@ -450,7 +529,7 @@ static int load_lists(glrmb200_engine* E, const int64_t* row_ptr, const int32_t*
   unsigned long long bad[2] = {0, 0};
   CUDA_OK(cudaMemcpyAsync(bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
   CUDA_OK(cudaStreamSynchronize(E->stream));
-  cudaFree(d_bad);
+  dfree(d_bad, E->stream);
   for (int side = 0; side < 2; ++side) {
     if (bad[side] == ~0ULL) continue;
     const int kind = -(int)(bad[side] & 15ULL);
@@ -472,6 +551,7 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   const int64_t m = P->m, n = P->n, k = P->k;
   if (m <= 0 || n <= 0 || k <= 0) return fail(GLRMB200_E_INVALID, "m, n, k must be positive");
   if (m >= INT32_MAX || n >= INT32_MAX) return fail(GLRMB200_E_INVALID, "m, n must fit int32");
+  if (E->nranks > MAX_RANKS) return fail(GLRMB200_E_INVALID, "at most %d ranks", MAX_RANKS);
   if (!P->loss_code || !P->loss_param || !P->rx_code || !P->ry_code) return fail(GLRMB200_E_INVALID, "null descriptor table");
   E->m = m; E->n = n; E->k = k; E->d = P->d;
   E->obs_full = P->obs_full != 0;
@@ -538,7 +618,6 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   if (E->cluster_threshold < E->heavy_threshold) E->cluster_threshold = E->heavy_threshold;
   if (E->cluster16_threshold < E->cluster_threshold) E->cluster16_threshold = E->cluster_threshold;
 
-  // ---- observation lists: validation (glrm.jl:63-71, losses.jl:104) ----------------------------
   Side& R = E->rows;
   Side& C = E->cols;
   R.units = m; C.units = n;
@@ -553,32 +632,36 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   }   // (observation lists: checked, sharded and uploaded by load_lists below)
   R.begin = R.bounds[E->rank]; R.end = R.bounds[E->rank + 1];
   C.begin = C.bounds[E->rank]; C.end = C.bounds[E->rank + 1];
-  // NB: the tier of a unit (warp / CTA / cluster) fixes its reduction tree, so the thresholds are constants of the
-  // unit's degree — never of the rank count — or a sharded fit would stop being bit-identical to the 1-GPU fit.
 
   // ---- device ---------------------------------------------------------------------------------------
   int rc = check_device();
   if (rc) return rc;
   if (E->device < 0 || E->device >= g_device_checked) return fail(GLRMB200_E_INVALID, "device %d out of range (%d visible)", E->device, g_device_checked);
   CUDA_OK(cudaSetDevice(E->device));
+  if ((rc = pool_setup(E->device))) return rc;
+  if ((rc = pinned_setup())) return rc;
+  E->h_pinned = g_pinned;
+  E->h_stop = reinterpret_cast<volatile int*>(g_pinned + 8);
   CUDA_OK(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
   CUDA_OK(cudaStreamCreateWithFlags(&E->stream2, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&E->ev_fork, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&E->ev_join, cudaEventDisableTiming));
-  for (auto& e : E->ev) CUDA_OK(cudaEventCreate(&e));
-  CUDA_OK(cudaMallocHost((void**)&E->h_pinned, 8 * sizeof(double)));
-  CUDA_OK(cudaMalloc((void**)&E->d_scalars, 4 * sizeof(double)));
-  CUDA_OK(cudaMalloc((void**)&E->d_trials, 2 * sizeof(unsigned long long)));
-  CUDA_OK(cudaMemset(E->d_trials, 0, 2 * sizeof(unsigned long long)));
+  CUDA_OK(cudaEventCreate(&E->ev_base));
+  CUDA_OK(cudaEventCreate(&E->ev_aux));
+  if ((rc = dalloc(&E->d_scalars, 4, E->stream))) return rc;
+  if ((rc = dalloc(&E->d_trials, 2, E->stream))) return rc;
+  if ((rc = dalloc(&E->d_stop, 2, E->stream))) return rc;
+  CUDA_OK(cudaMemsetAsync(E->d_trials, 0, 2 * sizeof(unsigned long long), E->stream));
+  CUDA_OK(cudaMemsetAsync(E->d_stop, 0, 2 * sizeof(int), E->stream));
 
-  if ((rc = upload(&E->d_loss_code, P->loss_code, (size_t)n))) return rc;
-  if ((rc = upload(&E->d_loss_param, P->loss_param, (size_t)n * GLRMB200_LOSS_NPARAM))) return rc;
-  if ((rc = setup_regs(R, P->rx_count, P->rx_code, P->rx_param, false))) return rc;
-  if ((rc = setup_regs(C, P->ry_count, P->ry_code, P->ry_param, true))) return rc;
+  if ((rc = upload(&E->d_loss_code, P->loss_code, (size_t)n, E->stream))) return rc;
+  if ((rc = upload(&E->d_loss_param, P->loss_param, (size_t)n * GLRMB200_LOSS_NPARAM, E->stream))) return rc;
+  if ((rc = setup_regs(E, R, P->rx_count, P->rx_code, P->rx_param, false))) return rc;
+  if ((rc = setup_regs(E, C, P->ry_count, P->ry_code, P->ry_param, true))) return rc;
   E->all_rows_vec.assign(E->has_vec ? (size_t)m : 0, 1);   // with block columns every row takes the vector path
   std::vector<char>& all_rows_vec = E->all_rows_vec;
   if (E->has_vec) {
-    if ((rc = upload(&E->d_ystart, E->ystart.data(), E->ystart.size()))) return rc;
+    if ((rc = upload(&E->d_ystart, E->ystart.data(), E->ystart.size(), E->stream))) return rc;
     for (int64_t f = 0; f < n; ++f) {
       if (!col_is_vec[(size_t)f]) continue;
       const int rcf = P->ry_code[P->ry_count == 1 ? 0 : f];
@@ -594,39 +677,40 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
     // column side streams the Julia (column-major) A as is; the row side gets a row-major copy
     const int64_t cb = C.begin, ce = C.end;
     C.nnz_local = (ce - cb) * m;
-    if ((rc = upload(&C.d_val, P->dense_A + cb * m, (size_t)C.nnz_local))) return rc;
+    if ((rc = upload(&C.d_val, P->dense_A + cb * m, (size_t)C.nnz_local, E->stream, 32))) return rc;
     // row-major copy of rows [R.begin, R.end): transpose on the device from a temporary full upload
     R.nnz_local = (R.end - R.begin) * n;
     double* d_full = nullptr;
     if (E->nranks == 1) d_full = C.d_val;
-    else if ((rc = upload(&d_full, P->dense_A, (size_t)(m * n)))) return rc;
+    else if ((rc = upload(&d_full, P->dense_A, (size_t)(m * n), E->stream))) return rc;
     double* d_rowmajor = nullptr;
-    CUDA_OK(cudaMalloc((void**)&d_rowmajor, (size_t)std::max<int64_t>(1, m * n) * sizeof(double)));
+    if ((rc = dalloc(&d_rowmajor, (size_t)(m * n) + 32, E->stream))) return rc;
+    CUDA_OK(cudaMemsetAsync(d_rowmajor + m * n, 0, 32 * sizeof(double), E->stream));
     dim3 blk(32, 8), grd((unsigned)((m + 31) / 32), (unsigned)((n + 31) / 32));
     transpose_kernel<<<grd, blk, 0, E->stream>>>(d_full, d_rowmajor, n, m);   // src = n x m row-major view of A
     CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaStreamSynchronize(E->stream));
     if (E->nranks == 1) {
       R.d_val = d_rowmajor;
     } else {
-      CUDA_OK(cudaMalloc((void**)&R.d_val, (size_t)std::max<int64_t>(1, R.nnz_local) * sizeof(double)));
-      CUDA_OK(cudaMemcpy(R.d_val, d_rowmajor + R.begin * n, (size_t)R.nnz_local * sizeof(double), cudaMemcpyDeviceToDevice));
-      cudaFree(d_rowmajor);
-      cudaFree(d_full);
+      if ((rc = dalloc(&R.d_val, (size_t)R.nnz_local + 32, E->stream))) return rc;
+      CUDA_OK(cudaMemsetAsync(R.d_val + R.nnz_local, 0, 32 * sizeof(double), E->stream));
+      CUDA_OK(cudaMemcpyAsync(R.d_val, d_rowmajor + R.begin * n, (size_t)R.nnz_local * sizeof(double), cudaMemcpyDeviceToDevice, E->stream));
+      dfree(d_rowmajor, E->stream);
+      dfree(d_full, E->stream);
     }
-    if ((rc = build_schedule(R, nullptr, E, E->has_vec ? &all_rows_vec : nullptr))) return rc;
-    if ((rc = build_schedule(C, nullptr, E, E->has_vec ? &col_is_vec : nullptr))) return rc;
+    if ((rc = build_schedule(E, R, nullptr, E->has_vec ? &all_rows_vec : nullptr))) return rc;
+    if ((rc = build_schedule(E, C, nullptr, E->has_vec ? &col_is_vec : nullptr))) return rc;
     {
       unsigned long long* d_bad = nullptr;
-      CUDA_OK(cudaMalloc((void**)&d_bad, sizeof(unsigned long long)));
-      CUDA_OK(cudaMemset(d_bad, 0xff, sizeof(unsigned long long)));
+      if ((rc = dalloc(&d_bad, 1, E->stream))) return rc;
+      CUDA_OK(cudaMemsetAsync(d_bad, 0xff, sizeof(unsigned long long), E->stream));
       const int64_t total = C.nnz_local;
       if (total > 0) validate_dense_kernel<<<(unsigned)((total + 255) / 256), 256, 0, E->stream>>>(C.d_val, total, m, E->d_loss_code + C.begin, E->d_loss_param + C.begin * GLRMB200_LOSS_NPARAM, d_bad);
       CUDA_OK(cudaGetLastError());
       unsigned long long bad = 0;
       CUDA_OK(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
       CUDA_OK(cudaStreamSynchronize(E->stream));
-      cudaFree(d_bad);
+      dfree(d_bad, E->stream);
       if (bad != ~0ULL) {
         const int kind = -(int)(bad & 15ULL);
         const int64_t pos = (int64_t)(bad >> 4);
@@ -640,29 +724,35 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   }
 
   {
-    // factors and obj_by_col share one allocation rounded to the 2 MiB allocation granule, so that a single CUDA
-    // IPC handle maps exactly this memory in the peers (small cudaMallocs share granules; handles would alias)
-    const size_t nx = (size_t)m * E->stride, ny = (size_t)E->d * E->stride, no = (size_t)n;
+    // factors, obj_by_col and the peer flags share one allocation rounded to the 2 MiB allocation granule, so that a
+    // single CUDA IPC handle maps exactly this memory in the peers (small cudaMallocs share granules; handles would alias)
+    const size_t nx = (size_t)m * E->stride, ny = (size_t)E->d * E->stride, no = ((size_t)n + 1) / 2 * 2, nf = MAX_RANKS;
     const size_t granule = (size_t)2 << 20;
-    E->xchg_bytes = ((nx + ny + no) * sizeof(double) + granule - 1) / granule * granule;
+    E->xchg_bytes = ((nx + ny + no + nf) * sizeof(double) + granule - 1) / granule * granule;
+    bool fresh = true;
     if (g_xc.d_xchg && g_xc.device == E->device && g_xc.rank == E->rank && g_xc.nranks == E->nranks && g_xc.bytes == E->xchg_bytes) {
       E->d_xchg = g_xc.d_xchg; E->peer_blobs = g_xc.blobs; E->opened = g_xc.opened;
-      E->d_peer_X = g_xc.dpx; E->d_peer_Y = g_xc.dpy; E->d_peer_objc = g_xc.dpo;
+      E->d_peer_X = g_xc.dpx; E->d_peer_Y = g_xc.dpy; E->d_peer_objc = g_xc.dpo; E->d_peer_flags = g_xc.dpf; E->d_peer_rank = g_xc.dpr;
       g_xc = XchgCache();
+      fresh = false;
     } else {
       CUDA_OK(cudaMalloc((void**)&E->d_xchg, E->xchg_bytes));
     }
-    CUDA_OK(cudaMemset(E->d_xchg, 0, E->xchg_bytes));
     E->d_X = E->d_xchg;
     E->d_Y = E->d_X + nx;
     C.d_obj = E->d_Y + ny;
+    E->d_flags = reinterpret_cast<unsigned long long*>(C.d_obj + no);
+    // a recycled allocation keeps its content: factors are fully rewritten by upload_factors (padding included) and
+    // obj_by_col by the first sweep; the flags are zeroed by glrmb200_ipc_export before any peer can write them
+    if (fresh) CUDA_OK(cudaMemsetAsync(E->d_xchg, 0, E->xchg_bytes, E->stream));
   }
-  CUDA_OK(cudaMalloc((void**)&R.d_alpha, (size_t)m * sizeof(double)));
-  CUDA_OK(cudaMalloc((void**)&C.d_alpha, (size_t)n * sizeof(double)));
-  CUDA_OK(cudaMalloc((void**)&R.d_obj, (size_t)m * sizeof(double)));
-  CUDA_OK(cudaMemset(R.d_obj, 0, (size_t)m * sizeof(double)));
-  CUDA_OK(cudaMemset(R.d_alpha, 0, (size_t)m * sizeof(double)));
-  CUDA_OK(cudaMemset(C.d_alpha, 0, (size_t)n * sizeof(double)));
+  if ((rc = dalloc(&R.d_alpha, (size_t)m, E->stream))) return rc;
+  if ((rc = dalloc(&C.d_alpha, (size_t)n, E->stream))) return rc;
+  if ((rc = dalloc(&R.d_obj, (size_t)m, E->stream))) return rc;
+  CUDA_OK(cudaMemsetAsync(R.d_obj, 0, (size_t)m * sizeof(double), E->stream));
+  CUDA_OK(cudaMemsetAsync(R.d_alpha, 0, (size_t)m * sizeof(double), E->stream));
+  CUDA_OK(cudaMemsetAsync(C.d_alpha, 0, (size_t)n * sizeof(double), E->stream));
+  CUDA_OK(cudaStreamSynchronize(E->stream));
   return 0;
 }
 
@@ -733,14 +823,30 @@ extern "C" int glrmb200_shard(glrmb200_handle E, int64_t* rb, int64_t* re, int64
   return 0;
 }
 
+// Barrier between the ranks on the engine's stream: with the fused exchange a flag exchange over peer memory
+// (peer_barrier_kernel), otherwise a 1-element NCCL all-reduce.
 static int comm_barrier(glrmb200_engine* E) {
   if (E->nranks == 1) return 0;
+  if (E->peer_ready) {
+    ++E->epoch;
+    peer_barrier_kernel<<<1, 64, 0, E->stream>>>(E->d_peer_flags, E->d_flags, E->d_peer_rank, E->rank, E->nranks - 1, E->epoch, E->d_stop + 1);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (!E->comm) return fail(GLRMB200_E_STATE, "glrmb200_comm_init was not called");
   if (!E->d_barrier) {
-    CUDA_OK(cudaMalloc((void**)&E->d_barrier, sizeof(double)));
-    CUDA_OK(cudaMemset(E->d_barrier, 0, sizeof(double)));
+    int rc = dalloc(&E->d_barrier, 1, E->stream);
+    if (rc) return rc;
+    CUDA_OK(cudaMemsetAsync(E->d_barrier, 0, sizeof(double), E->stream));
   }
   NCCL_OK(g_nccl.AllReduce(E->d_barrier, E->d_barrier, 1, kNcclDouble, /*ncclSum*/ 0, E->comm, E->stream));
+  return 0;
+}
+static int check_barrier_timeout(glrmb200_engine* E) {     // after a synchronisation
+  if (!E->peer_ready) return 0;
+  int flag = 0;
+  CUDA_OK(cudaMemcpy(&flag, E->d_stop + 1, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) return fail(GLRMB200_E_NCCL, "peer barrier timed out: a rank of the fused exchange stopped responding");
   return 0;
 }
 
@@ -750,13 +856,18 @@ extern "C" int glrmb200_comm_barrier(glrmb200_handle E) {
   int rc = comm_barrier(E);
   if (rc) return rc;
   CUDA_OK(cudaStreamSynchronize(E->stream));
-  return 0;
+  return check_barrier_timeout(E);
 }
 
 extern "C" int glrmb200_ipc_export(glrmb200_handle E, uint8_t out[GLRMB200_IPC_BYTES]) {
   if (!E || !out) return fail(GLRMB200_E_INVALID, "null argument");
   CUDA_OK(cudaSetDevice(E->device));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  // the host all-gathers the blobs between export and open: zeroing the flag array here means every rank's flags are
+  // clean before any peer can publish an epoch into them
+  CUDA_OK(cudaMemsetAsync(E->d_flags, 0, MAX_RANKS * sizeof(unsigned long long), E->stream));
+  CUDA_OK(cudaStreamSynchronize(E->stream));
+  E->epoch = 0;
   cudaIpcMemHandle_t h;
   CUDA_OK(cudaIpcGetMemHandle(&h, E->d_xchg));
   memcpy(out, &h, sizeof(h));
@@ -775,10 +886,12 @@ extern "C" int glrmb200_ipc_open(glrmb200_handle E, const uint8_t* blobs) {
   }
   for (void* p : E->opened) cudaIpcCloseMemHandle(p);
   E->opened.clear();
-  cudaFree(E->d_peer_X); cudaFree(E->d_peer_Y); cudaFree(E->d_peer_objc);
-  E->d_peer_X = E->d_peer_Y = E->d_peer_objc = nullptr;
+  cudaFree(E->d_peer_X); cudaFree(E->d_peer_Y); cudaFree(E->d_peer_objc); cudaFree(E->d_peer_flags); cudaFree(E->d_peer_rank);
+  E->d_peer_X = E->d_peer_Y = E->d_peer_objc = nullptr; E->d_peer_flags = nullptr; E->d_peer_rank = nullptr;
   E->peer_blobs.assign(blobs, blobs + nb);
   std::vector<double*> px, py, po;
+  std::vector<unsigned long long*> pf;
+  std::vector<int> pr;
   for (int r = 0; r < E->nranks; ++r) {
     if (r == E->rank) continue;
     cudaIpcMemHandle_t h;
@@ -786,30 +899,68 @@ extern "C" int glrmb200_ipc_open(glrmb200_handle E, const uint8_t* blobs) {
     void* base = nullptr;
     CUDA_OK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
     E->opened.push_back(base);
-    double* bx = (double*)base;                       // same layout in every rank: [X | Y | obj_by_col]
+    double* bx = (double*)base;                       // same layout in every rank: [X | Y | obj_by_col | flags]
     px.push_back(bx);
     py.push_back(bx + (E->d_Y - E->d_xchg));
     po.push_back(bx + (E->cols.d_obj - E->d_xchg));
+    pf.push_back(reinterpret_cast<unsigned long long*>(bx + (reinterpret_cast<double*>(E->d_flags) - E->d_xchg)));
+    pr.push_back(r);
   }
+  // these tables live in cudaMalloc memory (not the pool): they travel with the cached exchange allocation
+  auto up = [&](auto** dst, const auto* src, size_t cnt) -> int {
+    CUDA_OK(cudaMalloc((void**)dst, cnt * sizeof(**dst)));
+    CUDA_OK(cudaMemcpy(*dst, src, cnt * sizeof(**dst), cudaMemcpyHostToDevice));
+    return 0;
+  };
   int rc;
-  if ((rc = upload(&E->d_peer_X, px.data(), px.size()))) return rc;
-  if ((rc = upload(&E->d_peer_Y, py.data(), py.size()))) return rc;
-  if ((rc = upload(&E->d_peer_objc, po.data(), po.size()))) return rc;
+  if ((rc = up(&E->d_peer_X, px.data(), px.size()))) return rc;
+  if ((rc = up(&E->d_peer_Y, py.data(), py.size()))) return rc;
+  if ((rc = up(&E->d_peer_objc, po.data(), po.size()))) return rc;
+  if ((rc = up(&E->d_peer_flags, pf.data(), pf.size()))) return rc;
+  if ((rc = up(&E->d_peer_rank, pr.data(), pr.size()))) return rc;
   E->peer_ready = true;
   return 0;
+}
+
+// ---- factor transfers: one contiguous PCIe copy + a repack kernel -------------------------------------------------------
+static int ensure_stage(glrmb200_engine* E) {
+  if (E->d_stage) return 0;
+  return dalloc(&E->d_stage, (size_t)(E->m + E->d) * (size_t)E->k, E->stream);
+}
+static void pack_launch(glrmb200_engine* E, const double* src, double* dst, int64_t col0, int64_t ncols, double* const* peers, int n_peers) {
+  if (ncols <= 0) return;
+  const int64_t total = ncols * E->stride;
+  pack_factor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, E->stream>>>(src, dst, col0, ncols, (int)E->k, E->stride, peers, n_peers);
 }
 
 extern "C" int glrmb200_upload_factors(glrmb200_handle E, const double* X, const double* Y) {
   if (!E || !X || !Y) return fail(GLRMB200_E_INVALID, "null argument");
   CUDA_OK(cudaSetDevice(E->device));
-  const size_t kb = (size_t)E->k * sizeof(double), pb = (size_t)E->stride * sizeof(double);
-  if (E->stride != E->k) {
-    CUDA_OK(cudaMemsetAsync(E->d_X, 0, (size_t)E->m * pb, E->stream));
-    CUDA_OK(cudaMemsetAsync(E->d_Y, 0, (size_t)E->d * pb, E->stream));
+  int rc = ensure_stage(E);
+  if (rc) return rc;
+  const int64_t k = E->k;
+  double* sx = E->d_stage;
+  double* sy = E->d_stage + E->m * k;
+  if (E->peer_ready) {
+    // sharded upload: this rank moves only the columns it owns across PCIe and stores them into every replica over
+    // NVLink; the barrier makes all shards visible everywhere before the first sweep reads them
+    const int64_t rb = E->rows.begin, re = E->rows.end;
+    const int64_t yb = E->has_vec ? E->ystart[(size_t)E->cols.begin] : E->cols.begin, ye = E->has_vec ? E->ystart[(size_t)E->cols.end] : E->cols.end;
+    if ((rc = comm_barrier(E))) return rc;      // every rank is done reading its replicas (e.g. a download after the last fit)
+    if (re > rb) CUDA_OK(cudaMemcpyAsync(sx + rb * k, X + rb * k, (size_t)((re - rb) * k) * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+    if (ye > yb) CUDA_OK(cudaMemcpyAsync(sy + yb * k, Y + yb * k, (size_t)((ye - yb) * k) * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+    pack_launch(E, sx + rb * k, E->d_X, rb, re - rb, E->d_peer_X, E->nranks - 1);
+    pack_launch(E, sy + yb * k, E->d_Y, yb, ye - yb, E->d_peer_Y, E->nranks - 1);
+    CUDA_OK(cudaGetLastError());
+    if ((rc = comm_barrier(E))) return rc;
+  } else {
+    CUDA_OK(cudaMemcpyAsync(sx, X, (size_t)(E->m * k) * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+    CUDA_OK(cudaMemcpyAsync(sy, Y, (size_t)(E->d * k) * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+    pack_launch(E, sx, E->d_X, 0, E->m, nullptr, 0);
+    pack_launch(E, sy, E->d_Y, 0, E->d, nullptr, 0);
+    CUDA_OK(cudaGetLastError());
   }
-  CUDA_OK(cudaMemcpy2DAsync(E->d_X, pb, X, kb, kb, (size_t)E->m, cudaMemcpyHostToDevice, E->stream));
-  CUDA_OK(cudaMemcpy2DAsync(E->d_Y, pb, Y, kb, kb, (size_t)E->d, cudaMemcpyHostToDevice, E->stream));
-  CUDA_OK(cudaStreamSynchronize(E->stream));
+  CUDA_OK(cudaStreamSynchronize(E->stream));     // the host buffers are the caller's again
   E->factors_resident = true;
   return 0;
 }
@@ -818,9 +969,16 @@ extern "C" int glrmb200_download_factors(glrmb200_handle E, double* X, double* Y
   if (!E || !X || !Y) return fail(GLRMB200_E_INVALID, "null argument");
   if (!E->factors_resident) return fail(GLRMB200_E_STATE, "no factors on the device");
   CUDA_OK(cudaSetDevice(E->device));
-  const size_t kb = (size_t)E->k * sizeof(double), pb = (size_t)E->stride * sizeof(double);
-  CUDA_OK(cudaMemcpy2DAsync(X, kb, E->d_X, pb, kb, (size_t)E->m, cudaMemcpyDeviceToHost, E->stream));
-  CUDA_OK(cudaMemcpy2DAsync(Y, kb, E->d_Y, pb, kb, (size_t)E->d, cudaMemcpyDeviceToHost, E->stream));
+  int rc = ensure_stage(E);
+  if (rc) return rc;
+  const int64_t k = E->k;
+  double* sx = E->d_stage;
+  double* sy = E->d_stage + E->m * k;
+  unpack_factor_kernel<<<(unsigned)((E->m * k + 255) / 256), 256, 0, E->stream>>>(E->d_X, sx, E->m, (int)k, E->stride);
+  unpack_factor_kernel<<<(unsigned)((E->d * k + 255) / 256), 256, 0, E->stream>>>(E->d_Y, sy, E->d, (int)k, E->stride);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(X, sx, (size_t)(E->m * k) * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  CUDA_OK(cudaMemcpyAsync(Y, sy, (size_t)(E->d * k) * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
   CUDA_OK(cudaStreamSynchronize(E->stream));
   return 0;
 }
@@ -841,45 +999,38 @@ static int allgather_units(glrmb200_engine* E, double* buf, const Side& S, int64
   return 0;
 }
 
-// sum of per-unit objectives -> host (through the pinned scalar)
-static int reduce_to_host(glrmb200_engine* E, const double* v, int64_t n, double* out, int64_t* launches) {
-  sum_kernel<<<1, 1024, 0, E->stream>>>(v, n, E->d_scalars);
-  CUDA_OK(cudaGetLastError());
-  ++*launches;
-  CUDA_OK(cudaMemcpyAsync(E->h_pinned, E->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, E->stream));
-  CUDA_OK(cudaStreamSynchronize(E->stream));
-  *out = E->h_pinned[0];
-  return 0;
-}
-
-// objective(glrm, X, Y) on the resident factors: losses over observed_examples + penalties
+// objective(glrm, X, Y) on the resident factors: losses over observed_examples + penalties.  Every read of the factors
+// (the evaluation sweep over Y's columns, the row penalties over X) is enqueued BEFORE the barrier: once a rank has
+// passed it, its peers may start storing the next sweep's columns into this rank's replicas.
 static int objective_resident(glrmb200_engine* E, bool include_reg, double* out, int64_t* launches) {
   SweepArgs A = make_args(E, /*x_side=*/false, FLAG_EVAL_ONLY | (include_reg ? 0 : FLAG_NO_REG), INFINITY);
   cudaError_t ce = launch_sweep(E, A, E->cols, launches);
   if (ce == cudaSuccess) ce = launch_vec(E, A, false, E->cols, launches);
   if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "objective sweep launch: %s", cudaGetErrorString(ce));
-  int rc = E->peer_ready ? comm_barrier(E) : allgather_units(E, E->cols.d_obj, E->cols, 1);
-  if (rc) return rc;
-  double total = 0.0;
-  if ((rc = reduce_to_host(E, E->cols.d_obj, E->n, &total, launches))) return rc;
   if (include_reg) {
     ce = launch_reg_eval(E, E->d_X, E->rows, E->rows.d_obj);
     if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "penalty launch: %s", cudaGetErrorString(ce));
     ++*launches;
-    double pen = 0.0;
-    if ((rc = reduce_to_host(E, E->rows.d_obj, E->m, &pen, launches))) return rc;
-    total += pen;
   }
+  int rc = E->peer_ready ? comm_barrier(E) : allgather_units(E, E->cols.d_obj, E->cols, 1);
+  if (rc) return rc;
+  sum_kernel<<<1, 1024, 0, E->stream>>>(E->cols.d_obj, E->n, E->d_scalars);
+  ++*launches;
+  if (include_reg) {
+    sum_kernel<<<1, 1024, 0, E->stream>>>(E->rows.d_obj, E->m, E->d_scalars + 1);
+    ++*launches;
+  }
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(E->h_pinned, E->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  CUDA_OK(cudaStreamSynchronize(E->stream));
+  double total = E->h_pinned[0];
+  if (include_reg) total += E->h_pinned[1];
   *out = total;
   return 0;
 }
 
-__global__ void fill_kernel(double* p, int64_t n, double v) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
-}
-static int fill(glrmb200_engine* E, double* p, int64_t n, double v) {
-  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, E->stream>>>(p, n, v);
+static int fill(glrmb200_engine* E, double* p, int64_t n, double v, const int* stop = nullptr) {
+  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, E->stream>>>(p, n, v, stop);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -896,78 +1047,116 @@ extern "C" int glrmb200_fit_resident(glrmb200_handle E, const glrmb200_params* p
   memset(&prof, 0, sizeof(prof));
   int rc;
   using clk = std::chrono::steady_clock;
+  const int max_iter = prm->max_iter;
 
   // ---- setup (proxgrad.jl:69-76) ---------------------------------------------------------------------
-  CUDA_OK(cudaEventRecord(E->ev[0], E->stream));
+  CUDA_OK(cudaEventRecord(E->ev_base, E->stream));
   if ((rc = fill(E, E->rows.d_alpha, E->m, prm->stepsize))) return rc;       // :69
   if ((rc = fill(E, E->cols.d_alpha, E->n, prm->stepsize))) return rc;       // :70
   CUDA_OK(cudaMemsetAsync(E->d_trials, 0, 2 * sizeof(unsigned long long), E->stream));
+  CUDA_OK(cudaMemsetAsync(E->d_stop, 0, sizeof(int), E->stream));
+  *E->h_stop = 0;
+  if (E->objs_cap < max_iter + 1) {
+    dfree(E->d_objs, E->stream);
+    if ((rc = dalloc(&E->d_objs, (size_t)max_iter + 1, E->stream))) return rc;
+    E->objs_cap = max_iter + 1;
+  }
+  if (E->evpool.empty()) {
+    E->evpool.resize((size_t)EVENT_CHUNK * 5, nullptr);
+    for (auto& e : E->evpool) CUDA_OK(cudaEventCreate(&e));
+  }
   const double scaled_abs_tol = prm->abs_tol * (double)E->nnz_rows_total;     // :72
-  int nrec = 0;
   double obj0 = 0.0;
   if ((rc = objective_resident(E, true, &obj0, &prof.other_launches))) return rc;   // :76
-  ch_objective[nrec] = obj0;
-  ch_seconds[nrec++] = 0.0;
-  CUDA_OK(cudaEventRecord(E->ev[1], E->stream));
-  CUDA_OK(cudaEventSynchronize(E->ev[1]));
+  E->h_pinned[2] = obj0;
+  CUDA_OK(cudaMemcpyAsync(E->d_objs, E->h_pinned + 2, sizeof(double), cudaMemcpyHostToDevice, E->stream));
+  CUDA_OK(cudaEventRecord(E->ev_aux, E->stream));
+  CUDA_OK(cudaEventSynchronize(E->ev_aux));
   float ms = 0;
-  CUDA_OK(cudaEventElapsedTime(&ms, E->ev[0], E->ev[1]));
+  CUDA_OK(cudaEventElapsedTime(&ms, E->ev_base, E->ev_aux));
   prof.setup_ms = ms;
 
-  auto t_iter = clk::now();
-  const auto t_loop = t_iter;
-  for (int it = 1; it <= prm->max_iter; ++it) {                                // :107
-    if (prm->inner_iter_X > 1 || prm->inner_iter_Y > 1) {                      // :112-115
-      if ((rc = fill(E, E->rows.d_alpha, E->m, prm->stepsize))) return rc;
-      if ((rc = fill(E, E->cols.d_alpha, E->n, prm->stepsize))) return rc;
+  // ---- the loop (proxgrad.jl:107-217), enqueued ahead of the device -----------------------------------------------------
+  // The record and the stopping rule run on the device (record_kernel); the host never waits for an objective value.  It
+  // polls the mapped stop flag between iterations and stops enqueuing once the device has stopped; launches that were
+  // already enqueued return immediately (SweepArgs::stop).  Timing events are harvested in chunks of EVENT_CHUNK iterations.
+  std::vector<double> t_end((size_t)max_iter + 1, 0.0);
+  const auto t_loop = clk::now();
+  CUDA_OK(cudaEventRecord(E->ev_base, E->stream));
+  int enqueued = 0, harvested = 0;
+  auto harvest = [&](int upto) -> int {       // iterations (harvested, upto]; the stream has been synchronised up to `upto`
+    for (int it = harvested + 1; it <= upto; ++it) {
+      cudaEvent_t* e = &E->evpool[(size_t)((it - 1) % EVENT_CHUNK) * 5];
+      float a = 0, b = 0, c = 0, d2 = 0, te = 0;
+      cudaEventElapsedTime(&a, e[0], e[1]);
+      cudaEventElapsedTime(&b, e[1], e[2]);
+      cudaEventElapsedTime(&c, e[2], e[3]);
+      cudaEventElapsedTime(&d2, e[3], e[4]);
+      cudaEventElapsedTime(&te, E->ev_base, e[4]);
+      prof.update_x_ms += a; prof.update_y_ms += c; prof.comm_ms += b + d2;
+      t_end[(size_t)it] = te * 1e-3;
     }
-    CUDA_OK(cudaEventRecord(E->ev[0], E->stream));
-    for (int inner = 0; inner < prm->inner_iter_X; ++inner) {                  // :117-158
-      SweepArgs A = make_args(E, true, 0, prm->min_stepsize);
+    harvested = upto;
+    return 0;
+  };
+  for (int it = 1; it <= max_iter; ++it) {                                // :107
+    if (it > 1 && (it - 1) % EVENT_CHUNK == 0) {                           // the event pool wraps: harvest the chunk first
+      CUDA_OK(cudaStreamSynchronize(E->stream));
+      harvest(it - 1);
+    }
+    if (*E->h_stop != 0) break;                                            // the device has stopped: nothing more to enqueue
+    cudaEvent_t* ev = &E->evpool[(size_t)((it - 1) % EVENT_CHUNK) * 5];
+    if (prm->inner_iter_X > 1 || prm->inner_iter_Y > 1) {                  // :112-115
+      if ((rc = fill(E, E->rows.d_alpha, E->m, prm->stepsize, E->d_stop))) return rc;
+      if ((rc = fill(E, E->cols.d_alpha, E->n, prm->stepsize, E->d_stop))) return rc;
+    }
+    CUDA_OK(cudaEventRecord(ev[0], E->stream));
+    for (int inner = 0; inner < prm->inner_iter_X; ++inner) {              // :117-158
+      SweepArgs A = make_args(E, true, 0, prm->min_stepsize, true);
       cudaError_t ce = launch_sweep(E, A, E->rows, &prof.x_launches);
       if (ce == cudaSuccess) ce = launch_vec(E, A, true, E->rows, &prof.x_launches);
       if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "update-X launch: %s", cudaGetErrorString(ce));
     }
-    CUDA_OK(cudaEventRecord(E->ev[1], E->stream));
-    if (E->peer_ready) { if ((rc = comm_barrier(E))) return rc; }       // columns already stored into the peers
+    CUDA_OK(cudaEventRecord(ev[1], E->stream));
+    if (E->peer_ready) { if ((rc = comm_barrier(E))) return rc; }          // columns already stored into the peers
     else if ((rc = allgather_units(E, E->d_X, E->rows, E->stride))) return rc;
-    CUDA_OK(cudaEventRecord(E->ev[2], E->stream));
-    for (int inner = 0; inner < prm->inner_iter_Y; ++inner) {                  // :160-203
-      SweepArgs A = make_args(E, false, 0, prm->min_stepsize);
+    CUDA_OK(cudaEventRecord(ev[2], E->stream));
+    for (int inner = 0; inner < prm->inner_iter_Y; ++inner) {              // :160-203
+      SweepArgs A = make_args(E, false, 0, prm->min_stepsize, true);
       cudaError_t ce = launch_sweep(E, A, E->cols, &prof.y_launches);
       if (ce == cudaSuccess) ce = launch_vec(E, A, false, E->cols, &prof.y_launches);
       if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "update-Y launch: %s", cudaGetErrorString(ce));
     }
-    CUDA_OK(cudaEventRecord(E->ev[3], E->stream));
+    CUDA_OK(cudaEventRecord(ev[3], E->stream));
     if (E->peer_ready) { if ((rc = comm_barrier(E))) return rc; }
     else {
       if ((rc = allgather_units(E, E->d_Y, E->cols, E->stride, E->has_vec ? E->ystart.data() : nullptr))) return rc;
       if ((rc = allgather_units(E, E->cols.d_obj, E->cols, 1))) return rc;
     }
-    CUDA_OK(cudaEventRecord(E->ev[4], E->stream));
-    double obj = 0.0;
-    if ((rc = reduce_to_host(E, E->cols.d_obj, E->n, &obj, &prof.other_launches))) return rc;   // :205
-    const auto t_now = clk::now();
-    ch_objective[nrec] = obj;
-    ch_seconds[nrec++] = std::chrono::duration<double>(t_now - t_iter).count();                 // :206-207
-    t_iter = t_now;
-    float a = 0, b = 0, c = 0, d2 = 0;
-    cudaEventElapsedTime(&a, E->ev[0], E->ev[1]);
-    cudaEventElapsedTime(&b, E->ev[1], E->ev[2]);
-    cudaEventElapsedTime(&c, E->ev[2], E->ev[3]);
-    cudaEventElapsedTime(&d2, E->ev[3], E->ev[4]);
-    prof.update_x_ms += a; prof.update_y_ms += c; prof.comm_ms += b + d2;
-    prof.iterations = it;
-    const double obj_decrease = ch_objective[nrec - 2] - obj;                  // :210
-    if (it > 10 && (obj_decrease < scaled_abs_tol || obj_decrease / obj < prm->rel_tol)) break;   // :211
+    record_kernel<<<1, 1024, 0, E->stream>>>(E->cols.d_obj, E->n, E->d_objs, it, scaled_abs_tol, prm->rel_tol, E->d_stop,
+                                             const_cast<int*>(E->h_stop));                               // :204-213
+    CUDA_OK(cudaGetLastError());
+    ++prof.other_launches;
+    CUDA_OK(cudaEventRecord(ev[4], E->stream));
+    enqueued = it;
   }
+  CUDA_OK(cudaStreamSynchronize(E->stream));
   prof.loop_ms = std::chrono::duration<double, std::milli>(clk::now() - t_loop).count();
+  harvest(enqueued);
+  if ((rc = check_barrier_timeout(E))) return rc;
+  int stop_it = 0;
+  CUDA_OK(cudaMemcpy(&stop_it, E->d_stop, sizeof(int), cudaMemcpyDeviceToHost));
+  const int last = stop_it > 0 ? stop_it : enqueued;          // iterations actually executed
+  CUDA_OK(cudaMemcpy(ch_objective, E->d_objs, (size_t)(last + 1) * sizeof(double), cudaMemcpyDeviceToHost));
+  ch_seconds[0] = 0.0;
+  for (int it = 1; it <= last; ++it) ch_seconds[it] = t_end[(size_t)it] - t_end[(size_t)it - 1];           // :206-207
+  prof.iterations = last;
   prof.reduce_ms = prof.loop_ms - prof.update_x_ms - prof.update_y_ms - prof.comm_ms;
   unsigned long long tr[2] = {0, 0};
   CUDA_OK(cudaMemcpy(tr, E->d_trials, sizeof(tr), cudaMemcpyDeviceToHost));
   prof.x_trials = (int64_t)tr[0];
   prof.y_trials = (int64_t)tr[1];
-  *n_recorded = nrec;
+  *n_recorded = last + 1;
   if (profile) *profile = prof;
   return 0;
 }
@@ -1005,9 +1194,9 @@ extern "C" int glrmb200_fit_sparse(glrmb200_handle E, const glrmb200_sparse_para
   // best-so-far factors (glrm.X / glrm.Y in the reference) live next to the working copies on the device
   const size_t fac_doubles = (size_t)(E->m + E->d) * E->stride;   // X and Y are contiguous inside d_xchg
   double* d_best = nullptr;
-  CUDA_OK(cudaMalloc((void**)&d_best, fac_doubles * sizeof(double)));
+  if ((rc = dalloc(&d_best, fac_doubles, E->stream))) return rc;
   CUDA_OK(cudaMemcpyAsync(d_best, E->d_X, fac_doubles * sizeof(double), cudaMemcpyDeviceToDevice, E->stream));
-  auto cleanup = [&]() { cudaStreamSynchronize(E->stream); cudaFree(d_best); };
+  auto cleanup = [&]() { cudaStreamSynchronize(E->stream); dfree(d_best, E->stream); };
 
   double alpha = prm->stepsize;                                                   // :44
   const double tol = prm->abs_tol * (double)E->nnz_rows_total;                    // :46
@@ -1040,14 +1229,15 @@ extern "C" int glrmb200_fit_sparse(glrmb200_handle E, const glrmb200_sparse_para
       ch_objective[nrec] = obj;
       ch_seconds[nrec++] = std::chrono::duration<double>(now - t).count();        // :105-106
       CUDA_OK(cudaMemcpyAsync(d_best, E->d_X, fac_doubles * sizeof(double), cudaMemcpyDeviceToDevice, E->stream));   // :107
+      // with the fused exchange the peers store into this replica during their next sweep: the snapshot must be taken first
+      if (E->peer_ready && (rc = comm_barrier(E))) { cleanup(); return rc; }
       alpha = alpha * 1.05;                                                       // :108
       steps_in_a_row = std::max(1, steps_in_a_row + 1);                           // :109
       t = clk::now();
     } else {
       alpha = alpha / std::max(1.5, (double)(-steps_in_a_row));                   // :113
       CUDA_OK(cudaMemcpyAsync(E->d_X, d_best, fac_doubles * sizeof(double), cudaMemcpyDeviceToDevice, E->stream));   // :115
-      // with the fused exchange the peers store into this replica during their next sweep: they must not start
-      // before the revert has landed
+      // ... and they must not start before the revert has landed
       if (E->peer_ready && (rc = comm_barrier(E))) { cleanup(); return rc; }
       steps_in_a_row = std::min(0, steps_in_a_row - 1);                           // :116
     }
@@ -1062,6 +1252,7 @@ extern "C" int glrmb200_fit_sparse(glrmb200_handle E, const glrmb200_sparse_para
   // hand back the best model: working copies <- best, then the usual download
   CUDA_OK(cudaMemcpyAsync(E->d_X, d_best, fac_doubles * sizeof(double), cudaMemcpyDeviceToDevice, E->stream));
   cleanup();
+  if ((rc = check_barrier_timeout(E))) return rc;
   *n_recorded = nrec;
   if (profile) *profile = prof;
   return glrmb200_download_factors(E, X, Y);
@@ -1086,8 +1277,9 @@ extern "C" int glrmb200_set_reg_scale(glrmb200_handle E, double newscale) {
       const int base = S->h_reg_code[i] & GLRMB200_REG_BASE_MASK;
       if (base == GLRMB200_REG_QUAD || base == GLRMB200_REG_ONE) S->h_reg_param[i * GLRMB200_REG_NPARAM] = newscale;
     }
-    CUDA_OK(cudaMemcpy(S->d_reg_param, S->h_reg_param.data(), S->h_reg_param.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpyAsync(S->d_reg_param, S->h_reg_param.data(), S->h_reg_param.size() * sizeof(double), cudaMemcpyHostToDevice, E->stream));
   }
+  CUDA_OK(cudaStreamSynchronize(E->stream));
   return 0;
 }
 
@@ -1097,8 +1289,8 @@ extern "C" int glrmb200_get_stepsizes(glrmb200_handle E, double* alpharow, doubl
   int rc;
   if ((rc = allgather_units(E, E->rows.d_alpha, E->rows, 1))) return rc;
   if ((rc = allgather_units(E, E->cols.d_alpha, E->cols, 1))) return rc;
+  if (alpharow) CUDA_OK(cudaMemcpyAsync(alpharow, E->rows.d_alpha, (size_t)E->m * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  if (alphacol) CUDA_OK(cudaMemcpyAsync(alphacol, E->cols.d_alpha, (size_t)E->n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
   CUDA_OK(cudaStreamSynchronize(E->stream));
-  if (alpharow) CUDA_OK(cudaMemcpy(alpharow, E->rows.d_alpha, (size_t)E->m * sizeof(double), cudaMemcpyDeviceToHost));
-  if (alphacol) CUDA_OK(cudaMemcpy(alphacol, E->cols.d_alpha, (size_t)E->n * sizeof(double), cudaMemcpyDeviceToHost));
   return 0;
 }

@@ -19,6 +19,86 @@ __global__ void __launch_bounds__(1024) sum_kernel(const double* __restrict__ v,
   if (threadIdx.x == 0) out[0] = sh[0];
 }
 
+// One outer iteration's record and stopping rule on the device (proxgrad.jl:204-213): objs[it] = sum(obj_by_col) in the
+// same fixed order as sum_kernel; stop iff it > 10 and (decrease < scaled_abs_tol or decrease / obj < rel_tol).  The host
+// enqueues iterations without waiting for the objective; once `stop` is set every later launch of the fit returns at once.
+__global__ void __launch_bounds__(1024) record_kernel(const double* __restrict__ v, int64_t n, double* objs, int it,
+                                                      double scaled_abs_tol, double rel_tol, int* stop, volatile int* host_stop) {
+  __shared__ double sh[1024];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) acc += v[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && *stop == 0) {
+    const double obj = sh[0];
+    objs[it] = obj;                                                      // :205-207
+    const double obj_decrease = objs[it - 1] - obj;                      // :210
+    if (it > 10 && (obj_decrease < scaled_abs_tol || obj_decrease / obj < rel_tol)) {   // :211
+      *stop = it;
+      *host_stop = it;
+      __threadfence_system();
+    }
+  }
+}
+
+// p[i] = v unless the fit has stopped (step sizes are reset per outer iteration when inner_iter > 1, proxgrad.jl:112-115)
+__global__ void fill_kernel(double* p, int64_t n, double v, const int* stop) {
+  if (stop != nullptr && *reinterpret_cast<const volatile int*>(stop) != 0) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// Barrier between the ranks of a fused-exchange fit, over NVLink peer memory: thread p publishes this rank's epoch in
+// peer p's flag array and waits until peer p's epoch shows up in ours.  It follows the sweep kernels on the same stream,
+// so the peer stores of the sweep have been performed before the flag is written (kernel boundary + system fence), and it
+// precedes the kernels that read what the peers stored.  ~3 us instead of the 30-50 us of a 1-element NCCL all-reduce.
+__global__ void peer_barrier_kernel(unsigned long long* const* peer_flags, volatile unsigned long long* my_flags,
+                                    const int* peer_rank, int my_rank, int n_peers, unsigned long long epoch, int* timed_out) {
+  const int p = threadIdx.x;
+  if (p >= n_peers) return;
+  __threadfence_system();
+  volatile unsigned long long* dst = peer_flags[p] + my_rank;
+  *dst = epoch;
+  __threadfence_system();
+  const int pr = peer_rank[p];
+  unsigned long long t0 = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (my_flags[pr] < epoch) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 20000000000ull) { *timed_out = 1; break; }          // 20 s: a peer died; the host reports it
+    __nanosleep(100);
+  }
+  __threadfence_system();
+}
+
+// Factor matrices cross PCIe as one contiguous copy (k doubles per column) into / out of a staging buffer; these kernels
+// move them to / from the padded device layout (stride doubles per column, zero past k).  A 2-D cudaMemcpy of 400-byte rows
+// into a 512-byte pitch runs at 3.5 GB/s (measured, profiles/r2_microbench.json) against 55 GB/s for the contiguous copy.
+// With peers, the columns are stored into every replica (sharded upload: each rank uploads only its own columns).
+__global__ void pack_factor_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t col0, int64_t ncols,
+                                   int k, int stride, double* const* peers, int n_peers) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncols * stride) return;
+  const int64_t c = i / stride;
+  const int e = (int)(i - c * stride);
+  const double v = e < k ? src[c * k + e] : 0.0;
+  const int64_t o = (col0 + c) * stride + e;
+  dst[o] = v;
+  for (int p = 0; p < n_peers; ++p) peers[p][o] = v;
+}
+__global__ void unpack_factor_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t ncols, int k, int stride) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncols * k) return;
+  const int64_t c = i / k;
+  const int e = (int)(i - c * k);
+  dst[i] = src[c * stride + e];
+}
+
 // ---- input validation on the device (glrm.jl:63-71 NaN check; myBool / level bounds, losses.jl:104) ----
 // bad[0] = smallest offending entry position (or ~0), bad[1] = error kind of some offender at that position
 __device__ __forceinline__ int label_error(int code, const double* __restrict__ lp, double a) {

@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(128) vec_sweep_kernel(const VecArgs V) {
   const SweepArgs& A = V.s;
   const int lane = threadIdx.x & 31, lg = lane % G;
   const int64_t slot = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (slot >= A.n_units) return;
+  if (slot >= A.n_units || sweep_stopped(A)) return;
   const int64_t unit = A.order[slot];
   const int k = A.k, stride = A.stride;
   int64_t start, len;

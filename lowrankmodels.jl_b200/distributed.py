@@ -12,7 +12,7 @@ from . import _abi
 
 
 def plan_shards(ptr, count, nranks):
-    """Contiguous unit ranges balanced by observation count (C ABI glrmb200_plan_shards; host-only).
+    """Contiguous unit ranges balanced by predicted sweep cost (32-entry chunks + a per-unit overhead) (C ABI glrmb200_plan_shards; host-only).
     ptr: int64 array [count+1] or None.  Returns int64 bounds [nranks+1]."""
     b = np.zeros(nranks + 1, dtype=np.int64)
     p = None if ptr is None else np.ascontiguousarray(ptr, dtype=np.int64)
@@ -35,20 +35,3 @@ def broadcast_unique_id(dist, rank, make_id):
     dist.broadcast_object_list(box, src=0)
     assert isinstance(box[0], (bytes, bytearray)) and len(box[0]) == 128
     return bytes(box[0])
-
-
-def allgather_columns(dist, mat, bounds, elems_per_unit=1):
-    """In-place all-gather of a column-major (k, units) array whose unit ranges [bounds[r], bounds[r+1]) are
-    owned by rank r — the host-side twin of the engine's allgather_units (used by the CPU/gloo tests)."""
-    import torch
-    world = len(bounds) - 1
-    for r in range(world):
-        lo, hi = int(bounds[r]) * elems_per_unit, int(bounds[r + 1]) * elems_per_unit
-        if hi > lo:
-            t = torch.from_numpy(np.ascontiguousarray(mat[..., lo:hi].T if mat.ndim == 2 else mat[lo:hi]))
-            dist.broadcast(t, src=r)
-            if mat.ndim == 2:
-                mat[:, lo:hi] = t.numpy().T
-            else:
-                mat[lo:hi] = t.numpy()
-    return mat

@@ -1,5 +1,5 @@
 """world_size-2 gloo tests (CPU): the host side of the N>1 path — shard planning through the C ABI, the
-unique-id rendezvous, and the property the multi-GPU design rests on: "every rank sweeps its own nnz-balanced
+unique-id rendezvous, and the property the multi-GPU design rests on: "every rank sweeps its own cost-balanced
 shard, then the updated factor is all-gathered" reproduces the unsharded sweep bit for bit (rows of X are
 independent given Y, columns of Y given X: proxgrad.jl:118,162)."""
 import os
@@ -20,6 +20,23 @@ def _free_port():
     p = s.getsockname()[1]
     s.close()
     return p
+
+
+def allgather_columns(dist, mat, bounds, elems_per_unit=1):
+    """In-place all-gather of a column-major (k, units) array whose unit ranges [bounds[r], bounds[r+1]) are
+    owned by rank r — the host-side twin of the engine's allgather_units."""
+    import torch
+    world = len(bounds) - 1
+    for r in range(world):
+        lo, hi = int(bounds[r]) * elems_per_unit, int(bounds[r + 1]) * elems_per_unit
+        if hi > lo:
+            t = torch.from_numpy(np.ascontiguousarray(mat[..., lo:hi].T if mat.ndim == 2 else mat[lo:hi]))
+            dist.broadcast(t, src=r)
+            if mat.ndim == 2:
+                mat[:, lo:hi] = t.numpy().T
+            else:
+                mat[lo:hi] = t.numpy()
+    return mat
 
 
 def _worker(rank, world, port, q):
@@ -45,8 +62,11 @@ def _worker(rank, world, port, q):
         dist.broadcast(ref, src=0)
         assert (t == ref).all()
         assert rb[0] == 0 and rb[-1] == cfg["m"] and cb[0] == 0 and cb[-1] == cfg["n"]
-        nnz_r = np.diff(ep.keep["row_ptr"][rb])
-        assert nnz_r.max() - nnz_r.min() <= 2 * np.diff(ep.keep["row_ptr"]).max()
+        # shards are balanced by predicted cost: 32-entry chunks (a partial chunk costs a whole one) + one chunk per unit
+        cost = (np.diff(ep.keep["row_ptr"]) + 31) // 32 * 32 + 32
+        cum = np.concatenate([[0], np.cumsum(cost)])
+        cost_r = np.diff(cum[rb])
+        assert cost_r.max() - cost_r.min() <= 2 * cost.max()
         # unique-id rendezvous (any 128 bytes stand in for ncclUniqueId on the CPU)
         uid = D.broadcast_unique_id(dist, rank, lambda: bytes(range(128)))
         assert uid == bytes(range(128))
@@ -60,10 +80,10 @@ def _worker(rank, world, port, q):
         traj = []
         for _ in range(p.max_iter):
             oracle_py.half_sweep(ep, ps, X, Y, ar, 0, int(rb[rank]), int(rb[rank + 1]), orow)
-            D.allgather_columns(dist, X, rb)
+            allgather_columns(dist, X, rb)
             oracle_py.half_sweep(ep, ps, X, Y, ac, 1, int(cb[rank]), int(cb[rank + 1]), ocol)
-            D.allgather_columns(dist, Y, cb)
-            D.allgather_columns(dist, ocol, cb)
+            allgather_columns(dist, Y, cb)
+            allgather_columns(dist, ocol, cb)
             traj.append(float(np.sum(ocol)))
         Xo, Yo = g.X.copy(order="F"), g.Y.copy(order="F")
         want = oracle_py.fit(ep, ps, Xo, Yo, mode=1, nthreads=1)
