@@ -848,11 +848,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32, TileCfg<R>::HEAVY_CT
 }
 
 // super-heavy units: a cluster of CS CTAs (8 warps each) per unit — CLUSTER_CTAS for degrees >= cluster_threshold,
-// CLUSTER_CTAS_BIG (non-portable size, opt-in at launch) for degrees >= cluster16_threshold.  On one GPU these tiers cost
+// CLUSTER_CTAS_BIG for degrees >= cluster16_threshold (16-CTA clusters were measured slower: 128 warps leave each warp
+// 4-8 chunks per pass, and clusters of a non-portable size schedule poorly next to the warp tier).  On one GPU these tiers cost
 // a few % (per-pass pipeline start-up is amortised over fewer chunks per warp); sharded, they are what keeps the heaviest
 // columns from becoming the critical path of the sweep.
 constexpr int CLUSTER_CTAS = 4;
-constexpr int CLUSTER_CTAS_BIG = 16;
+constexpr int CLUSTER_CTAS_BIG = 8;
 template <int G, int R, int LOSS, int CS>
 __global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32, TileCfg<R>::HEAVY_CTAS) sweep_cluster_kernel(const SweepArgs A) {
   __shared__ double red[WARPS_PER_CTA_HEAVY * (G * 2 * R + 1)];

@@ -93,7 +93,7 @@ struct Side {
   int32_t* d_idx = nullptr;
   double* d_val = nullptr;
   int32_t* d_order = nullptr;
-  int64_t n_cluster16 = 0, n_cluster = 0, n_heavy = 0, n_light = 0;   // schedule = [16-CTA clusters | 4-CTA clusters | CTA tier | warp tier]
+  int64_t n_cluster16 = 0, n_cluster = 0, n_heavy = 0, n_light = 0;   // schedule = [8-CTA clusters | 4-CTA clusters | CTA tier | warp tier]
   int32_t* d_order_vec = nullptr;   // units that go through vec_sweep_kernel (block columns / all rows of a problem with them)
   int64_t n_vec = 0;
   int32_t* d_reg_code = nullptr;

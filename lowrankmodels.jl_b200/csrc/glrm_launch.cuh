@@ -8,7 +8,7 @@ namespace glrm {
 
 struct Streams { cudaStream_t main, side; cudaEvent_t fork, join; };
 
-// tier sizes of one sweep: schedule = [cluster16 | cluster4 | CTA | warp] (degree-sorted, heaviest first)
+// tier sizes of one sweep: schedule = [cluster8 | cluster4 | CTA | warp] (degree-sorted, heaviest first)
 struct TierCounts { int64_t n_cluster16, n_cluster4, n_heavy, n_light; };
 
 #define GLRM_DECLARE_LAUNCH(NAME) \

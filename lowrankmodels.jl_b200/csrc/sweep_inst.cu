@@ -40,7 +40,7 @@ static cudaError_t launch_tile(const SweepArgs& A0, const TierCounts& tc, const 
     cudaStreamWaitEvent(st.side, st.fork, 0);
   }
   const int32_t* order = A0.order;
-  if (tc.n_cluster16 > 0) {                  // heaviest units first (LPT): a cluster of 16 CTAs per unit
+  if (tc.n_cluster16 > 0) {                  // heaviest units first (LPT): a cluster of 8 CTAs per unit
     SweepArgs K = A0;
     K.order = order; K.n_units = tc.n_cluster16;
     cudaError_t ce = launch_cluster<G, R, LOSS, CLUSTER_CTAS_BIG>(K, tc.n_cluster16, st.main);
