@@ -1,0 +1,95 @@
+// dense_inst.cu — instantiations and launch wrappers of the fully observed path (csrc/glrm_dense.cuh)
+#include "glrm_dense.cuh"
+#include "glrm_dense_host.h"
+
+namespace glrm {
+
+template <class K>
+static cudaError_t set_smem(K kern, size_t smem) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+template <int KT, int TG, int TR>
+static cudaError_t launch_x_tile(int loss, const DenseArgs& P, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t ce;
+  if (loss == GLRMB200_LOSS_QUAD) {
+    if ((ce = set_smem(dense_x_kernel<KT, TG, TR, GLRMB200_LOSS_QUAD>, smem)) != cudaSuccess) return ce;
+    dense_x_kernel<KT, TG, TR, GLRMB200_LOSS_QUAD><<<grid, DN_THREADS, smem, st>>>(P);
+  } else {
+    if ((ce = set_smem(dense_x_kernel<KT, TG, TR, 0>, smem)) != cudaSuccess) return ce;
+    dense_x_kernel<KT, TG, TR, 0><<<grid, DN_THREADS, smem, st>>>(P);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t dense_launch_x(int kt, int tg, int tr, int loss, const DenseArgs& P, int grid, cudaStream_t st) {
+  const size_t smem = dense_smem_bytes(P.k, kt);
+#define T(KT, TG, TR) if (kt == KT && tg == TG && tr == TR) return launch_x_tile<KT, TG, TR>(loss, P, grid, smem, st)
+  T(1, 4, 1); T(1, 8, 1); T(2, 8, 2); T(3, 8, 3); T(4, 8, 4); T(5, 16, 3); T(6, 16, 3); T(7, 16, 4);
+#undef T
+  return cudaErrorInvalidValue;
+}
+
+template <int KT, int LOSS>
+static cudaError_t launch_y_mode(int mode, const DenseArgs& P, dim3 grid, size_t smem, cudaStream_t st) {
+  cudaError_t ce;
+  if (mode == 0) {
+    if ((ce = set_smem(dense_y_pass_kernel<KT, LOSS, 0>, smem)) != cudaSuccess) return ce;
+    dense_y_pass_kernel<KT, LOSS, 0><<<grid, DN_THREADS, smem, st>>>(P);
+  } else {
+    if ((ce = set_smem(dense_y_pass_kernel<KT, LOSS, 1>, smem)) != cudaSuccess) return ce;
+    dense_y_pass_kernel<KT, LOSS, 1><<<grid, DN_THREADS, smem, st>>>(P);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t dense_launch_y_pass(int kt, int loss, int mode, const DenseArgs& P, int n_blocks, int max_chunks, cudaStream_t st) {
+  const size_t smem = dense_smem_bytes(P.k, kt);
+  const dim3 grid((unsigned)n_blocks, (unsigned)max_chunks, 1);
+#define T(KT)                                                                                                   \
+  if (kt == KT) {                                                                                               \
+    if (loss == GLRMB200_LOSS_QUAD) return launch_y_mode<KT, GLRMB200_LOSS_QUAD>(mode, P, grid, smem, st);      \
+    return launch_y_mode<KT, 0>(mode, P, grid, smem, st);                                                       \
+  }
+  T(1) T(2) T(3) T(4) T(5) T(6) T(7)
+#undef T
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t dense_launch_reduce(const double* part, int n_blocks, int64_t len, double* out, const int32_t* nactive, cudaStream_t st) {
+  if (len <= 0) return cudaSuccess;
+  dense_reduce_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(part, n_blocks, len, out, nactive);
+  return cudaGetLastError();
+}
+
+cudaError_t dense_launch_plan(const DenseYState& Q, cudaStream_t st) {
+  dense_y_plan_kernel<<<1, 32, 0, st>>>(Q);
+  return cudaGetLastError();
+}
+
+cudaError_t dense_launch_begin(int tg, int tr, const DenseYState& Q, cudaStream_t st) {
+  const int64_t per_cta = 4 * (32 / tg);
+  const unsigned grid = (unsigned)((Q.n + per_cta - 1) / per_cta);
+#define T(TG, TR) if (tg == TG && tr == TR) { dense_y_begin_kernel<TG, TR><<<grid, 128, 0, st>>>(Q); return cudaGetLastError(); }
+  T(4, 1) T(8, 1) T(8, 2) T(8, 3) T(8, 4) T(16, 3) T(16, 4)
+#undef T
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t dense_launch_step(int tg, int tr, const DenseYState& Q, cudaStream_t st) {
+  const int64_t per_cta = 4 * (32 / tg);
+  const unsigned grid = (unsigned)((Q.n + per_cta - 1) / per_cta);
+#define T(TG, TR) if (tg == TG && tr == TR) { dense_y_step_kernel<TG, TR><<<grid, 128, 0, st>>>(Q); return cudaGetLastError(); }
+  T(4, 1) T(8, 1) T(8, 2) T(8, 3) T(8, 4) T(16, 3) T(16, 4)
+#undef T
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t dense_launch_decide(const DenseYState& Q, cudaStream_t st) {
+  dense_y_decide_kernel<<<(unsigned)((Q.n + 127) / 128), 128, 0, st>>>(Q);
+  return cudaGetLastError();
+}
+
+size_t dense_smem_needed(int k, int kt) { return dense_smem_bytes(k, kt); }
+
+}  // namespace glrm

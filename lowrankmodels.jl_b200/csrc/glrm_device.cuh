@@ -680,14 +680,26 @@ __device__ __forceinline__ void cluster_sum_g(double2 (&g)[R], double2* buf, int
 #ifndef GLRM_LIGHT_CTAS
 #define GLRM_LIGHT_CTAS 4      /* resident 4-warp CTAs per SM the warp-tier kernel is compiled for (register cap) */
 #endif
+// the CTA / cluster tiers run the units whose latency bounds a sharded sweep: their depth / residency are separate knobs
+#ifndef GLRM_HEAVY_DEPTH
+#define GLRM_HEAVY_DEPTH 2
+#endif
+#ifndef GLRM_HEAVY_TRIAL_DEPTH
+#define GLRM_HEAVY_TRIAL_DEPTH 4
+#endif
+#ifndef GLRM_HEAVY_CTAS
+#define GLRM_HEAVY_CTAS 2
+#endif
 template <int R> struct TileCfg {
   static constexpr int DEPTH = GLRM_PIPE_DEPTH;
   static constexpr int TRIAL_DEPTH = GLRM_TRIAL_DEPTH;
   static constexpr int LIGHT_CTAS = GLRM_LIGHT_CTAS;
-  static constexpr int HEAVY_CTAS = 2;
+  static constexpr int HEAVY_DEPTH = GLRM_HEAVY_DEPTH;
+  static constexpr int HEAVY_TRIAL_DEPTH = GLRM_HEAVY_TRIAL_DEPTH;
+  static constexpr int HEAVY_CTAS = GLRM_HEAVY_CTAS;
 };
 
-template <int G, int R, int W, int LOSS, int DEPTH, int CS = 1>
+template <int G, int R, int W, int LOSS, int DEPTH, int CS = 1, int TDEPTH = TileCfg<R>::TRIAL_DEPTH>
 __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, double* red, double* part, double* xg, double* clbuf = nullptr) {
   constexpr int NGW = 32 / G;
   const int lane = threadIdx.x & 31;
@@ -779,7 +791,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
       }
       double obj_new;
       if constexpr (G <= 8) {                       // shared-memory transposed reduction (k <= 64)
-        obj_new = trial_pass<G, R, WT, LOSS, TileCfg<R>::TRIAL_DEPTH>(
+        obj_new = trial_pass<G, R, WT, LOSS, (TDEPTH <= G ? TDEPTH : G)>(
             A, start, len, gwarp, lane, xn, ucode, us, up1, up2,
             part + (W == 1 ? (threadIdx.x >> 5) : warp) * TRIAL_TILE_DOUBLES(G));
         obj_new = block_sum_obj<W>(obj_new, red, lane, warp);
@@ -844,7 +856,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32, TileCfg<R>::HEAVY_CT
   __shared__ double part[WARPS_PER_CTA_HEAVY * TRIAL_TILE_DOUBLES(G)];
   __shared__ __align__(16) double xg[4 * G * R];
   if (sweep_stopped(A)) return;
-  process_unit<G, R, WARPS_PER_CTA_HEAVY, LOSS, TileCfg<R>::DEPTH>(A, A.order[blockIdx.x], red, part, xg);
+  process_unit<G, R, WARPS_PER_CTA_HEAVY, LOSS, (TileCfg<R>::HEAVY_DEPTH <= G ? TileCfg<R>::HEAVY_DEPTH : G), 1, TileCfg<R>::HEAVY_TRIAL_DEPTH>(A, A.order[blockIdx.x], red, part, xg);
 }
 
 // super-heavy units: a cluster of CS CTAs (8 warps each) per unit — CLUSTER_CTAS for degrees >= cluster_threshold,
@@ -861,7 +873,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32, TileCfg<R>::HEAVY_CT
   __shared__ __align__(16) double xg[4 * G * R];
   __shared__ __align__(16) double clbuf[2 + 2 * G * R];
   if (sweep_stopped(A)) return;                // the same value in every CTA of the cluster: the flag only changes between kernels
-  process_unit<G, R, WARPS_PER_CTA_HEAVY, LOSS, TileCfg<R>::DEPTH, CS>(A, A.order[blockIdx.x / CS], red, part, xg, clbuf);
+  process_unit<G, R, WARPS_PER_CTA_HEAVY, LOSS, (TileCfg<R>::HEAVY_DEPTH <= G ? TileCfg<R>::HEAVY_DEPTH : G), CS, TileCfg<R>::HEAVY_TRIAL_DEPTH>(A, A.order[blockIdx.x / CS], red, part, xg, clbuf);
 }
 
 // out[unit] = r(own[:, unit])  — the penalty terms of calc_penalty (evaluate_fit.jl:91-104)

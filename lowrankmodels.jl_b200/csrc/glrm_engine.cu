@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -20,6 +21,7 @@
 #include "glrm_launch.cuh"
 #include "glrm_small.cuh"
 #include "glrm_vec.cuh"
+#include "glrm_dense_host.h"
 
 using namespace glrm;
 
@@ -106,6 +108,26 @@ struct Side {
   std::vector<int64_t> bounds;  // [nranks+1] shard boundaries (all ranks)
 };
 
+// fully observed problems (csrc/glrm_dense.cuh): A as Julia stores it, the static chunk plan (all features), the plan of the
+// features still searching, and the Y-sweep work buffers
+struct DenseHost {
+  bool on = false;
+  int kt = 0;
+  int sms = 148;
+  double* d_A = nullptr;
+  int32_t *d_chunk_ptr = nullptr, *d_feat_list = nullptr, *d_feat_off = nullptr, *d_nchunks = nullptr;
+  int32_t *d_chunk_ptr2 = nullptr, *d_feat_list2 = nullptr, *d_feat_off2 = nullptr, *d_nchunks2 = nullptr;
+  int32_t *d_nactive = nullptr, *d_active = nullptr;
+  int max_chunks = 1;
+  double *d_gscratch = nullptr, *d_gpart = nullptr, *d_objpart = nullptr, *d_G = nullptr, *d_Ynew = nullptr;
+  double *d_colobj = nullptr, *d_objold = nullptr, *d_regnew = nullptr;
+  int n_blocks = 1;
+  int64_t rows_per_block = 0;
+  int x_grid = 1;
+  volatile int32_t* h_nactive = nullptr;    // mapped pinned [2]: (features still searching, sweep sequence number)
+  int32_t seq = 0;
+};
+
 constexpr int EVENT_CHUNK = 64;   // iterations whose timing events are in flight before the host harvests them
 constexpr int MAX_RANKS = 64;     // slots of the peer flag array
 
@@ -141,8 +163,8 @@ struct glrmb200_engine {
   double* d_objs = nullptr;                 // [objs_cap] objective record of the running fit
   int64_t objs_cap = 0;
   double* d_stage = nullptr;                // staging buffer for contiguous factor transfers [(m + d) * k]
-  double* h_pinned = nullptr;               // [8] process-level pinned scratch (not owned)
-  volatile int* h_stop = nullptr;           // mapped pinned flag written by record_kernel (not owned)
+  double* h_pinned = nullptr;               // [16] pinned, device-mapped scratch (pinned_get / pinned_put)
+  volatile int* h_stop = nullptr;           // mapped flag written by record_kernel (inside h_pinned)
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;            // the warp-tier launch of a sweep runs here, concurrently with the CTA tier
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -161,6 +183,7 @@ struct glrmb200_engine {
   int* d_peer_rank = nullptr;
   unsigned long long epoch = 0;              // barriers executed since the flags were last zeroed (glrmb200_ipc_export)
   double* d_barrier = nullptr;
+  DenseHost dn;
 };
 
 static int g_device_checked = -1;
@@ -177,13 +200,25 @@ static int check_device() {
   return 0;
 }
 
-// process-level pinned scratch: [0..7] doubles for scalar read-backs, then the mapped stop flag
-static double* g_pinned = nullptr;
-static int pinned_setup() {
-  if (g_pinned) return 0;
-  CUDA_OK(cudaHostAlloc((void**)&g_pinned, 16 * sizeof(double), cudaHostAllocMapped | cudaHostAllocPortable));
-  memset(g_pinned, 0, 16 * sizeof(double));
+// Pinned, device-mapped scratch of a handle: [0..7] doubles for scalar read-backs, [8] the stop flag, [10] the dense path's
+// (features still searching, sweep number) pair.  cudaHostAlloc / cudaFreeHost are slow and synchronising, so blocks are
+// recycled through a process-level free list (distinct handles never share a block: they may run on different threads).
+static std::mutex g_pinned_mu;
+static std::vector<double*> g_pinned_free;
+static int pinned_get(double** out) {
+  {
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    if (!g_pinned_free.empty()) { *out = g_pinned_free.back(); g_pinned_free.pop_back(); }
+    else *out = nullptr;
+  }
+  if (!*out) CUDA_OK(cudaHostAlloc((void**)out, 16 * sizeof(double), cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(*out, 0, 16 * sizeof(double));
   return 0;
+}
+static void pinned_put(double* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pinned_mu);
+  g_pinned_free.push_back(p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -393,6 +428,191 @@ static SweepArgs make_args(const glrmb200_engine* E, bool x_side, int flags, dou
 }
 
 // ------------------------------------------------------------------------------------------------
+// fully observed path (csrc/glrm_dense.cuh)
+static void dense_free(glrmb200_engine* E) {
+  DenseHost& D = E->dn;
+  dfree(D.d_A, E->stream);
+  dfree(D.d_chunk_ptr, E->stream); dfree(D.d_feat_list, E->stream); dfree(D.d_feat_off, E->stream); dfree(D.d_nchunks, E->stream);
+  dfree(D.d_chunk_ptr2, E->stream); dfree(D.d_feat_list2, E->stream); dfree(D.d_feat_off2, E->stream); dfree(D.d_nchunks2, E->stream);
+  dfree(D.d_nactive, E->stream); dfree(D.d_active, E->stream);
+  dfree(D.d_gscratch, E->stream); dfree(D.d_gpart, E->stream); dfree(D.d_objpart, E->stream); dfree(D.d_G, E->stream);
+  dfree(D.d_Ynew, E->stream); dfree(D.d_colobj, E->stream); dfree(D.d_objold, E->stream); dfree(D.d_regnew, E->stream);
+  D.on = false;
+}
+
+// can this problem take the dense kernels?  fully observed, rank within the register-tile range, regularizers that act
+// element-wise on block columns (the ordinal block regularizers stay on the gather path), one rank
+static bool dense_eligible(const glrmb200_engine* E, const glrmb200_problem* P) {
+  if (!E->obs_full || E->k > 104 || E->nranks != 1) return false;
+  if (const char* t = getenv("GLRMB200_DENSE")) { if (atoi(t) == 0) return false; }
+  if (getenv("GLRMB200_TILE")) return false;
+  for (int64_t i = 0; i < P->ry_count; ++i)
+    if (P->ry_code[i] & (GLRMB200_REG_ORDINAL | GLRMB200_REG_MNL_ORDINAL)) return false;
+  return true;
+}
+
+static int dense_setup(glrmb200_engine* E, const glrmb200_problem* P) {
+  DenseHost& D = E->dn;
+  const int64_t m = E->m, n = E->n, d = E->d;
+  int rc;
+  D.kt = (int)((E->k + 15) / 16);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, E->device);
+  D.sms = sms;
+  if ((rc = upload(&D.d_A, P->dense_A, (size_t)(m * n), E->stream))) return rc;
+  // static plan: all features in order, chunks of <= DN_TN columns made of whole features
+  std::vector<int32_t> chunk_ptr{0}, feat_list, feat_off;
+  int used = 0;
+  for (int64_t f = 0; f < n; ++f) {
+    const int dim = (int)(E->ystart[(size_t)f + 1] - E->ystart[(size_t)f]);
+    if (used + dim > DN_TN) { chunk_ptr.push_back((int32_t)feat_list.size()); used = 0; }
+    feat_list.push_back((int32_t)f);
+    feat_off.push_back(used);
+    used += dim;
+  }
+  chunk_ptr.push_back((int32_t)feat_list.size());
+  const int32_t nchunks = (int32_t)chunk_ptr.size() - 1;
+  D.max_chunks = 2 * (int)((d + DN_TN - 1) / DN_TN) + 1;           // next-fit bound for any subset of the features
+  if (D.max_chunks < nchunks) D.max_chunks = nchunks;
+  if ((rc = upload(&D.d_chunk_ptr, chunk_ptr.data(), chunk_ptr.size(), E->stream))) return rc;
+  if ((rc = upload(&D.d_feat_list, feat_list.data(), feat_list.size(), E->stream))) return rc;
+  if ((rc = upload(&D.d_feat_off, feat_off.data(), feat_off.size(), E->stream))) return rc;
+  if ((rc = upload(&D.d_nchunks, &nchunks, 1, E->stream))) return rc;
+  if ((rc = dalloc(&D.d_chunk_ptr2, (size_t)n + 2, E->stream))) return rc;
+  if ((rc = dalloc(&D.d_feat_list2, (size_t)n + 1, E->stream))) return rc;
+  if ((rc = dalloc(&D.d_feat_off2, (size_t)n + 1, E->stream))) return rc;
+  if ((rc = dalloc(&D.d_nchunks2, 1, E->stream))) return rc;
+  if ((rc = dalloc(&D.d_nactive, 1, E->stream))) return rc;
+  if ((rc = dalloc(&D.d_active, (size_t)n, E->stream))) return rc;
+  CUDA_OK(cudaMemsetAsync(D.d_active, 0, (size_t)n * sizeof(int32_t), E->stream));
+  CUDA_OK(cudaMemsetAsync(D.d_nactive, 0, sizeof(int32_t), E->stream));
+  CUDA_OK(cudaMemsetAsync(D.d_nchunks2, 0, sizeof(int32_t), E->stream));
+  // row blocks of the Y sweep: 8 groups of up to 37 blocks (two CTA waves of 148), fixed by m alone so that the
+  // reduction order never depends on the launch
+  const int64_t tiles = (m + DN_TM - 1) / DN_TM;
+  const int bg = (int)std::min<int64_t>(37, std::max<int64_t>(1, (tiles + 7) / 8));
+  D.n_blocks = 8 * bg;
+  D.rows_per_block = ((m + D.n_blocks - 1) / D.n_blocks + DN_TM - 1) / DN_TM * DN_TM;
+  D.x_grid = (int)std::min<int64_t>(tiles, sms);
+  if ((rc = dalloc(&D.d_gscratch, (size_t)D.x_grid * DN_TM * E->stride, E->stream))) return rc;
+  if ((rc = dalloc(&D.d_gpart, (size_t)D.n_blocks * (size_t)d * E->stride, E->stream))) return rc;
+  if ((rc = dalloc(&D.d_objpart, (size_t)D.n_blocks * (size_t)n, E->stream))) return rc;
+  CUDA_OK(cudaMemsetAsync(D.d_objpart, 0, (size_t)D.n_blocks * (size_t)n * sizeof(double), E->stream));
+  if ((rc = dalloc(&D.d_G, (size_t)d * E->stride, E->stream))) return rc;
+  if ((rc = dalloc(&D.d_Ynew, (size_t)d * E->stride, E->stream))) return rc;
+  CUDA_OK(cudaMemsetAsync(D.d_Ynew, 0, (size_t)d * E->stride * sizeof(double), E->stream));
+  if ((rc = dalloc(&D.d_colobj, (size_t)n, E->stream))) return rc;
+  if ((rc = dalloc(&D.d_objold, (size_t)n, E->stream))) return rc;
+  if ((rc = dalloc(&D.d_regnew, (size_t)n, E->stream))) return rc;
+  D.h_nactive = reinterpret_cast<volatile int32_t*>(E->h_pinned + 10);
+  if (dense_smem_needed((int)E->k, D.kt) > 227 * 1024) return fail(GLRMB200_E_UNSUPPORTED, "dense path: k = %lld needs too much shared memory", (long long)E->k);
+  D.on = true;
+  return 0;
+}
+
+static DenseArgs dense_args(const glrmb200_engine* E, bool static_plan, const double* Ymat, int flags, double min_stepsize, bool honour_stop) {
+  const DenseHost& D = E->dn;
+  DenseArgs P;
+  memset(&P, 0, sizeof(P));
+  P.A = D.d_A; P.m = E->m; P.n = E->n;
+  P.row0 = 0; P.row1 = E->m;
+  P.X = E->d_X; P.Ymat = Ymat;
+  P.stride = E->stride; P.k = (int)E->k; P.kp = E->kp;
+  P.ystart = E->d_ystart;
+  P.loss_code = E->d_loss_code; P.loss_param = E->d_loss_param;
+  P.chunk_ptr = static_plan ? D.d_chunk_ptr : D.d_chunk_ptr2;
+  P.feat_list = static_plan ? D.d_feat_list : D.d_feat_list2;
+  P.feat_off = static_plan ? D.d_feat_off : D.d_feat_off2;
+  P.nchunks = static_plan ? D.d_nchunks : D.d_nchunks2;
+  P.reg_code = E->rows.d_reg_code; P.reg_param = E->rows.d_reg_param; P.reg_uniform = E->rows.reg_uniform;
+  P.alpha = E->rows.d_alpha; P.min_stepsize = min_stepsize; P.obj_out = E->rows.d_obj;
+  P.gscratch = D.d_gscratch;
+  P.trial_counter = E->d_trials;
+  P.stop = honour_stop ? E->d_stop : nullptr;
+  P.flags = flags;
+  P.gpart = D.d_gpart; P.objpart = D.d_objpart;
+  P.rows_per_block = D.rows_per_block; P.n_blocks = D.n_blocks;
+  return P;
+}
+static DenseYState dense_ystate(glrmb200_engine* E, int flags, double min_stepsize, bool honour_stop) {
+  DenseHost& D = E->dn;
+  DenseYState Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.Y = E->d_Y; Q.Ynew = D.d_Ynew; Q.G = D.d_G;
+  Q.ystart = E->d_ystart;
+  Q.colobj = D.d_colobj; Q.objold = D.d_objold; Q.regnew = D.d_regnew;
+  Q.alpha = E->cols.d_alpha; Q.obj_out = E->cols.d_obj;
+  Q.active = D.d_active; Q.nactive = D.d_nactive; Q.h_nactive = D.h_nactive;
+  Q.chunk_ptr = D.d_chunk_ptr2; Q.feat_list = D.d_feat_list2; Q.feat_off = D.d_feat_off2; Q.nchunks = D.d_nchunks2;
+  Q.reg_code = E->cols.d_reg_code; Q.reg_param = E->cols.d_reg_param; Q.reg_uniform = E->cols.reg_uniform;
+  Q.n = E->n; Q.d = E->d; Q.m = E->m;
+  Q.stride = E->stride; Q.k = (int)E->k;
+  Q.min_stepsize = min_stepsize;
+  Q.trial_counter = E->d_trials + 1;
+  Q.stop = honour_stop ? E->d_stop : nullptr;
+  Q.flags = flags;
+  Q.seq = D.seq;
+  return Q;
+}
+#define DN_OK(call)                                                                                                   \
+  do {                                                                                                                \
+    cudaError_t ce__ = (call);                                                                                        \
+    if (ce__ != cudaSuccess) return fail(GLRMB200_E_CUDA, "%s: %s", #call, cudaGetErrorString(ce__));                  \
+  } while (0)
+
+static int dense_sweep_x(glrmb200_engine* E, double min_stepsize, bool honour_stop, int64_t* launches) {
+  const DenseHost& D = E->dn;
+  const int loss = E->loss_template == GLRMB200_LOSS_QUAD ? GLRMB200_LOSS_QUAD : 0;
+  DenseArgs P = dense_args(E, true, E->d_Y, 0, min_stepsize, honour_stop);
+  DN_OK(dense_launch_x(D.kt, E->tile_g, E->tile_r, loss, P, D.x_grid, E->stream));
+  ++*launches;
+  return 0;
+}
+
+// losses of every feature at the current Y -> colobj (mode 0: and the gradient G_Y); then obj_by_col = loss + ry and the
+// search state (dense_y_begin_kernel)
+static int dense_eval_cols(glrmb200_engine* E, int flags, double min_stepsize, bool honour_stop, int mode, int64_t* launches) {
+  DenseHost& D = E->dn;
+  const int loss = E->loss_template == GLRMB200_LOSS_QUAD ? GLRMB200_LOSS_QUAD : 0;
+  DenseArgs P = dense_args(E, true, E->d_Y, flags, min_stepsize, honour_stop);
+  DN_OK(dense_launch_y_pass(D.kt, loss, mode, P, D.n_blocks, D.max_chunks, E->stream));
+  if (mode == 0) DN_OK(dense_launch_reduce(D.d_gpart, D.n_blocks, E->d * (int64_t)E->stride, D.d_G, nullptr, E->stream));
+  DN_OK(dense_launch_reduce(D.d_objpart, D.n_blocks, E->n, D.d_colobj, nullptr, E->stream));
+  DenseYState Q = dense_ystate(E, flags, min_stepsize, honour_stop);
+  DN_OK(dense_launch_begin(E->tile_g, E->tile_r, Q, E->stream));
+  *launches += mode == 0 ? 4 : 3;
+  return 0;
+}
+
+// the Y sweep (proxgrad.jl:160-203): gradient pass, then line-search rounds over the features still searching.  Rounds are
+// enqueued without waiting; every kernel of a round returns at once when no feature is left, and the host stops enqueuing
+// when the mapped counter says so.
+static int dense_sweep_y(glrmb200_engine* E, double min_stepsize, bool honour_stop, int64_t* launches) {
+  DenseHost& D = E->dn;
+  const int loss = E->loss_template == GLRMB200_LOSS_QUAD ? GLRMB200_LOSS_QUAD : 0;
+  int rc;
+  ++D.seq;
+  if ((rc = dense_eval_cols(E, 0, min_stepsize, honour_stop, 0, launches))) return rc;
+  DenseYState Q = dense_ystate(E, 0, min_stepsize, honour_stop);
+  DenseArgs P = dense_args(E, false, D.d_Ynew, 0, min_stepsize, honour_stop);
+  for (int round = 0;; ++round) {
+    if (round >= 2 && D.h_nactive[1] == D.seq && D.h_nactive[0] == 0) break;
+    if (round > 0 && round % 64 == 0) {                      // far more rounds than any step-size history needs: make sure
+      CUDA_OK(cudaStreamSynchronize(E->stream));
+      if (D.h_nactive[1] == D.seq && D.h_nactive[0] == 0) break;
+      if (round >= 4096) return fail(GLRMB200_E_STATE, "dense Y line search did not terminate");
+    }
+    DN_OK(dense_launch_plan(Q, E->stream));
+    DN_OK(dense_launch_step(E->tile_g, E->tile_r, Q, E->stream));
+    DN_OK(dense_launch_y_pass(D.kt, loss, 1, P, D.n_blocks, D.max_chunks, E->stream));
+    DN_OK(dense_launch_reduce(D.d_objpart, D.n_blocks, E->n, D.d_colobj, D.d_nactive, E->stream));
+    DN_OK(dense_launch_decide(Q, E->stream));
+    *launches += 5;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // C ABI
 extern "C" int glrmb200_version(void) { return GLRMB200_VERSION; }
 extern "C" const char* glrmb200_last_error(void) { return g_err; }
@@ -454,6 +674,7 @@ extern "C" int glrmb200_destroy(glrmb200_handle E) {
     dfree(E->d_loss_code, E->stream); dfree(E->d_loss_param, E->stream); dfree(E->d_ystart, E->stream);
     dfree(E->d_scalars, E->stream); dfree(E->d_trials, E->stream); dfree(E->d_stop, E->stream);
     dfree(E->d_objs, E->stream); dfree(E->d_stage, E->stream); dfree(E->d_barrier, E->stream);
+    dense_free(E);
   }
   for (auto& e : E->evpool) if (e) cudaEventDestroy(e);
   if (E->ev_base) cudaEventDestroy(E->ev_base);
@@ -462,6 +683,7 @@ extern "C" int glrmb200_destroy(glrmb200_handle E) {
   if (E->ev_join) cudaEventDestroy(E->ev_join);
   if (E->stream2) cudaStreamDestroy(E->stream2);
   if (E->stream) cudaStreamDestroy(E->stream);   // work already enqueued (the frees) still completes
+  pinned_put(E->h_pinned);                       // the stream was synchronised above: no kernel still writes the flags
   delete E;
   return 0;
 }
@@ -610,7 +832,8 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
     }
   }
   E->stride = 2 * E->tile_g * E->tile_r;
-  if (E->has_vec && E->tile_r > 2)
+  const bool want_dense = dense_eligible(E, P);
+  if (E->has_vec && E->tile_r > 2 && !want_dense)
     return fail(GLRMB200_E_UNSUPPORTED, "vector-valued losses are supported on the device for k <= 32 this round (k = %lld)", (long long)k);
   if (const char* t = getenv("GLRMB200_HEAVY")) E->heavy_threshold = std::max<long long>(1, atoll(t));
   if (const char* t = getenv("GLRMB200_CLUSTER")) E->cluster_threshold = std::max<long long>(1, atoll(t));
@@ -639,9 +862,8 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   if (E->device < 0 || E->device >= g_device_checked) return fail(GLRMB200_E_INVALID, "device %d out of range (%d visible)", E->device, g_device_checked);
   CUDA_OK(cudaSetDevice(E->device));
   if ((rc = pool_setup(E->device))) return rc;
-  if ((rc = pinned_setup())) return rc;
-  E->h_pinned = g_pinned;
-  E->h_stop = reinterpret_cast<volatile int*>(g_pinned + 8);
+  if ((rc = pinned_get(&E->h_pinned))) return rc;
+  E->h_stop = reinterpret_cast<volatile int*>(E->h_pinned + 8);
   CUDA_OK(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
   CUDA_OK(cudaStreamCreateWithFlags(&E->stream2, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&E->ev_fork, cudaEventDisableTiming));
@@ -660,8 +882,10 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   if ((rc = setup_regs(E, C, P->ry_count, P->ry_code, P->ry_param, true))) return rc;
   E->all_rows_vec.assign(E->has_vec ? (size_t)m : 0, 1);   // with block columns every row takes the vector path
   std::vector<char>& all_rows_vec = E->all_rows_vec;
-  if (E->has_vec) {
+  if (E->has_vec || want_dense) {
     if ((rc = upload(&E->d_ystart, E->ystart.data(), E->ystart.size(), E->stream))) return rc;
+  }
+  if (E->has_vec) {
     for (int64_t f = 0; f < n; ++f) {
       if (!col_is_vec[(size_t)f]) continue;
       const int rcf = P->ry_code[P->ry_count == 1 ? 0 : f];
@@ -673,7 +897,27 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
     }
   }
 
-  if (E->obs_full) {
+  if (E->obs_full && want_dense) {
+    // dense kernels: A stays exactly as Julia stores it (one copy, no transposed twin, no schedules)
+    if ((rc = dense_setup(E, P))) return rc;
+    R.nnz_local = C.nnz_local = m * n;
+    unsigned long long* d_bad = nullptr;
+    if ((rc = dalloc(&d_bad, 1, E->stream))) return rc;
+    CUDA_OK(cudaMemsetAsync(d_bad, 0xff, sizeof(unsigned long long), E->stream));
+    validate_dense_kernel<<<(unsigned)((m * n + 255) / 256), 256, 0, E->stream>>>(E->dn.d_A, m * n, m, E->d_loss_code, E->d_loss_param, d_bad);
+    CUDA_OK(cudaGetLastError());
+    unsigned long long bad = 0;
+    CUDA_OK(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
+    CUDA_OK(cudaStreamSynchronize(E->stream));
+    dfree(d_bad, E->stream);
+    if (bad != ~0ULL) {
+      const int kind = -(int)(bad & 15ULL);
+      const int64_t pos = (int64_t)(bad >> 4);
+      const int64_t f = pos / m, e = pos % m;
+      if (kind == GLRMB200_E_NAN) return fail(kind, "Observed value in entry (%lld, %lld) is NaN.", (long long)e + 1, (long long)f + 1);
+      return fail(kind, "entry (%lld, %lld): label %g is outside the domain of loss code %d", (long long)e + 1, (long long)f + 1, P->dense_A[f * m + e], P->loss_code[f]);
+    }
+  } else if (E->obs_full) {
     // column side streams the Julia (column-major) A as is; the row side gets a row-major copy
     const int64_t cb = C.begin, ce = C.end;
     C.nnz_local = (ce - cb) * m;
@@ -774,6 +1018,11 @@ extern "C" int glrmb200_set_obs(glrmb200_handle E, const int64_t* row_ptr, const
   if (!E) return fail(GLRMB200_E_STATE, "null handle");
   CUDA_OK(cudaSetDevice(E->device));
   CUDA_OK(cudaStreamSynchronize(E->stream));
+  if (E->dn.on) {
+    if (E->has_vec && E->tile_r > 2)
+      return fail(GLRMB200_E_UNSUPPORTED, "observation lists with vector-valued losses need k <= 32 (k = %lld)", (long long)E->k);
+    dense_free(E);                             // a fully observed handle becomes list mode
+  }
   return load_lists(E, row_ptr, row_idx, row_val, col_ptr, col_idx, col_val);
 }
 
@@ -827,6 +1076,8 @@ extern "C" int glrmb200_shard(glrmb200_handle E, int64_t* rb, int64_t* re, int64
 // (peer_barrier_kernel), otherwise a 1-element NCCL all-reduce.
 static int comm_barrier(glrmb200_engine* E) {
   if (E->nranks == 1) return 0;
+  static const bool no_exchange = getenv("GLRMB200_NO_EXCHANGE") && atoi(getenv("GLRMB200_NO_EXCHANGE"));
+  if (no_exchange) return 0;      // tuning hook (tools/tune.py): time one shard of an N-rank fit on a single GPU; results are wrong
   if (E->peer_ready) {
     ++E->epoch;
     peer_barrier_kernel<<<1, 64, 0, E->stream>>>(E->d_peer_flags, E->d_flags, E->d_peer_rank, E->rank, E->nranks - 1, E->epoch, E->d_stop + 1);
@@ -986,6 +1237,7 @@ extern "C" int glrmb200_download_factors(glrmb200_handle E, double* X, double* Y
 // all-gather of per-unit arrays whose shards are contiguous (`elems` doubles per unit)
 static int allgather_units(glrmb200_engine* E, double* buf, const Side& S, int64_t elems, const int64_t* colmap = nullptr) {
   if (E->nranks == 1) return 0;
+  if (getenv("GLRMB200_NO_EXCHANGE") && atoi(getenv("GLRMB200_NO_EXCHANGE"))) return 0;   // tuning hook, see comm_barrier
   if (!E->comm) return fail(GLRMB200_E_STATE, "glrmb200_comm_init was not called");
   NCCL_OK(g_nccl.GroupStart());
   for (int r = 0; r < E->nranks; ++r) {
@@ -1003,10 +1255,16 @@ static int allgather_units(glrmb200_engine* E, double* buf, const Side& S, int64
 // (the evaluation sweep over Y's columns, the row penalties over X) is enqueued BEFORE the barrier: once a rank has
 // passed it, its peers may start storing the next sweep's columns into this rank's replicas.
 static int objective_resident(glrmb200_engine* E, bool include_reg, double* out, int64_t* launches) {
-  SweepArgs A = make_args(E, /*x_side=*/false, FLAG_EVAL_ONLY | (include_reg ? 0 : FLAG_NO_REG), INFINITY);
-  cudaError_t ce = launch_sweep(E, A, E->cols, launches);
-  if (ce == cudaSuccess) ce = launch_vec(E, A, false, E->cols, launches);
-  if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "objective sweep launch: %s", cudaGetErrorString(ce));
+  cudaError_t ce = cudaSuccess;
+  if (E->dn.on) {
+    int rc0 = dense_eval_cols(E, FLAG_EVAL_ONLY | (include_reg ? 0 : FLAG_NO_REG), INFINITY, false, 1, launches);
+    if (rc0) return rc0;
+  } else {
+    SweepArgs A = make_args(E, /*x_side=*/false, FLAG_EVAL_ONLY | (include_reg ? 0 : FLAG_NO_REG), INFINITY);
+    ce = launch_sweep(E, A, E->cols, launches);
+    if (ce == cudaSuccess) ce = launch_vec(E, A, false, E->cols, launches);
+    if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "objective sweep launch: %s", cudaGetErrorString(ce));
+  }
   if (include_reg) {
     ce = launch_reg_eval(E, E->d_X, E->rows, E->rows.d_obj);
     if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "penalty launch: %s", cudaGetErrorString(ce));
@@ -1112,6 +1370,7 @@ extern "C" int glrmb200_fit_resident(glrmb200_handle E, const glrmb200_params* p
     }
     CUDA_OK(cudaEventRecord(ev[0], E->stream));
     for (int inner = 0; inner < prm->inner_iter_X; ++inner) {              // :117-158
+      if (E->dn.on) { if ((rc = dense_sweep_x(E, prm->min_stepsize, true, &prof.x_launches))) return rc; continue; }
       SweepArgs A = make_args(E, true, 0, prm->min_stepsize, true);
       cudaError_t ce = launch_sweep(E, A, E->rows, &prof.x_launches);
       if (ce == cudaSuccess) ce = launch_vec(E, A, true, E->rows, &prof.x_launches);
@@ -1122,6 +1381,7 @@ extern "C" int glrmb200_fit_resident(glrmb200_handle E, const glrmb200_params* p
     else if ((rc = allgather_units(E, E->d_X, E->rows, E->stride))) return rc;
     CUDA_OK(cudaEventRecord(ev[2], E->stream));
     for (int inner = 0; inner < prm->inner_iter_Y; ++inner) {              // :160-203
+      if (E->dn.on) { if ((rc = dense_sweep_y(E, prm->min_stepsize, true, &prof.y_launches))) return rc; continue; }
       SweepArgs A = make_args(E, false, 0, prm->min_stepsize, true);
       cudaError_t ce = launch_sweep(E, A, E->cols, &prof.y_launches);
       if (ce == cudaSuccess) ce = launch_vec(E, A, false, E->cols, &prof.y_launches);
@@ -1180,6 +1440,7 @@ extern "C" int glrmb200_fit_sparse(glrmb200_handle E, const glrmb200_sparse_para
                                    glrmb200_profile* profile) {
   if (!E || !prm || !X || !Y || !ch_objective || !ch_seconds || !n_recorded) return fail(GLRMB200_E_INVALID, "null argument");
   if (E->has_vec) return fail(GLRMB200_E_UNSUPPORTED, "SparseProxGradParams handles scalar-embedding losses only (sparse_proxgrad.jl:70 uses dot(x_e, y_f))");
+  if (E->dn.on) return fail(GLRMB200_E_UNSUPPORTED, "SparseProxGradParams on a fully observed handle: create it with GLRMB200_DENSE=0 (gather kernels) or pass observation lists");
   if (cap < prm->max_iter + 2) return fail(GLRMB200_E_INVALID, "cap %d < max_iter+2", cap);
   if (prm->inner_iter < 1) return fail(GLRMB200_E_INVALID, "inner_iter must be >= 1");
   bool allzero = true;

@@ -73,3 +73,50 @@ int glrm_synth_pattern(int64_t m, int64_t n, const int64_t* deg, const double* c
   free(cptr); free(rptr); free(rcols);
   return 0;
 }
+
+/* ---- dense synthetic matrices for configs 4 and 5 (synth.py::config4 / config5), filled in parallel ------------------ */
+#include <math.h>
+static inline double n01(uint64_t key, uint64_t idx) {       /* synth.py::normal: Box-Muller on counters 2 idx, 2 idx + 1 */
+  const double u1 = u01(key, idx * 2ULL), u2 = u01(key, idx * 2ULL + 1ULL);
+  return sqrt(-2.0 * log(u1)) * cos(2.0 * M_PI * u2);
+}
+
+/* C5: A[i + m j] = Cn[z_i + centroids j] + 0.1 N(0,1)(counter j m + i); Cn is (centroids x n) column-major */
+void glrm_synth_c5(int64_t m, int64_t n, int64_t centroids, const double* Cn, const int64_t* z, uint64_t key, double* A) {
+#pragma omp parallel for schedule(static) collapse(1)
+  for (int64_t j = 0; j < n; ++j) {
+    const double* c = Cn + j * centroids;
+    double* a = A + j * m;
+    for (int64_t i = 0; i < m; ++i) a[i] = c[z[i]] + 0.1 * n01(key, (uint64_t)(j * m + i));
+  }
+}
+
+/* C4: base = P Q / 2 (P m x 4 column-major, Q 4 x n column-major);
+ *     columns [0, nq): base + 0.3 N(key_n); [nq, nq + nh): sign(base + 0.3 N(key_n)) in {-1, +1};
+ *     the rest: clip(floor(U(key_u) levels) + 1 + clip(round(base), -2, 2), 1, levels) */
+void glrm_synth_c4(int64_t m, int64_t n, int64_t nq, int64_t nh, int64_t levels, const double* P, const double* Q,
+                   uint64_t key_n, uint64_t key_u, double* A) {
+#pragma omp parallel for schedule(static)
+  for (int64_t j = 0; j < n; ++j) {
+    const double q0 = Q[4 * j], q1 = Q[4 * j + 1], q2 = Q[4 * j + 2], q3 = Q[4 * j + 3];
+    double* a = A + j * m;
+    for (int64_t i = 0; i < m; ++i) {
+      const double base = (P[i] * q0 + P[i + m] * q1 + P[i + 2 * m] * q2 + P[i + 3 * m] * q3) / 2.0;
+      const uint64_t idx = (uint64_t)(j * m + i);
+      if (j < nq) a[i] = base + 0.3 * n01(key_n, idx);
+      else if (j < nq + nh) a[i] = (base + 0.3 * n01(key_n, idx)) >= 0.0 ? 1.0 : -1.0;
+      else {
+        double shift = rint(base);
+        shift = shift < -2.0 ? -2.0 : (shift > 2.0 ? 2.0 : shift);
+        double v = floor(u01(key_u, idx) * (double)levels) + 1.0 + shift;
+        a[i] = v < 1.0 ? 1.0 : (v > (double)levels ? (double)levels : v);
+      }
+    }
+  }
+}
+
+/* out[i] = N(0,1)(counter start + i) — synth.py::normal_matrix for the big factor initialisations */
+void glrm_synth_normal_fill(uint64_t key, int64_t start, int64_t count, double* out) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < count; ++i) out[i] = n01(key, (uint64_t)(start + i));
+}

@@ -29,6 +29,8 @@ def _synth_lib():
             raise RuntimeError(f"{path} is missing: run __graft_entry__.build()")
         _SYNTH_LIB = C.CDLL(path)
         _SYNTH_LIB.glrm_synth_pattern.restype = C.c_int
+        for fn in ("glrm_synth_c4", "glrm_synth_c5", "glrm_synth_normal_fill"):
+            getattr(_SYNTH_LIB, fn).restype = None
     return _SYNTH_LIB
 
 
@@ -70,7 +72,13 @@ def normal(seed, stream, idx):
 
 
 def normal_matrix(seed, stream, rows, cols):
-    """(rows, cols) Fortran-ordered N(0,1): element (r, c) uses counter c*rows + r."""
+    """(rows, cols) Fortran-ordered N(0,1): element (r, c) uses counter c*rows + r.  Large matrices are filled by the C
+    helper (same counters, OpenMP; libm's log / cos instead of numpy's, i.e. equal up to the last ulp)."""
+    if rows * cols >= 4_000_000:
+        out = np.empty((rows, cols), order="F")
+        _synth_lib().glrm_synth_normal_fill(C.c_uint64(int(_key(seed, stream))), C.c_int64(0), C.c_int64(rows * cols),
+                                            out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
     return normal(seed, stream, np.arange(rows * cols, dtype=np.uint64)).reshape((rows, cols), order="F")
 
 
@@ -189,14 +197,12 @@ def config4(scale=1, seed=1, k=20, levels=5):
     nm = n - nq - nh
     P = normal_matrix(seed, 31, m, 4)
     Q = normal_matrix(seed, 32, 4, n)
-    base = P @ Q / 2.0
     A = np.empty((m, n), order="F")
-    idx = np.arange(m * n, dtype=np.uint64).reshape((m, n), order="F")
-    A[:, :nq] = base[:, :nq] + 0.3 * normal(seed, 33, idx[:, :nq])
-    A[:, nq:nq + nh] = np.where(base[:, nq:nq + nh] + 0.3 * normal(seed, 33, idx[:, nq:nq + nh]) >= 0, 1.0, -1.0)
-    u = uniform(seed, 34, idx[:, nq + nh:])
-    shift = np.clip(np.round(base[:, nq + nh:]), -2, 2)
-    A[:, nq + nh:] = np.clip(np.floor(u * levels) + 1 + shift, 1, levels)
+    dp = C.POINTER(C.c_double)
+    _synth_lib().glrm_synth_c4(C.c_int64(m), C.c_int64(n), C.c_int64(nq), C.c_int64(nh), C.c_int64(levels),
+                               np.ascontiguousarray(P.ravel(order="F")).ctypes.data_as(dp),
+                               np.ascontiguousarray(Q.ravel(order="F")).ctypes.data_as(dp),
+                               C.c_uint64(int(_key(seed, 33))), C.c_uint64(int(_key(seed, 34))), A.ctypes.data_as(dp))
     d = nq + nh + nm * levels
     return dict(name=f"C4/{scale}", m=m, n=n, k=k, A=A, full=True, n_quad=nq, n_hinge=nh, n_multi=nm,
                 levels=levels, d=d, X0=normal_matrix(seed, 3, k, m), Y0=normal_matrix(seed, 4, k, d))
@@ -207,6 +213,11 @@ def config5(scale=1, seed=1, k=100, n=128, centroids=100):
     m = 10_000_000 // scale
     Cn = normal_matrix(seed, 41, centroids, n)
     z = np.minimum((uniform(seed, 42, np.arange(m)) * centroids).astype(np.int64), centroids - 1)
-    A = np.asfortranarray(Cn[z] + 0.1 * normal(seed, 43, np.arange(m * n, dtype=np.uint64)).reshape((m, n), order="F"))
+    A = np.empty((m, n), order="F")
+    dp = C.POINTER(C.c_double)
+    _synth_lib().glrm_synth_c5(C.c_int64(m), C.c_int64(n), C.c_int64(centroids),
+                               np.ascontiguousarray(Cn.ravel(order="F")).ctypes.data_as(dp),
+                               np.ascontiguousarray(z, dtype=np.int64).ctypes.data_as(C.POINTER(C.c_int64)),
+                               C.c_uint64(int(_key(seed, 43))), A.ctypes.data_as(dp))
     return dict(name=f"C5/{scale}", m=m, n=n, k=k, A=A, full=True,
                 X0=normal_matrix(seed, 3, k, m), Y0=normal_matrix(seed, 4, k, n))

@@ -577,9 +577,23 @@ static inline double dotk(const double* a, const double* b, int64_t k) {
   return s;
 }
 
-/* XY = X'Y, stored row-major per example: XY[e*d + c]  (gemm!('T','N',...), proxgrad.jl:66) */
+/* XY = X'Y, stored row-major per example: XY[e*d + c]  (gemm!('T','N',...), proxgrad.jl:66).
+ * The reference calls BLAS dgemm (OpenBLAS ships with Julia).  When the host has handed over a cblas_dgemm entry point
+ * (oracle_set_dgemm: bench.py passes the one of NumPy's bundled OpenBLAS, ILP64 interface) it is used here, so the
+ * CPU baseline pays what the reference pays for this product; otherwise a plain dot-product loop computes it. */
+typedef void (*cblas_dgemm64_fn)(int order, int transa, int transb, int64_t M, int64_t N, int64_t K, double alpha,
+                                 const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
+static cblas_dgemm64_fn g_dgemm = NULL;
+void oracle_set_dgemm(void* fn) { g_dgemm = (cblas_dgemm64_fn)fn; }
+int oracle_has_dgemm(void) { return g_dgemm != NULL; }
+
 static void gemm_xty(const view_t* V, const double* X, const double* Y, double* XY) {
   const int64_t m = V->m, d = V->d, k = V->k;
+  if (g_dgemm) {
+    /* XY (row-major m x d) == column-major d x m == Y' X: CblasColMajor=102, CblasTrans=112, CblasNoTrans=111 */
+    g_dgemm(102, 112, 111, d, m, k, 1.0, Y, k, X, k, 0.0, XY, d);
+    return;
+  }
 #pragma omp parallel for schedule(static)
   for (int64_t eb = 0; eb < m; eb += 8) {
     const int64_t e1 = eb + 8 < m ? eb + 8 : m;

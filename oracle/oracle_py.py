@@ -52,6 +52,38 @@ def _d(a):
     return a.ctypes.data_as(_dp)
 
 
+_blas = None
+
+
+def use_openblas_dgemm(nthreads=0):
+    """Route the faithful form's XY = X'Y through cblas_dgemm of the OpenBLAS bundled with NumPy (ILP64 symbols
+    `scipy_cblas_dgemm64_`), as the reference does through Julia's BLAS.  Returns True when the entry point was found."""
+    global _blas
+    import glob
+    L = lib()
+    L.oracle_set_dgemm.restype = None
+    L.oracle_set_dgemm.argtypes = [C.c_void_p]
+    if _blas is None:
+        cands = glob.glob(os.path.join(os.path.dirname(np.__file__), "..", "numpy.libs", "libscipy_openblas64_*.so"))
+        for path in cands:
+            try:
+                B = C.CDLL(path)
+                fn = C.cast(B.scipy_cblas_dgemm64_, C.c_void_p).value
+                _blas = (B, fn)
+                break
+            except (OSError, AttributeError):
+                continue
+    if _blas is None:
+        return False
+    if nthreads > 0:
+        try:
+            _blas[0].scipy_openblas_set_num_threads64_(C.c_int(nthreads))
+        except AttributeError:
+            pass
+    L.oracle_set_dgemm(C.c_void_p(_blas[1]))
+    return True
+
+
 def loss_eval(loss, u, a):
     code, p = loss.encode()
     u = np.atleast_1d(np.asarray(u, dtype=np.float64)).copy()

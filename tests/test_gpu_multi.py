@@ -19,7 +19,7 @@ def _ngpus():
     return n.value
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_fit_is_bit_identical_to_single_gpu(world):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")

@@ -229,6 +229,7 @@ def test_alternative_tiles_same_result(orc, tile, monkeypatch):
 def test_heavy_units_cta_path(orc, monkeypatch):
     """Force every unit with >= 8 observations through the one-CTA-per-unit kernel."""
     monkeypatch.setenv("GLRMB200_HEAVY", "8")
+    monkeypatch.setenv("GLRMB200_DENSE", "0")                          # fully observed cases below: gather kernels, implicit indices
     A, obs, X0 = small_sparse(seed=24, m=70, n=45, density=0.5)
     g = lrm.GLRM(A, lrm.LogisticLoss() if False else lrm.QuadLoss(), lrm.QuadReg(0.1), lrm.QuadReg(0.1), 4, obs=obs,
                  X=synth.normal_matrix(25, 1, 4, 70), Y=synth.normal_matrix(25, 2, 4, 45))
@@ -242,6 +243,7 @@ def test_super_heavy_units_cluster_path(orc, monkeypatch):
     """Force units with >= 16 observations through the 8-CTA thread-block-cluster kernel (DSMEM reductions)."""
     monkeypatch.setenv("GLRMB200_HEAVY", "8")
     monkeypatch.setenv("GLRMB200_CLUSTER", "16")
+    monkeypatch.setenv("GLRMB200_DENSE", "0")
     A, obs, X0 = small_sparse(seed=26, m=300, n=45, density=0.5)
     g = lrm.GLRM(A, lrm.QuadLoss(), lrm.QuadReg(0.1), lrm.OneReg(0.05), 4, obs=obs,
                  X=synth.normal_matrix(27, 1, 4, 300), Y=synth.normal_matrix(27, 2, 4, 45))
@@ -426,3 +428,105 @@ def test_full_size_config2_properties():
     with lrm.Engine(ep) as eng:
         obj2, _ = eng.fit(p, X2, Y2)
     assert (obj2 == obj).all() and (X2 == X).all() and (Y2 == Y).all()           # deterministic reduction trees
+
+
+# ---- the fully observed (dense) path: csrc/glrm_dense.cuh ----------------------------------------------------------------
+def dense_problem(m=150, n=90, k=7, seed=40, losses=None, rx=None, ry=None, labels=None):
+    P = synth.normal_matrix(seed, 1, m, 3)
+    Q = synth.normal_matrix(seed, 2, 3, n)
+    A = P @ Q + 0.1 * synth.normal_matrix(seed, 3, m, n)
+    if labels == "bool":
+        A = np.where(A >= 0, 1.0, -1.0)
+    elif labels == "count":
+        A = np.floor(np.abs(A) * 2)
+    elif isinstance(labels, int):
+        A = np.clip(np.floor((A - A.min()) / (A.max() - A.min() + 1e-9) * labels) + 1, 1, labels)
+    losses = losses if losses is not None else lrm.QuadLoss()
+    d = n if not isinstance(losses, list) else sum(l.embedding_dim() for l in losses)
+    return lrm.GLRM(np.asfortranarray(A), losses, rx or lrm.QuadReg(0.1), ry or lrm.QuadReg(0.1), k,
+                    X=0.4 * synth.normal_matrix(seed, 4, k, m), Y=0.4 * synth.normal_matrix(seed, 5, k, d))
+
+
+@pytest.mark.parametrize("k", [1, 3, 8, 13, 20, 33, 50, 64, 70, 96, 100, 104, 130])
+def test_dense_path_every_rank_tile(orc, k):
+    """Fully observed problems run the streaming kernels for k <= 104 (8 register-tile shapes) and the gather kernels above;
+    rows not a multiple of the 64-row tile, columns spanning two 64-column chunks."""
+    check(orc, dense_problem(k=k), lrm.ProxGradParams(max_iter=5))
+
+
+def test_dense_path_equals_gather_path(orc, monkeypatch):
+    """The same fully observed fit through the dense kernels and (GLRMB200_DENSE=0) the gather kernels with implicit indices."""
+    g = dense_problem(m=333, n=70, k=20)
+    p = lrm.ProxGradParams(max_iter=8)
+    a = engine_fit(g, p)
+    monkeypatch.setenv("GLRMB200_DENSE", "0")
+    b = engine_fit(g, p)
+    assert_traj_close(a["objective"], b["objective"], 1e-9, "dense vs gather")
+    np.testing.assert_allclose(a["alpharow"], b["alpharow"], rtol=1e-9)
+    np.testing.assert_allclose(a["X"], b["X"], rtol=1e-6, atol=1e-9)
+    assert a["profile"]["x_trials"] == b["profile"]["x_trials"] and a["profile"]["y_trials"] == b["profile"]["y_trials"]
+
+
+@pytest.mark.parametrize("reg", REG_CASES + [lrm.UnitOneSparseConstraint(), lrm.NonNegConstraint(), lrm.ZeroReg()],
+                         ids=lambda r: repr(r).replace(" ", ""))
+def test_dense_path_each_regularizer(orc, reg):
+    g = dense_problem(m=100, n=40, k=5, seed=41, rx=reg, ry=lrm.QuadReg(0.05))
+    check(orc, g, lrm.ProxGradParams(max_iter=6), rtol=1e-6, factors=False)
+    g = dense_problem(m=80, n=30, k=5, seed=42, rx=lrm.QuadReg(0.05), ry=reg)
+    check(orc, g, lrm.ProxGradParams(max_iter=6), rtol=1e-6, factors=False)
+
+
+@pytest.mark.parametrize("name,mk,labels", SCALAR_LOSS_CASES + [("logistic", lambda: lrm.LogisticLoss(), "bool")],
+                         ids=[c[0] for c in SCALAR_LOSS_CASES] + ["logistic"])
+def test_dense_path_each_scalar_loss(orc, name, mk, labels):
+    g = dense_problem(m=130, n=20, k=4, seed=43, losses=mk(), labels=labels)
+    check(orc, g, lrm.ProxGradParams(max_iter=6), rtol=1e-6, factors=False)
+
+
+def test_dense_path_heterogeneous_and_vector_losses(orc):
+    """Scalar and vector-valued losses side by side, fully observed (the shape of config 4), incl. k above the gather
+    path's k <= 32 limit for block columns."""
+    m, n = 200, 24
+    lv = 4
+    A = np.empty((m, n), order="F")
+    base = synth.normal_matrix(44, 1, m, n)
+    A[:, :8] = base[:, :8]
+    A[:, 8:14] = np.where(base[:, 8:14] >= 0, 1.0, -1.0)
+    A[:, 14:] = np.clip(np.floor(np.abs(base[:, 14:]) * 2) + 1, 1, lv)
+    losses = ([lrm.QuadLoss()] * 4 + [lrm.HuberLoss()] * 4 + [lrm.HingeLoss()] * 3 + [lrm.LogisticLoss()] * 3 +
+              [lrm.MultinomialLoss(lv)] * 3 + [lrm.OvALoss(lv)] * 2 + [lrm.BvSLoss(lv)] * 2 + [lrm.OrdisticLoss(lv)] * 2 +
+              [lrm.MultinomialOrdinalLoss(lv)])
+    for k in (6, 40):
+        d = sum(l.embedding_dim() for l in losses)
+        g = lrm.GLRM(A, losses, lrm.QuadReg(0.1), lrm.QuadReg(0.1), k, X=0.3 * synth.normal_matrix(44, 2, k, m),
+                     Y=0.3 * synth.normal_matrix(44, 3, k, d))
+        check(orc, g, lrm.ProxGradParams(max_iter=5), rtol=1e-6, factors=False)
+
+
+def test_dense_path_many_chunks_and_inner_iterations(orc):
+    """d = 5 * 64 + 7 columns (six chunks), inner_iter = 2, offset wrappers."""
+    g = dense_problem(m=70, n=327, k=9, seed=45)
+    check(orc, g, lrm.ProxGradParams(max_iter=4, inner_iter=2), rtol=1e-6, factors=False)
+    g = dense_problem(m=70, n=50, k=9, seed=46)
+    lrm.add_offset(g)
+    check(orc, g, lrm.ProxGradParams(max_iter=5), rtol=1e-6, factors=False)
+
+
+def test_dense_handle_objective_and_set_obs(orc):
+    """glrmb200_objective on a dense handle; set_obs turns it into a list-mode handle."""
+    g = dense_problem(m=90, n=33, k=6, seed=47)
+    ep = lrm.encode_problem(g)
+    with lrm.Engine(g) as eng:
+        for reg in (True, False):
+            want = orc.objective(ep, g.X, g.Y, include_reg=reg)
+            got = eng.objective(g.X, g.Y, include_regularization=reg)
+            assert abs(got - want) <= 1e-12 * abs(want)
+        A = np.asarray(g.A)
+        ii, jj = np.nonzero(synth.uniform(48, 1, np.arange(90 * 33)).reshape(90, 33) < 0.5)
+        sub = lrm.GLRM(A, lrm.QuadLoss(), lrm.QuadReg(0.1), lrm.QuadReg(0.1), 6, obs=np.stack([ii, jj], axis=1),
+                       X=g.X.copy(), Y=g.Y.copy())
+        eng.set_obs(lrm.encode_problem(sub))
+        X, Y = sub.X.copy(order="F"), sub.Y.copy(order="F")
+        obj, _ = eng.fit(lrm.ProxGradParams(max_iter=5), X, Y)
+        want = run_oracle(orc, sub, lrm.ProxGradParams(max_iter=5))
+        assert_traj_close(obj, want["objective"], TIGHT, "dense handle after set_obs")

@@ -21,14 +21,21 @@ pk = lrm.ProxGradParams(max_iter=10, abs_tol=0, rel_tol=0)
 ref = None
 for v in variants:
     keys = []
+    rank, nranks = 0, 1
+    lrm._abi._lib = lrm._abi.load(lrm._abi.LIB_PATH)          # every variant starts from the default build
     for kv in v.split():
         k_, val = kv.split("=")
         if k_ == "LIB":                      # a differently compiled engine build, loaded side by side
             lrm._abi._lib = lrm._abi.load(os.path.join(ROOT, val))
             continue
+        if k_ == "SHARD":                    # "r/N": time rank r's shard of an N-rank fit on this GPU (no exchange: timing only)
+            rank, nranks = (int(x) for x in val.split("/"))
+            os.environ["GLRMB200_NO_EXCHANGE"] = "1"
+            keys.append("GLRMB200_NO_EXCHANGE")
+            continue
         os.environ[k_] = val
         keys.append(k_)
-    eng = lrm.Engine(ep, validate=False)
+    eng = lrm.Engine(ep, validate=False, rank=rank, nranks=nranks)
     eng.upload(g.X, g.Y)
     eng.fit_resident(pw)
     obj, _ = eng.fit_resident(pk)
