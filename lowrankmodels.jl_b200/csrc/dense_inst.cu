@@ -6,7 +6,9 @@ namespace glrm {
 
 template <class K>
 static cudaError_t set_smem(K kern, size_t smem) {
-  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ce != cudaSuccess) return ce;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 template <int KT, int TG, int TR>
@@ -23,7 +25,7 @@ static cudaError_t launch_x_tile(int loss, const DenseArgs& P, int grid, size_t 
 }
 
 cudaError_t dense_launch_x(int kt, int tg, int tr, int loss, const DenseArgs& P, int grid, cudaStream_t st) {
-  const size_t smem = dense_smem_bytes(P.k, kt);
+  const size_t smem = dense_smem_bytes(P.k, kt, P.nbuf);
 #define T(KT, TG, TR) if (kt == KT && tg == TG && tr == TR) return launch_x_tile<KT, TG, TR>(loss, P, grid, smem, st)
   T(1, 4, 1); T(1, 8, 1); T(2, 8, 2); T(3, 8, 3); T(4, 8, 4); T(5, 16, 3); T(6, 16, 3); T(7, 16, 4);
 #undef T
@@ -44,7 +46,7 @@ static cudaError_t launch_y_mode(int mode, const DenseArgs& P, dim3 grid, size_t
 }
 
 cudaError_t dense_launch_y_pass(int kt, int loss, int mode, const DenseArgs& P, int n_blocks, int max_chunks, cudaStream_t st) {
-  const size_t smem = dense_smem_bytes(P.k, kt);
+  const size_t smem = dense_smem_bytes(P.k, kt, P.nbuf);
   const dim3 grid((unsigned)n_blocks, (unsigned)max_chunks, 1);
 #define T(KT)                                                                                                   \
   if (kt == KT) {                                                                                               \
@@ -56,9 +58,9 @@ cudaError_t dense_launch_y_pass(int kt, int loss, int mode, const DenseArgs& P, 
   return cudaErrorInvalidValue;
 }
 
-cudaError_t dense_launch_reduce(const double* part, int n_blocks, int64_t len, double* out, const int32_t* nactive, cudaStream_t st) {
+cudaError_t dense_launch_reduce(const double* part, int n_blocks, int64_t len, double* out, const int32_t* nactive, const int* stop, cudaStream_t st) {
   if (len <= 0) return cudaSuccess;
-  dense_reduce_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(part, n_blocks, len, out, nactive);
+  dense_reduce_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(part, n_blocks, len, out, nactive, stop);
   return cudaGetLastError();
 }
 
@@ -90,6 +92,6 @@ cudaError_t dense_launch_decide(const DenseYState& Q, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-size_t dense_smem_needed(int k, int kt) { return dense_smem_bytes(k, kt); }
+size_t dense_smem_needed(int k, int kt, int nbuf) { return dense_smem_bytes(k, kt, nbuf); }
 
 }  // namespace glrm

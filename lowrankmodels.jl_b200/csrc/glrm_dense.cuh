@@ -5,19 +5,27 @@
 //     R = dL/dU(U, A)         element-wise (per feature; vector-valued losses see the feature's block of U)
 //     G_X = Y R'              (k x m, inner d)        gradient of every row          (proxgrad.jl:122-132)
 //     G_Y = X R               (k x d, inner m)        gradient of every column block (proxgrad.jl:165-175)
-// These kernels stream A exactly once per pass, straight from the column-major array Julia hands over (no index lists,
-// no transposed copy), and never materialise U, R or a dense G_X: a CTA owns a tile of 64 rows, keeps the tile of X, a
-// chunk of <= 64 columns of Y and the 64 x 64 tile of U / R in shared memory, and runs the two contractions as
-// register-tiled FP64 FMA loops (8 x 4 accumulators per thread).  Float64 throughout: the line search's strict `<`
-// (proxgrad.jl:143,186) needs the same arithmetic as the reference; the roof is the FP64 pipe (36.6 TFLOP/s measured),
-// not tensor cores — B200's FP64 tensor rate equals its FP64 FMA rate, and an error-compensated bf16 split needs
-// >= 28 partial products to carry 53 bits, i.e. less than the FMA pipe delivers directly.
+// These kernels stream A exactly once per pass, straight from the column-major array Julia hands over (device copy with
+// the leading dimension padded to the 64-row tile; no index lists, no transposed copy), and never materialise U, R or a
+// dense G_X.  A CTA owns a tile of 64 rows, keeps the tile of X, a chunk of <= 64 columns of Y and the 64 x 64 tile of
+// U / R in shared memory, and runs the two contractions as register-tiled FP64 FMA loops (8 x 4 accumulators per thread).
+//
+// The 64 x 64 tile of A belonging to a step lands in shared memory through the TMA unit: one 512-byte bulk copy
+// (cp.async.bulk.shared::cluster.global, SASS UBLKCP) per feature column, completion counted on an mbarrier, issued one
+// step ahead of its use (two tile buffers when shared memory allows, else one buffer refilled as soon as the element-wise
+// phase has consumed it) — the loads of A are never on the critical path of the FMA loops.
+//
+// Float64 throughout: the line search's strict `<` (proxgrad.jl:143,186) needs the same arithmetic as the reference; the
+// roof is the FP64 pipe (36.6 TFLOP/s measured), not tensor cores — B200's FP64 tensor rate equals its FP64 FMA rate, and
+// an error-compensated bf16 split needs >= 28 partial products to carry 53 bits, i.e. less than the FMA pipe delivers
+// directly.
 //
 //   dense_x_kernel      the whole X sweep for a tile: gradient pass over all chunks, then the per-row backtracking line
-//                       search (each trial = one more pass over the chunks with the trial points), write-back.
+//                       search.  Rows still searching are compacted to the front of the trial tile after every round and
+//                       dealt round-robin over the thread rows, so a round costs ~ceil(active/16)/4 of a full pass.
 //   dense_y_pass_kernel one pass of the Y sweep for (row block, chunk): partial G_Y and partial per-feature objectives
 //                       (MODE 0), or objectives only for a list of features evaluated at trial blocks (MODE 1).
-//   dense_y_reduce_kernel / dense_y_step_kernel / dense_y_decide_kernel / dense_y_plan_kernel
+//   dense_reduce_kernel / dense_y_begin_kernel / dense_y_step_kernel / dense_y_decide_kernel / dense_y_plan_kernel
 //                       fixed-order reduction over the row blocks, trial blocks prox(y - (alpha/l) g), accept / reject
 //                       per feature (proxgrad.jl:179-200), and the compacted list of features still searching.
 // Rows of a tile and features of a chunk keep fixed positions in every reduction, so results do not depend on the grid.
@@ -29,47 +37,105 @@
 namespace glrm {
 
 struct DenseSmem {
+  double* As;    // [nbuf][DN_TN][DN_TM]  tiles of A, [feature of the chunk][row]  (bulk-copy destination)
   double* Ys;    // [KT*16][DN_YP]
-  double* Xs;    // [k][DN_RP]   current rows of X, [i][r]
-  double* Xn;    // [k][DN_RP]   trial points
-  double* Rs;    // [DN_TN][DN_RP]  U, then R, [column][row]
+  double* Xs;    // [k][DN_RP]   rows of X (gradient pass) / trial points of the rows still searching (line search)
+  double* Rs;    // [DN_TN][DN_RP]  U, then R, [column][row position]
   double* rowv;  // [6][64] per-row scalars
   double* red;   // [4][DN_TN] per-warp partials
+  uint64_t* bar; // [2] mbarriers of the A tile buffers
   int* s_col;    // [DN_TN] global Y column of local column jj (-1: unused)
   int* s_feat;   // [DN_TN] feature of chunk position p
   int* s_foff;   // [DN_TN + 1] first local column of chunk position p
   int* s_state;  // [64]
+  int* s_perm;   // [64] slot -> row of the tile (rows still searching, in row order)
+  int* s_cnt;    // [4]
 };
-__host__ __device__ inline size_t dense_smem_bytes(int k, int kt) {
-  return ((size_t)kt * 16 * DN_YP + 2 * (size_t)k * DN_RP + (size_t)DN_TN * DN_RP + 6 * 64 + 4 * DN_TN) * sizeof(double) +
-         (3 * DN_TN + 1 + 64 + 3) * sizeof(int) + 64;
+__host__ __device__ inline size_t dense_smem_bytes(int k, int kt, int nbuf) {
+  return 128 + (size_t)nbuf * DN_TN * DN_TM * sizeof(double) +
+         ((size_t)kt * 16 * DN_YP + 1 + (size_t)k * DN_RP + (size_t)DN_TN * DN_RP + 6 * 64 + 4 * DN_TN) * sizeof(double) +
+         2 * sizeof(uint64_t) + (3 * DN_TN + 1 + 64 + 64 + 4 + 3) * sizeof(int);
 }
-__device__ __forceinline__ DenseSmem dense_carve(unsigned char* base, int k, int kt) {
+__device__ __forceinline__ DenseSmem dense_carve(unsigned char* base, int k, int kt, int nbuf) {
   DenseSmem S;
+  base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(base) + 127) & ~(uintptr_t)127);
   double* p = reinterpret_cast<double*>(base);
+  S.As = p; p += (size_t)nbuf * DN_TN * DN_TM;
   S.Ys = p; p += (size_t)kt * 16 * DN_YP;
   if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) p += 1;       // 16-byte alignment for the LDS.128 tiles
   S.Xs = p; p += (size_t)k * DN_RP;
-  S.Xn = p; p += (size_t)k * DN_RP;
   S.Rs = p; p += (size_t)DN_TN * DN_RP;
   S.rowv = p; p += 6 * 64;
   S.red = p; p += 4 * DN_TN;
+  S.bar = reinterpret_cast<uint64_t*>(p); p += 2;
   int* q = reinterpret_cast<int*>(p);
   S.s_col = q; q += DN_TN;
   S.s_feat = q; q += DN_TN;
   S.s_foff = q; q += DN_TN + 1;
-  S.s_state = q;
+  S.s_state = q; q += 64;
+  S.s_perm = q; q += 64;
+  S.s_cnt = q;
   return S;
 }
+
+// ---- TMA-fed tiles of A -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t dn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dn_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dn_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void dn_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nDN_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DN_DONE_%=;\nbra DN_WAIT_%=;\nDN_DONE_%=:\n}" ::"r"(dn_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// State of the tile buffers; every thread of the CTA carries the same copy (all control flow around it is CTA-uniform).
+struct APipe {
+  int nbuf;
+  bool pend[2];
+  uint32_t par[2];
+  int64_t held_e0[2];
+  int held_c[2];
+  __device__ __forceinline__ void init(int nb) {
+    nbuf = nb;
+    pend[0] = pend[1] = false; par[0] = par[1] = 0;
+    held_e0[0] = held_e0[1] = -1; held_c[0] = held_c[1] = -1;
+  }
+  __device__ __forceinline__ void wait(const DenseSmem& S, int b) {
+    if (pend[b]) { dn_mbar_wait(S.bar + b, par[b]); par[b] ^= 1u; pend[b] = false; }
+  }
+  // rows [e0, e0 + 64) of the features of chunk c -> buffer b.  The caller guarantees (by a __syncthreads since the last
+  // element-wise phase that read buffer b) that nobody still reads it.  A copy in flight to b is drained first.
+  __device__ __forceinline__ void fetch(const DenseArgs& P, const DenseSmem& S, int b, int64_t e0, int c) {
+    if (held_e0[b] == e0 && held_c[b] == c) return;
+    wait(S, b);
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      const int p0 = P.chunk_ptr[c], nf = P.chunk_ptr[c + 1] - p0;
+      const uint32_t bar = dn_smem_u32(S.bar + b);
+      if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nf * DN_TM * 8) : "memory");
+      __syncwarp();
+      double* dst = S.As + (size_t)b * DN_TN * DN_TM;
+      for (int p = lane; p < nf; p += 32) {
+        const int f = P.feat_list[p0 + p];
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dn_smem_u32(dst + p * DN_TM)), "l"(P.A + (int64_t)f * P.lda + e0), "r"(DN_TM * 8), "r"(bar) : "memory");
+      }
+    }
+    pend[b] = true;
+    held_e0[b] = e0; held_c[b] = c;
+  }
+};
 
 // ---- chunk set-up: feature list, local column map, the chunk of Y ([i][jj], rows >= k zero) ------------------------------
 template <int KT>
 __device__ __forceinline__ int dense_load_chunk(const DenseArgs& P, const DenseSmem& S, int c) {
   const int t = threadIdx.x;
   const int p0 = P.chunk_ptr[c], nf = P.chunk_ptr[c + 1] - p0;
+  __syncthreads();                                   // the previous chunk's readers of Ys / s_* are done
   for (int jj = t; jj < DN_TN; jj += DN_THREADS) S.s_col[jj] = -1;
   __syncthreads();
-  int ncols = 0;
   for (int p = t; p < nf; p += DN_THREADS) {
     const int f = P.feat_list[p0 + p], off = P.feat_off[p0 + p];
     const int64_t y0 = P.ystart[f];
@@ -80,7 +146,6 @@ __device__ __forceinline__ int dense_load_chunk(const DenseArgs& P, const DenseS
     for (int cc = 0; cc < D; ++cc) S.s_col[off + cc] = (int)(y0 + cc);
   }
   __syncthreads();
-  ncols = S.s_foff[nf];
   // Y chunk: lanes run over i (coalesced in global memory), one column per iteration
   for (int idx = t; idx < KT * 16 * DN_TN; idx += DN_THREADS) {
     const int jj = idx / (KT * 16), i = idx - jj * (KT * 16);
@@ -88,66 +153,76 @@ __device__ __forceinline__ int dense_load_chunk(const DenseArgs& P, const DenseS
     S.Ys[i * DN_YP + jj] = (col >= 0 && i < P.k) ? P.Ymat[(int64_t)col * P.stride + i] : 0.0;
   }
   __syncthreads();
-  return ncols;
+  return S.s_foff[nf];
 }
 
-// tile of X -> Xs[i][r] (zero rows past the end)
+// tile of X -> Xs[i][r] (zero rows past the end): a warp per row, lanes over i (coalesced), no integer division
 __device__ __forceinline__ void dense_load_x(const DenseArgs& P, double* Xs, int64_t e0, int nrows) {
-  const int k = P.k;
-  for (int idx = threadIdx.x; idx < DN_TM * k; idx += DN_THREADS) {
-    const int r = idx / k, i = idx - r * k;
-    Xs[i * DN_RP + r] = r < nrows ? P.X[(e0 + r) * P.stride + i] : 0.0;
+  const int k = P.k, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 4
+  for (int r = warp; r < DN_TM; r += DN_THREADS / 32) {
+    const double* src = P.X + (e0 + r) * P.stride;
+    for (int i = lane; i < k; i += 32) Xs[i * DN_RP + r] = r < nrows ? src[i] : 0.0;
   }
 }
 
-// U[r][jj] = sum_i Xt[i][r] * Ys[i][jj]; thread (trow = t/16, tcol = t%16) owns rows trow*8..+7, columns tcol + 16 q.
-// The result goes to Rs[jj][r] (4 conflict-free 16-byte stores per column).
+// U[r][jj] = sum_i Xt[i][r] * Ys[i][jj]; thread (trow = t/16, tcol = t%16) owns row positions trow*8 .. trow*8+NR-1,
+// columns tcol + 16 q.  The result goes to Rs[jj][r] (conflict-free 16-byte stores per column).  NR < 8 is the line
+// search with few rows left: slot s sits at position (s % 8) * 8 + s / 8, so the first 8 NR slots are the first NR
+// positions of every thread row.
+template <int NR>
 __device__ __forceinline__ void dense_gemm_u(const double* __restrict__ Xt, const double* __restrict__ Ys, double* __restrict__ Rs, int k) {
   const int t = threadIdx.x, trow = t >> 4, tcol = t & 15;
-  double acc[8][DN_CT];
+  double acc[NR][DN_CT];
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+  for (int a = 0; a < NR; ++a)
 #pragma unroll
     for (int b = 0; b < DN_CT; ++b) acc[a][b] = 0.0;
   const double* xp = Xt + trow * 8;
   const double* yp = Ys + tcol;
 #pragma unroll 2
   for (int i = 0; i < k; ++i) {
-    const double2 x01 = *reinterpret_cast<const double2*>(xp + i * DN_RP);
-    const double2 x23 = *reinterpret_cast<const double2*>(xp + i * DN_RP + 2);
-    const double2 x45 = *reinterpret_cast<const double2*>(xp + i * DN_RP + 4);
-    const double2 x67 = *reinterpret_cast<const double2*>(xp + i * DN_RP + 6);
-    const double x[8] = {x01.x, x01.y, x23.x, x23.y, x45.x, x45.y, x67.x, x67.y};
+    double x[NR];
+#pragma unroll
+    for (int a = 0; a < NR; a += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(xp + i * DN_RP + a);
+      x[a] = v.x; x[a + 1] = v.y;
+    }
     double y[DN_CT];
 #pragma unroll
     for (int b = 0; b < DN_CT; ++b) y[b] = yp[i * DN_YP + 16 * b];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < NR; ++a)
 #pragma unroll
       for (int b = 0; b < DN_CT; ++b) acc[a][b] = fma(x[a], y[b], acc[a][b]);
   }
 #pragma unroll
   for (int b = 0; b < DN_CT; ++b) {
     double* dst = Rs + (tcol + 16 * b) * DN_RP + trow * 8;
-    *reinterpret_cast<double2*>(dst) = make_double2(acc[0][b], acc[1][b]);
-    *reinterpret_cast<double2*>(dst + 2) = make_double2(acc[2][b], acc[3][b]);
-    *reinterpret_cast<double2*>(dst + 4) = make_double2(acc[4][b], acc[5][b]);
-    *reinterpret_cast<double2*>(dst + 6) = make_double2(acc[6][b], acc[7][b]);
+#pragma unroll
+    for (int a = 0; a < NR; a += 2) *reinterpret_cast<double2*>(dst + a) = make_double2(acc[a][b], acc[a + 1][b]);
   }
 }
+__device__ __forceinline__ void dense_gemm_u_rows(int nr, const double* Xt, const double* Ys, double* Rs, int k) {
+  if (nr <= 2) dense_gemm_u<2>(Xt, Ys, Rs, k);
+  else if (nr <= 4) dense_gemm_u<4>(Xt, Ys, Rs, k);
+  else if (nr <= 6) dense_gemm_u<6>(Xt, Ys, Rs, k);
+  else dense_gemm_u<8>(Xt, Ys, Rs, k);
+}
 
-// Element-wise phase on the U tile in shared memory: thread <-> (row r = t % 64, features p = t/64, t/64 + 2, ...) so the
-// reads of A are coalesced down the column.  GRAD: U is replaced by dL/dU in place.  Returns this thread's share of the
-// row's loss; COLSUM additionally reduces every feature's loss over the 64 rows into red[warp][p] (fixed shuffle tree).
+// Element-wise phase on the U tile in shared memory: thread <-> (row position r = t % 64, features p = t/64, t/64 + 2, ...).
+// `arow` is the tile row whose entries of A this position holds (== r outside the compacted line search), `valid` whether
+// the position carries a real row.  GRAD: U is replaced by dL/dU in place.  Returns this thread's share of the row's loss;
+// COLSUM additionally reduces every feature's loss over the 64 rows into red[warp][p] (fixed shuffle tree).
 template <int LOSS, bool GRAD, bool COLSUM>
-__device__ __forceinline__ double dense_elementwise(const DenseArgs& P, const DenseSmem& S, int nf, int64_t e0, int nrows) {
+__device__ __forceinline__ double dense_elementwise(const DenseArgs& P, const DenseSmem& S, const double* __restrict__ At, int nf,
+                                                    int arow, bool valid) {
   const int t = threadIdx.x, r = t & 63, half = t >> 6, warp = t >> 5;
-  const bool valid = r < nrows;
-  const int64_t e = e0 + (valid ? r : 0);
   double rowsum = 0.0;
+  if (!COLSUM && !GRAD && !valid) return 0.0;               // compacted line search: positions past the active rows idle
   for (int p = half; p < nf; p += 2) {
     const int f = S.s_feat[p], off = S.s_foff[p], D = S.s_foff[p + 1] - off;
-    const double a = P.A[(int64_t)f * P.m + e];
+    const double a = At[p * DN_TM + arow];
     const int code = LOSS ? LOSS : P.loss_code[f];
     const double* lp = P.loss_param + (int64_t)f * GLRMB200_LOSS_NPARAM;
     double l;
@@ -200,30 +275,42 @@ __device__ __forceinline__ void dense_gemm_gx(const double* __restrict__ Ys, con
   }
 }
 
+// slot <-> position of the compacted line search (an involution: swaps the two octal digits)
+__device__ __forceinline__ int dense_slot_pos(int s) { return ((s & 7) << 3) | (s >> 3); }
+
 // ---- X sweep ------------------------------------------------------------------------------------------------------------
-// rowv slots: 0 obj_old, 1 obj_new (trial), 2 reg of the trial point, 3 alpha, 4 recorded objective, 5 partial
+// rowv slots: 0 obj_old, 1 partial sums, 2 reg of the trial point, 3 alpha, 4 recorded objective
 template <int KT, int TG, int TR, int LOSS>
 __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs P) {
-  extern __shared__ __align__(16) unsigned char dn_smem[];
+  extern __shared__ __align__(128) unsigned char dn_smem[];
   if (P.stop != nullptr && *reinterpret_cast<const volatile int*>(P.stop) != 0) return;
-  const DenseSmem S = dense_carve(dn_smem, P.k, KT);
+  const DenseSmem S = dense_carve(dn_smem, P.k, KT, P.nbuf);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int k = P.k;
   const int nchunks = *P.nchunks;
   const int64_t ntiles = (P.row1 - P.row0 + DN_TM - 1) / DN_TM;
   double* Gg = P.gscratch + (int64_t)blockIdx.x * DN_TM * P.stride;
   const double l1 = (double)(P.n + 1);                                   // proxgrad.jl:134: length(observed_features[e]) + 1
-  double* objold = S.rowv, *objnew = S.rowv + 64, *regnew = S.rowv + 128, *alpha = S.rowv + 192, *objrec = S.rowv + 256, *part = S.rowv + 320;
+  double* objold = S.rowv, *part = S.rowv + 64, *regnew = S.rowv + 128, *alpha = S.rowv + 192, *objrec = S.rowv + 256;
   int chunk_loaded = -1;
   constexpr int NGW = 32 / TG;
   const int lg = lane % TG, gq = lane / TG;
+  if (t == 0) { dn_mbar_init(S.bar, 1); dn_mbar_init(S.bar + 1, 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  APipe ap;
+  ap.init(P.nbuf);
+  unsigned stepno = 0;
+  // buffer of a step: with one or two chunks the tiles of A stay put for the whole tile (no refetch in the line search)
+  auto bufof = [&](int c) { return ap.nbuf == 1 ? 0 : (nchunks <= 2 ? c : (int)(stepno & 1u)); };
+  auto bufnext = [&](int c) { return ap.nbuf == 1 ? 0 : (nchunks <= 2 ? c : (int)((stepno + 1u) & 1u)); };
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t e0 = P.row0 + tile * DN_TM;
     const int nrows = (int)((P.row1 - e0) < DN_TM ? (P.row1 - e0) : DN_TM);
-    __syncthreads();
+    __syncthreads();                                   // everybody is done with the previous tile's shared memory
+    ap.fetch(P, S, bufof(0), e0, 0);
     dense_load_x(P, S.Xs, e0, nrows);
-    dense_load_x(P, S.Xn, e0, nrows);              // rows that are not searching keep a finite point in the trial tile
     double G[KT][8];
 #pragma unroll
     for (int q = 0; q < KT; ++q)
@@ -232,15 +319,22 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
     double rowsum = 0.0;
     // ---- gradient pass (proxgrad.jl:119-135) ----
     for (int c = 0; c < nchunks; ++c) {
+      const int b = bufof(c);
       int ncols;
       if (chunk_loaded != c) { ncols = dense_load_chunk<KT>(P, S, c); chunk_loaded = c; }
       else { __syncthreads(); ncols = S.s_foff[P.chunk_ptr[c + 1] - P.chunk_ptr[c]]; }
       const int nf = P.chunk_ptr[c + 1] - P.chunk_ptr[c];
-      dense_gemm_u(S.Xs, S.Ys, S.Rs, k);
+      ap.fetch(P, S, b, e0, c);                        // normally a no-op: issued one step ahead
+      dense_gemm_u<8>(S.Xs, S.Ys, S.Rs, k);
       __syncthreads();
-      rowsum += dense_elementwise<LOSS, true, false>(P, S, nf, e0, nrows);
+      const int cn = c + 1 < nchunks ? c + 1 : 0;      // next step: the next chunk, or chunk 0 again (first trial round)
+      if (ap.nbuf == 2) ap.fetch(P, S, bufnext(cn), e0, cn);
+      ap.wait(S, b);
+      rowsum += dense_elementwise<LOSS, true, false>(P, S, S.As + (size_t)b * DN_TN * DN_TM, nf, t & 63, (t & 63) < nrows);
       __syncthreads();
+      if (ap.nbuf == 1) ap.fetch(P, S, 0, e0, cn);
       dense_gemm_gx<KT>(S.Ys, S.Rs, ncols, G);
+      ++stepno;
     }
     // gradient -> scratch [r][i] (read back lane-group-wise when trial points are formed)
     {
@@ -281,16 +375,26 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
       }
     }
     __syncthreads();
+    // rows that search, in row order
+    int na;
+    {
+      const bool act = t < 64 && S.s_state[t] == 0;
+      const unsigned bal = __ballot_sync(FULLMASK, act);
+      if (lane == 0) S.s_cnt[warp] = __popc(bal);
+      __syncthreads();
+      if (act) S.s_perm[(warp ? S.s_cnt[0] : 0) + __popc(bal & ((1u << lane) - 1u))] = t;
+      na = S.s_cnt[0] + S.s_cnt[1];
+      __syncthreads();
+    }
     int ntrials = 0;
     // ---- line search (proxgrad.jl:136-155): all searching rows of the tile try their step together ----
-    while (true) {
-      const int any = __syncthreads_or(t < 64 && S.s_state[t] == 0);
-      if (!any) break;
-      for (int step = 0; step < 16 / NGW; ++step) {
-        // every lane group runs the step (the shuffles inside reg_prox / reg_eval are warp-wide); only searching rows store
-        const int r = warp * 16 + step * NGW + gq;
-        const bool searching = S.s_state[r] == 0;
-        const int64_t e = e0 + (r < nrows ? r : 0);
+    while (na > 0) {
+      // trial points x_new = prox(x - (alpha/l) g) of the active slots -> Xs[.][position of the slot]; a lane group per slot
+      for (int base = 0; base < na; base += 4 * NGW) {
+        const int s = base + warp * NGW + gq;
+        const bool ok = s < na;
+        const int r = S.s_perm[ok ? s : 0];
+        const int64_t e = e0 + r;
         const int rcode = P.reg_code[P.reg_uniform ? 0 : e];
         const double* rp = P.reg_param + (P.reg_uniform ? 0 : e) * GLRMB200_REG_NPARAM;
         const double stepsize = alpha[r] / l1;                            // :137
@@ -298,55 +402,78 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
 #pragma unroll
         for (int rr = 0; rr < TR; ++rr) {
           const int i0 = 2 * (lg + TG * rr);
-          const double x0 = i0 < k ? S.Xs[i0 * DN_RP + r] : 0.0, x1 = i0 + 1 < k ? S.Xs[(i0 + 1) * DN_RP + r] : 0.0;
+          const double2 x0 = *reinterpret_cast<const double2*>(P.X + e * P.stride + i0);      // padding past k is zero
           const double2 g = *reinterpret_cast<const double2*>(Gg + (int64_t)r * P.stride + i0);
-          xn[rr].x = fma(-stepsize, g.x, x0); xn[rr].y = fma(-stepsize, g.y, x1);          // :140
+          xn[rr].x = fma(-stepsize, g.x, x0.x); xn[rr].y = fma(-stepsize, g.y, x0.y);          // :140
         }
         reg_prox<TG, TR>(rcode, rp, xn, lg, k, stepsize);                  // :142
         const double rv = reg_eval<TG, TR>(rcode, rp, xn, lg, k);
-        if (searching) {
+        if (ok) {
+          const int pos = dense_slot_pos(s);
 #pragma unroll
           for (int rr = 0; rr < TR; ++rr) {
             const int i0 = 2 * (lg + TG * rr);
-            if (i0 < k) S.Xn[i0 * DN_RP + r] = xn[rr].x;
-            if (i0 + 1 < k) S.Xn[(i0 + 1) * DN_RP + r] = xn[rr].y;
+            if (i0 < k) S.Xs[i0 * DN_RP + pos] = xn[rr].x;
+            if (i0 + 1 < k) S.Xs[(i0 + 1) * DN_RP + pos] = xn[rr].y;
           }
           if (lg == 0) regnew[r] = rv;
         }
       }
       __syncthreads();
+      const int myslot = dense_slot_pos(t & 63);                           // the slot whose position this thread serves
+      const bool mine = myslot < na;
+      const int myrow = S.s_perm[mine ? myslot : 0];
+      const int nr = (na + 7) >> 3;                                        // row positions per thread row that are in use
       double trialsum = 0.0;
       for (int c = 0; c < nchunks; ++c) {
+        const int b = bufof(c);
         if (chunk_loaded != c) { dense_load_chunk<KT>(P, S, c); chunk_loaded = c; }
         const int nf = P.chunk_ptr[c + 1] - P.chunk_ptr[c];
-        dense_gemm_u(S.Xn, S.Ys, S.Rs, k);
+        ap.fetch(P, S, b, e0, c);
+        dense_gemm_u_rows(nr, S.Xs, S.Ys, S.Rs, k);
         __syncthreads();
-        trialsum += dense_elementwise<LOSS, false, false>(P, S, nf, e0, nrows);
+        const int cn = c + 1 < nchunks ? c + 1 : 0;
+        if (ap.nbuf == 2) ap.fetch(P, S, bufnext(cn), e0, cn);
+        ap.wait(S, b);
+        trialsum += dense_elementwise<LOSS, false, false>(P, S, S.As + (size_t)b * DN_TN * DN_TM, nf, myrow, mine);
         __syncthreads();
+        if (ap.nbuf == 1) ap.fetch(P, S, 0, e0, cn);
+        ++stepno;
       }
       if (t >= 64) part[t - 64] = trialsum;
       __syncthreads();
-      if (t < 64 && S.s_state[t] == 0) {
-        const double on = (trialsum + part[t]) + regnew[t];
-        objnew[t] = on;
+      if (t < 64 && mine) {
+        const double on = (trialsum + part[t]) + regnew[myrow];
         ++ntrials;
-        if (on < objold[t]) {                                              // :143 (strict; NaN rejects)
-          S.s_state[t] = 2;                                                // accepted: written back below
-          alpha[t] *= 1.05;                                                // :145
-          objrec[t] = on;
+        if (on < objold[myrow]) {                                          // :143 (strict; NaN rejects)
+          S.s_state[myrow] = 2;                                            // accepted: written back below
+          alpha[myrow] *= 1.05;                                            // :145
+          objrec[myrow] = on;
         } else {
-          alpha[t] *= .7;                                                  // :149
-          if (alpha[t] < P.min_stepsize) { alpha[t] = P.min_stepsize * 1.1; S.s_state[t] = 1; }   // :150-153
+          alpha[myrow] *= .7;                                              // :149
+          if (alpha[myrow] < P.min_stepsize) { alpha[myrow] = P.min_stepsize * 1.1; S.s_state[myrow] = 1; }   // :150-153
         }
       }
       __syncthreads();
       // accepted rows: the trial point becomes the row of X (:144)
-      for (int idx = t; idx < DN_TM * k; idx += DN_THREADS) {
-        const int r = idx / k, i = idx - r * k;
-        if (S.s_state[r] == 2) P.X[(e0 + r) * P.stride + i] = S.Xn[i * DN_RP + r];
+      for (int idx = t; idx < na * k; idx += DN_THREADS) {
+        const int s = idx / k, i = idx - s * k;
+        const int r = S.s_perm[s];
+        if (S.s_state[r] == 2) P.X[(e0 + r) * P.stride + i] = S.Xs[i * DN_RP + dense_slot_pos(s)];
       }
-      __syncthreads();
-      if (t < 64 && S.s_state[t] == 2) S.s_state[t] = 1;
+      // compact the rows still searching (order kept)
+      {
+        const int r = (t < 64 && t < na) ? S.s_perm[t] : -1;
+        const bool act = r >= 0 && S.s_state[r] == 0;
+        const unsigned bal = __ballot_sync(FULLMASK, act);
+        __syncthreads();                                                   // every read of the old s_perm is done
+        if (lane == 0) S.s_cnt[warp] = __popc(bal);
+        if (r >= 0 && S.s_state[r] == 2) S.s_state[r] = 1;
+        __syncthreads();
+        if (act) S.s_perm[(warp ? S.s_cnt[0] : 0) + __popc(bal & ((1u << lane) - 1u))] = r;
+        na = S.s_cnt[0] + S.s_cnt[1];
+        __syncthreads();
+      }
     }
     if (t < 64 && t < nrows) {
       if (!(P.flags & FLAG_EVAL_ONLY)) P.alpha[e0 + t] = alpha[t];
@@ -354,6 +481,8 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
     }
     if (ntrials && P.trial_counter) atomicAdd(P.trial_counter, (unsigned long long)ntrials);
   }
+  ap.wait(S, 0);                                       // no bulk copy may be in flight when the CTA exits
+  ap.wait(S, 1);
 }
 
 // ---- Y sweep: one pass for (row block, chunk) ------------------------------------------------------------------------------
@@ -361,16 +490,22 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
 // MODE 1: losses only (trial blocks / objective evaluation).
 template <int KT, int LOSS, int MODE>
 __global__ void __launch_bounds__(DN_THREADS, 1) dense_y_pass_kernel(const DenseArgs P) {
-  extern __shared__ __align__(16) unsigned char dn_smem[];
+  extern __shared__ __align__(128) unsigned char dn_smem[];
   if (P.stop != nullptr && *reinterpret_cast<const volatile int*>(P.stop) != 0) return;
   const int c = blockIdx.y;
   if (c >= *P.nchunks) return;
-  const DenseSmem S = dense_carve(dn_smem, P.k, KT);
+  const DenseSmem S = dense_carve(dn_smem, P.k, KT, P.nbuf);
   const int t = threadIdx.x;
   const int k = P.k;
   const int b = blockIdx.x;
   const int64_t rb0 = P.row0 + (int64_t)b * P.rows_per_block;
   const int64_t rb1 = (rb0 + P.rows_per_block) < P.row1 ? (rb0 + P.rows_per_block) : P.row1;
+  if (t == 0) { dn_mbar_init(S.bar, 1); dn_mbar_init(S.bar + 1, 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  APipe ap;
+  ap.init(P.nbuf);
+  if (rb0 < rb1) ap.fetch(P, S, 0, rb0, c);
   const int ncols = dense_load_chunk<KT>(P, S, c);
   const int nf = P.chunk_ptr[c + 1] - P.chunk_ptr[c];
   // accumulators: thread (ti = t%16, tj = t/16) owns i = ti + 16 q, columns tj + 8 b2
@@ -384,15 +519,20 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_y_pass_kernel(const Dense
   }
   double* colacc = S.rowv;                 // [DN_TN] running per-feature sums (first 64 slots of rowv are enough: nf <= 64)
   if (t < DN_TN) colacc[t] = 0.0;
-  for (int64_t e0 = rb0; e0 < rb1; e0 += DN_TM) {
+  int j = 0;
+  for (int64_t e0 = rb0; e0 < rb1; e0 += DN_TM, ++j) {
     const int nrows = (int)((rb1 - e0) < DN_TM ? (rb1 - e0) : DN_TM);
-    __syncthreads();
+    const int buf = ap.nbuf == 2 ? (j & 1) : 0;
+    __syncthreads();                       // the previous tile's readers of Xs / Rs / the other A buffer are done
     dense_load_x(P, S.Xs, e0, nrows);
+    if (ap.nbuf == 2 && e0 + DN_TM < rb1) ap.fetch(P, S, buf ^ 1, e0 + DN_TM, c);
     __syncthreads();
-    dense_gemm_u(S.Xs, S.Ys, S.Rs, k);
+    dense_gemm_u<8>(S.Xs, S.Ys, S.Rs, k);
     __syncthreads();
-    dense_elementwise<LOSS, MODE == 0, true>(P, S, nf, e0, nrows);
+    ap.wait(S, buf);
+    dense_elementwise<LOSS, MODE == 0, true>(P, S, S.As + (size_t)buf * DN_TN * DN_TM, nf, t & 63, (t & 63) < nrows);
     __syncthreads();
+    if (ap.nbuf == 1 && e0 + DN_TM < rb1) ap.fetch(P, S, 0, e0 + DN_TM, c);
     // per-feature sums of the tile, in a fixed order: rows 0-31 + rows 32-63 (feature p was handled by half p % 2)
     if (t < nf) {
       const int h = t & 1;
@@ -435,13 +575,21 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_y_pass_kernel(const Dense
       }
     }
   }
+  ap.wait(S, 0);
+  ap.wait(S, 1);
 }
 
 // ---- Y sweep: small kernels -----------------------------------------------------------------------------------------------
-// out[x] = sum over row blocks (fixed order) of part[b][x]; `feat_only`: only features of the current plan matter, but
-// summing everything is cheap (n_blocks * n doubles)
+// Iterations are enqueued ahead of the device (glrm_engine.cu): once the stopping rule has fired, every kernel of the
+// iterations still in the queue must leave the model untouched — the small kernels check the same flag as the sweeps.
+__device__ __forceinline__ bool dense_stopped(const int* stop) {
+  return stop != nullptr && *reinterpret_cast<const volatile int*>(stop) != 0;
+}
+
+// out[x] = sum over row blocks (fixed order) of part[b][x]
 __global__ void dense_reduce_kernel(const double* __restrict__ part, int32_t n_blocks, int64_t len, double* __restrict__ out,
-                                    const int32_t* nactive) {
+                                    const int32_t* nactive, const int* stop) {
+  if (dense_stopped(stop)) return;
   if (nactive != nullptr && *nactive == 0) return;
   const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= len) return;
@@ -454,17 +602,19 @@ __global__ void dense_reduce_kernel(const double* __restrict__ part, int32_t n_b
 __global__ void dense_y_plan_kernel(DenseYState Q) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int nact = 0, nch = 0, used = 0;
-  Q.chunk_ptr[0] = 0;
-  for (int64_t f = 0; f < Q.n; ++f) {
-    if (!Q.active[f]) continue;
-    const int D = (int)(Q.ystart[f + 1] - Q.ystart[f]);
-    if (used + D > DN_TN) { ++nch; Q.chunk_ptr[nch] = nact; used = 0; }
-    Q.feat_list[nact] = (int32_t)f;
-    Q.feat_off[nact] = used;
-    used += D;
-    ++nact;
+  if (!dense_stopped(Q.stop)) {
+    Q.chunk_ptr[0] = 0;
+    for (int64_t f = 0; f < Q.n; ++f) {
+      if (!Q.active[f]) continue;
+      const int D = (int)(Q.ystart[f + 1] - Q.ystart[f]);
+      if (used + D > DN_TN) { ++nch; Q.chunk_ptr[nch] = nact; used = 0; }
+      Q.feat_list[nact] = (int32_t)f;
+      Q.feat_off[nact] = used;
+      used += D;
+      ++nact;
+    }
+    if (nact > 0) { ++nch; Q.chunk_ptr[nch] = nact; }
   }
-  if (nact > 0) { ++nch; Q.chunk_ptr[nch] = nact; }
   *Q.nchunks = nch;
   *Q.nactive = nact;
   Q.h_nactive[0] = nact;               // the host stops enqueuing line-search rounds once it reads (0, this sweep's number)
@@ -476,6 +626,7 @@ __global__ void dense_y_plan_kernel(DenseYState Q) {
 // after the gradient pass: obj_old = loss + ry(y_f), search state (proxgrad.jl:177-179); one lane group per feature column
 template <int TG, int TR>
 __global__ void __launch_bounds__(128) dense_y_begin_kernel(DenseYState Q) {
+  if (dense_stopped(Q.stop)) return;
   const int lane = threadIdx.x & 31, lg = lane % TG;
   const int64_t f = ((int64_t)blockIdx.x * 4 + (threadIdx.x >> 5)) * (32 / TG) + lane / TG;
   const bool ok = f < Q.n;
@@ -511,7 +662,7 @@ __global__ void __launch_bounds__(128) dense_y_step_kernel(DenseYState Q) {
   const int nact = *Q.nactive;
   const int lane = threadIdx.x & 31, lg = lane % TG;
   const int64_t p = ((int64_t)blockIdx.x * 4 + (threadIdx.x >> 5)) * (32 / TG) + lane / TG;
-  if (nact == 0) return;
+  if (nact == 0 || dense_stopped(Q.stop)) return;
   const bool ok = p < nact;
   const int64_t f = Q.feat_list[ok ? p : 0];
   const int rcode = Q.reg_code[Q.reg_uniform ? 0 : f];
@@ -547,6 +698,7 @@ __global__ void __launch_bounds__(128) dense_y_step_kernel(DenseYState Q) {
 
 // accept / reject per feature (proxgrad.jl:186-199)
 __global__ void dense_y_decide_kernel(DenseYState Q) {
+  if (dense_stopped(Q.stop)) return;
   const int nact = *Q.nactive;
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nact) return;

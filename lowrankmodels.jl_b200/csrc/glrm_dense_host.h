@@ -14,8 +14,9 @@ constexpr int DN_YP = DN_TN + 1;     // pitch of the Y chunk [i][column]: column
 constexpr int DN_CT = DN_TN / 16;    // columns per thread in the U contraction
 
 struct DenseArgs {
-  const double* A;            // column-major m x n, as Julia stores it
-  int64_t m, n;
+  const double* A;            // column-major m x n as Julia stores it, leading dimension lda (multiple of 64, zero rows past m)
+  int64_t m, n, lda;
+  int32_t nbuf;               // tile buffers of A in shared memory (1 or 2)
   int64_t row0, row1;         // rows this launch covers
   double* X;                  // k x m factor (device layout: `stride` doubles per column)
   const double* Ymat;         // k x d matrix the pass contracts with (Y, or the trial blocks Ynew)
@@ -64,11 +65,11 @@ struct DenseYState {
 
 cudaError_t dense_launch_x(int kt, int tg, int tr, int loss, const DenseArgs& P, int grid, cudaStream_t st);
 cudaError_t dense_launch_y_pass(int kt, int loss, int mode, const DenseArgs& P, int n_blocks, int max_chunks, cudaStream_t st);
-cudaError_t dense_launch_reduce(const double* part, int n_blocks, int64_t len, double* out, const int32_t* nactive, cudaStream_t st);
+cudaError_t dense_launch_reduce(const double* part, int n_blocks, int64_t len, double* out, const int32_t* nactive, const int* stop, cudaStream_t st);
 cudaError_t dense_launch_plan(const DenseYState& Q, cudaStream_t st);
 cudaError_t dense_launch_begin(int tg, int tr, const DenseYState& Q, cudaStream_t st);
 cudaError_t dense_launch_step(int tg, int tr, const DenseYState& Q, cudaStream_t st);
 cudaError_t dense_launch_decide(const DenseYState& Q, cudaStream_t st);
-size_t dense_smem_needed(int k, int kt);
+size_t dense_smem_needed(int k, int kt, int nbuf);
 
 }  // namespace glrm

@@ -6,6 +6,7 @@
 // src/evaluate_fit.jl:57-83.  No CPU compute path exists here: without a CUDA device every entry
 // point fails with GLRMB200_E_NO_DEVICE.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -114,6 +115,9 @@ struct DenseHost {
   bool on = false;
   int kt = 0;
   int sms = 148;
+  int nbuf = 2;                             // tile buffers of A in shared memory
+  int ctas_per_sm = 1;
+  int64_t lda = 0;                          // leading dimension of the device copy of A (multiple of the 64-row tile)
   double* d_A = nullptr;
   int32_t *d_chunk_ptr = nullptr, *d_feat_list = nullptr, *d_feat_off = nullptr, *d_nchunks = nullptr;
   int32_t *d_chunk_ptr2 = nullptr, *d_feat_list2 = nullptr, *d_feat_off2 = nullptr, *d_nchunks2 = nullptr;
@@ -459,7 +463,28 @@ static int dense_setup(glrmb200_engine* E, const glrmb200_problem* P) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, E->device);
   D.sms = sms;
-  if ((rc = upload(&D.d_A, P->dense_A, (size_t)(m * n), E->stream))) return rc;
+  // A as Julia stores it (column-major), columns padded to whole 64-row tiles: every tile column is one aligned
+  // 512-byte bulk copy, and the rows past m read as zero
+  D.lda = (m + DN_TM - 1) / DN_TM * DN_TM;
+  if ((rc = dalloc(&D.d_A, (size_t)(D.lda * n), E->stream))) return rc;
+  if (D.lda == m) {
+    CUDA_OK(cudaMemcpyAsync(D.d_A, P->dense_A, (size_t)(m * n) * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+  } else {
+    CUDA_OK(cudaMemsetAsync(D.d_A, 0, (size_t)(D.lda * n) * sizeof(double), E->stream));
+    CUDA_OK(cudaMemcpy2DAsync(D.d_A, (size_t)D.lda * sizeof(double), P->dense_A, (size_t)m * sizeof(double), (size_t)m * sizeof(double),
+                              (size_t)n, cudaMemcpyHostToDevice, E->stream));
+  }
+  // shared memory: two tile buffers of A when a CTA fills the SM anyway, one when that lets two CTAs share the SM
+  {
+    const size_t cap = 227 * 1024;
+    const size_t s1 = dense_smem_needed((int)E->k, D.kt, 1) + 1024, s2 = dense_smem_needed((int)E->k, D.kt, 2) + 1024;
+    if (s1 > cap) return fail(GLRMB200_E_UNSUPPORTED, "dense path: k = %lld needs too much shared memory", (long long)E->k);
+    if (2 * s2 <= cap) { D.nbuf = 2; D.ctas_per_sm = 2; }
+    else if (2 * s1 <= cap) { D.nbuf = 1; D.ctas_per_sm = 2; }
+    else if (s2 <= cap) { D.nbuf = 2; D.ctas_per_sm = 1; }
+    else { D.nbuf = 1; D.ctas_per_sm = 1; }
+    if (const char* t = getenv("GLRMB200_DENSE_NBUF")) { const int v = atoi(t); if (v == 1 || (v == 2 && s2 <= cap)) { D.nbuf = v; D.ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, cap / (v == 1 ? s1 : s2))); } }
+  }
   // static plan: all features in order, chunks of <= DN_TN columns made of whole features
   std::vector<int32_t> chunk_ptr{0}, feat_list, feat_off;
   int used = 0;
@@ -493,8 +518,9 @@ static int dense_setup(glrmb200_engine* E, const glrmb200_problem* P) {
   const int bg = (int)std::min<int64_t>(37, std::max<int64_t>(1, (tiles + 7) / 8));
   D.n_blocks = 8 * bg;
   D.rows_per_block = ((m + D.n_blocks - 1) / D.n_blocks + DN_TM - 1) / DN_TM * DN_TM;
-  D.x_grid = (int)std::min<int64_t>(tiles, sms);
+  D.x_grid = (int)std::min<int64_t>(tiles, (int64_t)sms * D.ctas_per_sm);
   if ((rc = dalloc(&D.d_gscratch, (size_t)D.x_grid * DN_TM * E->stride, E->stream))) return rc;
+  CUDA_OK(cudaMemsetAsync(D.d_gscratch, 0, (size_t)D.x_grid * DN_TM * E->stride * sizeof(double), E->stream));   // lanes past the register tiles stay zero
   if ((rc = dalloc(&D.d_gpart, (size_t)D.n_blocks * (size_t)d * E->stride, E->stream))) return rc;
   if ((rc = dalloc(&D.d_objpart, (size_t)D.n_blocks * (size_t)n, E->stream))) return rc;
   CUDA_OK(cudaMemsetAsync(D.d_objpart, 0, (size_t)D.n_blocks * (size_t)n * sizeof(double), E->stream));
@@ -505,7 +531,6 @@ static int dense_setup(glrmb200_engine* E, const glrmb200_problem* P) {
   if ((rc = dalloc(&D.d_objold, (size_t)n, E->stream))) return rc;
   if ((rc = dalloc(&D.d_regnew, (size_t)n, E->stream))) return rc;
   D.h_nactive = reinterpret_cast<volatile int32_t*>(E->h_pinned + 10);
-  if (dense_smem_needed((int)E->k, D.kt) > 227 * 1024) return fail(GLRMB200_E_UNSUPPORTED, "dense path: k = %lld needs too much shared memory", (long long)E->k);
   D.on = true;
   return 0;
 }
@@ -514,7 +539,7 @@ static DenseArgs dense_args(const glrmb200_engine* E, bool static_plan, const do
   const DenseHost& D = E->dn;
   DenseArgs P;
   memset(&P, 0, sizeof(P));
-  P.A = D.d_A; P.m = E->m; P.n = E->n;
+  P.A = D.d_A; P.m = E->m; P.n = E->n; P.lda = D.lda; P.nbuf = D.nbuf;
   P.row0 = 0; P.row1 = E->m;
   P.X = E->d_X; P.Ymat = Ymat;
   P.stride = E->stride; P.k = (int)E->k; P.kp = E->kp;
@@ -576,38 +601,53 @@ static int dense_eval_cols(glrmb200_engine* E, int flags, double min_stepsize, b
   const int loss = E->loss_template == GLRMB200_LOSS_QUAD ? GLRMB200_LOSS_QUAD : 0;
   DenseArgs P = dense_args(E, true, E->d_Y, flags, min_stepsize, honour_stop);
   DN_OK(dense_launch_y_pass(D.kt, loss, mode, P, D.n_blocks, D.max_chunks, E->stream));
-  if (mode == 0) DN_OK(dense_launch_reduce(D.d_gpart, D.n_blocks, E->d * (int64_t)E->stride, D.d_G, nullptr, E->stream));
-  DN_OK(dense_launch_reduce(D.d_objpart, D.n_blocks, E->n, D.d_colobj, nullptr, E->stream));
+  if (mode == 0) DN_OK(dense_launch_reduce(D.d_gpart, D.n_blocks, E->d * (int64_t)E->stride, D.d_G, nullptr, P.stop, E->stream));
+  DN_OK(dense_launch_reduce(D.d_objpart, D.n_blocks, E->n, D.d_colobj, nullptr, P.stop, E->stream));
   DenseYState Q = dense_ystate(E, flags, min_stepsize, honour_stop);
   DN_OK(dense_launch_begin(E->tile_g, E->tile_r, Q, E->stream));
   *launches += mode == 0 ? 4 : 3;
   return 0;
 }
 
-// the Y sweep (proxgrad.jl:160-203): gradient pass, then line-search rounds over the features still searching.  Rounds are
-// enqueued without waiting; every kernel of a round returns at once when no feature is left, and the host stops enqueuing
-// when the mapped counter says so.
+// the Y sweep (proxgrad.jl:160-203): gradient pass, then line-search rounds over the features still searching.  Every round
+// ends with the plan of the next one (compacted feature list + its size, published to mapped host memory).  The host runs
+// one round ahead of the device: it enqueues round r, then waits for the plan of round r (complete when round r-1 is) and
+// stops if nothing is left — the round it enqueued in vain returns at once.
 static int dense_sweep_y(glrmb200_engine* E, double min_stepsize, bool honour_stop, int64_t* launches) {
   DenseHost& D = E->dn;
   const int loss = E->loss_template == GLRMB200_LOSS_QUAD ? GLRMB200_LOSS_QUAD : 0;
   int rc;
-  ++D.seq;
+  D.seq = (D.seq + 1) & 0x3ffff;
+  auto key = [&](int round) { return (int32_t)((D.seq << 12) | round); };
   if ((rc = dense_eval_cols(E, 0, min_stepsize, honour_stop, 0, launches))) return rc;
   DenseYState Q = dense_ystate(E, 0, min_stepsize, honour_stop);
   DenseArgs P = dense_args(E, false, D.d_Ynew, 0, min_stepsize, honour_stop);
+  Q.seq = key(0);
+  DN_OK(dense_launch_plan(Q, E->stream));
+  ++*launches;
   for (int round = 0;; ++round) {
-    if (round >= 2 && D.h_nactive[1] == D.seq && D.h_nactive[0] == 0) break;
-    if (round > 0 && round % 64 == 0) {                      // far more rounds than any step-size history needs: make sure
-      CUDA_OK(cudaStreamSynchronize(E->stream));
-      if (D.h_nactive[1] == D.seq && D.h_nactive[0] == 0) break;
-      if (round >= 4096) return fail(GLRMB200_E_STATE, "dense Y line search did not terminate");
-    }
-    DN_OK(dense_launch_plan(Q, E->stream));
+    if (round >= 4095) return fail(GLRMB200_E_STATE, "dense Y line search did not terminate");
     DN_OK(dense_launch_step(E->tile_g, E->tile_r, Q, E->stream));
     DN_OK(dense_launch_y_pass(D.kt, loss, 1, P, D.n_blocks, D.max_chunks, E->stream));
-    DN_OK(dense_launch_reduce(D.d_objpart, D.n_blocks, E->n, D.d_colobj, D.d_nactive, E->stream));
+    DN_OK(dense_launch_reduce(D.d_objpart, D.n_blocks, E->n, D.d_colobj, D.d_nactive, P.stop, E->stream));
     DN_OK(dense_launch_decide(Q, E->stream));
+    Q.seq = key(round + 1);
+    DN_OK(dense_launch_plan(Q, E->stream));
     *launches += 5;
+    if (round == 0) continue;
+    // plan(round) or a later one of this sweep has been published?
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int spin = 0;; ++spin) {
+      const int32_t k1 = D.h_nactive[1];
+      if ((k1 >> 12) == D.seq && (k1 & 4095) >= round) break;
+      if ((spin & 1023) == 1023) {
+        if (cudaStreamQuery(E->stream) == cudaSuccess) break;              // everything enqueued has run: the plan is there
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 600.0)
+          return fail(GLRMB200_E_STATE, "dense Y line search: the device did not publish its plan");
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (D.h_nactive[0] == 0) break;
   }
   return 0;
 }
@@ -904,7 +944,7 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
     unsigned long long* d_bad = nullptr;
     if ((rc = dalloc(&d_bad, 1, E->stream))) return rc;
     CUDA_OK(cudaMemsetAsync(d_bad, 0xff, sizeof(unsigned long long), E->stream));
-    validate_dense_kernel<<<(unsigned)((m * n + 255) / 256), 256, 0, E->stream>>>(E->dn.d_A, m * n, m, E->d_loss_code, E->d_loss_param, d_bad);
+    validate_dense_kernel<<<(unsigned)((E->dn.lda * n + 255) / 256), 256, 0, E->stream>>>(E->dn.d_A, E->dn.lda * n, m, E->dn.lda, E->d_loss_code, E->d_loss_param, d_bad);
     CUDA_OK(cudaGetLastError());
     unsigned long long bad = 0;
     CUDA_OK(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
@@ -949,7 +989,7 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
       if ((rc = dalloc(&d_bad, 1, E->stream))) return rc;
       CUDA_OK(cudaMemsetAsync(d_bad, 0xff, sizeof(unsigned long long), E->stream));
       const int64_t total = C.nnz_local;
-      if (total > 0) validate_dense_kernel<<<(unsigned)((total + 255) / 256), 256, 0, E->stream>>>(C.d_val, total, m, E->d_loss_code + C.begin, E->d_loss_param + C.begin * GLRMB200_LOSS_NPARAM, d_bad);
+      if (total > 0) validate_dense_kernel<<<(unsigned)((total + 255) / 256), 256, 0, E->stream>>>(C.d_val, total, m, m, E->d_loss_code + C.begin, E->d_loss_param + C.begin * GLRMB200_LOSS_NPARAM, d_bad);
       CUDA_OK(cudaGetLastError());
       unsigned long long bad = 0;
       CUDA_OK(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));

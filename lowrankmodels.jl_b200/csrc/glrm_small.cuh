@@ -145,14 +145,16 @@ __global__ void validate_cols_kernel(const int64_t* __restrict__ ptr, const int3
   }
 }
 // fully observed: A is column-major m x n, element i belongs to feature i / m
-__global__ void validate_dense_kernel(const double* __restrict__ A, int64_t total, int64_t m,
+__global__ void validate_dense_kernel(const double* __restrict__ A, int64_t total, int64_t m, int64_t lda,
                                       const int32_t* __restrict__ loss_code, const double* __restrict__ loss_param,
                                       unsigned long long* bad) {
+  // `total` = lda * columns positions of a column-major array with leading dimension lda >= m; reports f * m + e
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int64_t f = i / m;
+  const int64_t f = i / lda, e = i - f * lda;
+  if (e >= m) return;
   const int err = label_error(loss_code[f], loss_param + f * GLRMB200_LOSS_NPARAM, A[i]);
-  if (err) report_bad(bad, (unsigned long long)i, err);
+  if (err) report_bad(bad, (unsigned long long)(f * m + e), err);
 }
 
 // dst[c*rows + r] = src[r*cols + c]   (row-major copy of the Julia column-major A for the X sweep)
