@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GLRMB200_VERSION 100          /* major*100 + minor */
+#define GLRMB200_VERSION 101          /* major*100 + minor */
 #define GLRMB200_LOSS_NPARAM 8        /* doubles per loss descriptor */
 #define GLRMB200_REG_NPARAM 4         /* doubles per regularizer descriptor */
 
@@ -97,6 +97,15 @@ enum {
  * wrappers (the offset path, src/modify_glrm.jl:21-24):
  *   LASTENTRY1            regularizers.jl:163-174   last factor entry pinned to 1
  *   LASTENTRY_UNPENALIZED regularizers.jl:178-189   last factor entry skipped by the inner reg
+ *   REM_QUAD        regularizers.jl:412-423   [0]=scale, payload = the mean m (k values)
+ * wrappers with a vector payload (rx_payload / ry_payload below; not combined with the offset wrappers, REM_QUAD or the
+ * block regularizers):
+ *   FIXED_FIRST     regularizers.jl:193-210   fixed_latent_features: the first n entries are pinned to the payload y
+ *                                             (n = payload length), the inner regularizer sees the other k-n;
+ *                                             evaluate = Inf unless a[1:n] == y
+ *   FIXED_LAST      regularizers.jl:214-231   fixed_last_latent_features: the last n entries pinned to y.  Restated
+ *                                             literally: prox = [prox(inner, u[n+1:end]); y] (:223 feeds the LAST k-n
+ *                                             entries to the inner prox, not the first); evaluate uses a[1:k-n] (:230)
  * block regularizers of the ordinal losses (ry only; applied to the whole k x d_f block of a column):
  *   ORDINAL_REG           regularizers.jl:356-380   first k-1 rows: mean over the block's columns, inner prox, copied
  *                                                    back to every column; evaluate = inner reg on a[1:k-1, 1]
@@ -113,11 +122,14 @@ enum {
   GLRMB200_REG_KSPARSE = 7,
   GLRMB200_REG_UNIT_ONE_SPARSE = 8,
   GLRMB200_REG_SIMPLEX = 9,
+  GLRMB200_REG_REM_QUAD = 10,
   GLRMB200_REG_BASE_MASK = 0xff,
   GLRMB200_REG_LASTENTRY1 = 0x100,
   GLRMB200_REG_LASTENTRY_UNPENALIZED = 0x200,
   GLRMB200_REG_ORDINAL = 0x400,
-  GLRMB200_REG_MNL_ORDINAL = 0x800
+  GLRMB200_REG_MNL_ORDINAL = 0x800,
+  GLRMB200_REG_FIXED_FIRST = 0x1000,
+  GLRMB200_REG_FIXED_LAST = 0x2000
 };
 
 /* ---- the problem: what `GLRM(A, losses, rx, ry, k; ...)` holds (src/glrm.jl:12-22) ---------- *
@@ -155,6 +167,14 @@ typedef struct glrmb200_problem {
   const int64_t* col_ptr;    /* [n+1]                                                          */
   const int32_t* col_idx;    /* [nnz_cols] example index e (0-based)                           */
   const double*  col_val;    /* [nnz_cols] A[e,f]                                              */
+
+  /* optional vector payloads of the regularizers (fixed_latent_features.y, fixed_last_latent_features.y,
+   * RemQuadReg.m: src/regularizers.jl:193-231,412-423).  Regularizer i of the side owns
+   * payload[payload_ptr[i] .. payload_ptr[i+1]); NULL pointers = no regularizer carries a payload.    */
+  const int64_t* rx_payload_ptr;  /* [rx_count + 1]                                            */
+  const double*  rx_payload;
+  const int64_t* ry_payload_ptr;  /* [ry_count + 1]                                            */
+  const double*  ry_payload;
 } glrmb200_problem;
 
 /* ---- ProxGradParams (src/algorithms/proxgrad.jl:4-31), same seven fields -------------------- */

@@ -15,7 +15,8 @@ from .params import AbstractParams, B200ProxGradParams, Params, ProxGradParams, 
 from .regularizers import (KSparseConstraint, MNLOrdinalReg, NonNegConstraint, NonNegOneReg, OneReg,
                            OneSparseConstraint, OrdinalReg, QuadConstraint, QuadReg, Regularizer,
                            RemQuadReg, SimplexConstraint, UnitOneSparseConstraint, ZeroReg,
-                           fixed_last_latent_features, fixed_latent_features, lastentry1,
+                           fixed_last_latent_features, fixed_latent_features, FixedLatentFeaturesConstraint,
+                           FixedLastLatentFeaturesConstraint, lastentry1,
                            lastentry_unpenalized)
 from .encode import encode_params, encode_problem, encode_sparse_params
 from . import _abi, distributed, synth

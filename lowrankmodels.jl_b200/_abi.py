@@ -23,6 +23,8 @@ class Problem(C.Structure):
         ("obs_full", C.c_int32), ("dense_A", c_double_p),
         ("row_ptr", c_int64_p), ("row_idx", c_int32_p), ("row_val", c_double_p),
         ("col_ptr", c_int64_p), ("col_idx", c_int32_p), ("col_val", c_double_p),
+        ("rx_payload_ptr", c_int64_p), ("rx_payload", c_double_p),
+        ("ry_payload_ptr", c_int64_p), ("ry_payload", c_double_p),
     ]
 
 

@@ -44,34 +44,36 @@ struct DenseSmem {
   double* rowv;  // [6][64] per-row scalars
   double* red;   // [4][DN_TN] per-warp partials
   uint64_t* bar; // [2] mbarriers of the A tile buffers
-  int* s_col;    // [DN_TN] global Y column of local column jj (-1: unused)
-  int* s_feat;   // [DN_TN] feature of chunk position p
-  int* s_foff;   // [DN_TN + 1] first local column of chunk position p
+  int* s_col;    // [2][DN_TN] global Y column of local column jj (-1: unused); two slots: the next chunk's map is built
+  int* s_feat;   // [2][DN_TN] feature of chunk position p                      while the current one is still in use
+  int* s_foff;   // [2][DN_TN + 2] first local column of chunk position p
   int* s_state;  // [64]
   int* s_perm;   // [64] slot -> row of the tile (rows still searching, in row order)
   int* s_cnt;    // [4]
 };
+// every region starts on a 16-byte boundary (sizes below are multiples of 16 bytes)
+__host__ __device__ inline size_t dense_ys_doubles(int kt) { return ((size_t)kt * 16 * DN_YP + 1) & ~(size_t)1; }
 __host__ __device__ inline size_t dense_smem_bytes(int k, int kt, int nbuf) {
-  return 128 + (size_t)nbuf * DN_TN * DN_TM * sizeof(double) +
-         ((size_t)kt * 16 * DN_YP + 1 + (size_t)k * DN_RP + (size_t)DN_TN * DN_RP + 6 * 64 + 4 * DN_TN) * sizeof(double) +
-         2 * sizeof(uint64_t) + (3 * DN_TN + 1 + 64 + 64 + 4 + 3) * sizeof(int);
+  return (size_t)nbuf * DN_TN * DN_TM * sizeof(double) +
+         (dense_ys_doubles(kt) + (size_t)k * DN_RP + (size_t)DN_TN * DN_RP + 6 * 64 + 4 * DN_TN) * sizeof(double) +
+         2 * sizeof(uint64_t) + (2 * DN_TN + 2 * DN_TN + 2 * (DN_TN + 2) + 64 + 64 + 4) * sizeof(int);
 }
+// `base` must be the extern __shared__ array itself: plain pointer arithmetic on it keeps the address space known to the
+// compiler (LDS / STS instead of generic loads)
 __device__ __forceinline__ DenseSmem dense_carve(unsigned char* base, int k, int kt, int nbuf) {
   DenseSmem S;
-  base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(base) + 127) & ~(uintptr_t)127);
   double* p = reinterpret_cast<double*>(base);
   S.As = p; p += (size_t)nbuf * DN_TN * DN_TM;
-  S.Ys = p; p += (size_t)kt * 16 * DN_YP;
-  if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) p += 1;       // 16-byte alignment for the LDS.128 tiles
+  S.Ys = p; p += dense_ys_doubles(kt);
   S.Xs = p; p += (size_t)k * DN_RP;
   S.Rs = p; p += (size_t)DN_TN * DN_RP;
   S.rowv = p; p += 6 * 64;
   S.red = p; p += 4 * DN_TN;
   S.bar = reinterpret_cast<uint64_t*>(p); p += 2;
   int* q = reinterpret_cast<int*>(p);
-  S.s_col = q; q += DN_TN;
-  S.s_feat = q; q += DN_TN;
-  S.s_foff = q; q += DN_TN + 1;
+  S.s_col = q; q += 2 * DN_TN;
+  S.s_feat = q; q += 2 * DN_TN;
+  S.s_foff = q; q += 2 * (DN_TN + 2);
   S.s_state = q; q += 64;
   S.s_perm = q; q += 64;
   S.s_cnt = q;
@@ -128,42 +130,60 @@ struct APipe {
   }
 };
 
-// ---- chunk set-up: feature list, local column map, the chunk of Y ([i][jj], rows >= k zero) ------------------------------
+// ---- asynchronous staging of the factor tiles ------------------------------------------------------------------------------
+// Both tiles are stored transposed ([factor index][column / row]) so the FMA loops read them conflict-free; an 8-byte
+// cp.async (LDGSTS) per element does the transposition on the way in, with all copies of a tile in flight at once.
+// src_bytes = 0 zero-fills the destination (rows past the end, factor rows past k).
+__device__ __forceinline__ void dn_cp_async8(double* dst, const double* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dn_smem_u32(dst)), "l"(src), "r"(valid ? 8 : 0) : "memory");
+}
+__device__ __forceinline__ void dn_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// every copy this thread issued has landed, and (barrier) so has everybody else's
+__device__ __forceinline__ void dn_async_wait() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+}
+
+// chunk set-up into meta slot `ms`: feature list, local column map; then the chunk of Y ([i][jj], rows >= k zero) is put in
+// flight.  The caller guarantees that nobody reads Ys or meta slot `ms` any more, and calls dn_async_wait before using Ys.
 template <int KT>
-__device__ __forceinline__ int dense_load_chunk(const DenseArgs& P, const DenseSmem& S, int c) {
-  const int t = threadIdx.x;
+__device__ __forceinline__ void dense_chunk_begin(const DenseArgs& P, const DenseSmem& S, int c, int ms) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int p0 = P.chunk_ptr[c], nf = P.chunk_ptr[c + 1] - p0;
-  __syncthreads();                                   // the previous chunk's readers of Ys / s_* are done
-  for (int jj = t; jj < DN_TN; jj += DN_THREADS) S.s_col[jj] = -1;
+  int* s_col = S.s_col + ms * DN_TN;
+  int* s_feat = S.s_feat + ms * DN_TN;
+  int* s_foff = S.s_foff + ms * (DN_TN + 2);
+  for (int jj = t; jj < DN_TN; jj += DN_THREADS) s_col[jj] = -1;
   __syncthreads();
   for (int p = t; p < nf; p += DN_THREADS) {
     const int f = P.feat_list[p0 + p], off = P.feat_off[p0 + p];
     const int64_t y0 = P.ystart[f];
     const int D = (int)(P.ystart[f + 1] - y0);
-    S.s_feat[p] = f;
-    S.s_foff[p] = off;
-    if (p == nf - 1) S.s_foff[nf] = off + D;
-    for (int cc = 0; cc < D; ++cc) S.s_col[off + cc] = (int)(y0 + cc);
+    s_feat[p] = f;
+    s_foff[p] = off;
+    if (p == nf - 1) s_foff[nf] = off + D;
+    for (int cc = 0; cc < D; ++cc) s_col[off + cc] = (int)(y0 + cc);
   }
+  if (nf == 0 && t == 0) s_foff[0] = 0;
   __syncthreads();
-  // Y chunk: lanes run over i (coalesced in global memory), one column per iteration
-  for (int idx = t; idx < KT * 16 * DN_TN; idx += DN_THREADS) {
-    const int jj = idx / (KT * 16), i = idx - jj * (KT * 16);
-    const int col = S.s_col[jj];
-    S.Ys[i * DN_YP + jj] = (col >= 0 && i < P.k) ? P.Ymat[(int64_t)col * P.stride + i] : 0.0;
+  // a warp per column, lanes over i: 256-byte coalesced reads, conflict-free transposed writes (pitch 65)
+  for (int jj = warp; jj < DN_TN; jj += DN_THREADS / 32) {
+    const int col = s_col[jj];
+    const double* src = P.Ymat + (int64_t)(col >= 0 ? col : 0) * P.stride;
+#pragma unroll
+    for (int i = lane; i < KT * 16; i += 32) dn_cp_async8(S.Ys + i * DN_YP + jj, src + (i < P.k ? i : 0), col >= 0 && i < P.k);
   }
-  __syncthreads();
-  return S.s_foff[nf];
+  dn_async_commit();
 }
 
-// tile of X -> Xs[i][r] (zero rows past the end): a warp per row, lanes over i (coalesced), no integer division
-__device__ __forceinline__ void dense_load_x(const DenseArgs& P, double* Xs, int64_t e0, int nrows) {
+// tile of X -> Xs[i][r] (zero rows past the end): a warp per row, lanes over i (coalesced)
+__device__ __forceinline__ void dense_x_begin(const DenseArgs& P, double* Xs, int64_t e0, int nrows) {
   const int k = P.k, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll 4
   for (int r = warp; r < DN_TM; r += DN_THREADS / 32) {
-    const double* src = P.X + (e0 + r) * P.stride;
-    for (int i = lane; i < k; i += 32) Xs[i * DN_RP + r] = r < nrows ? src[i] : 0.0;
+    const double* src = P.X + (e0 + (r < nrows ? r : 0)) * P.stride;
+    for (int i = lane; i < k; i += 32) dn_cp_async8(Xs + i * DN_RP + r, src + i, r < nrows);
   }
+  dn_async_commit();
 }
 
 // U[r][jj] = sum_i Xt[i][r] * Ys[i][jj]; thread (trow = t/16, tcol = t%16) owns row positions trow*8 .. trow*8+NR-1,
@@ -215,13 +235,15 @@ __device__ __forceinline__ void dense_gemm_u_rows(int nr, const double* Xt, cons
 // the position carries a real row.  GRAD: U is replaced by dL/dU in place.  Returns this thread's share of the row's loss;
 // COLSUM additionally reduces every feature's loss over the 64 rows into red[warp][p] (fixed shuffle tree).
 template <int LOSS, bool GRAD, bool COLSUM>
-__device__ __forceinline__ double dense_elementwise(const DenseArgs& P, const DenseSmem& S, const double* __restrict__ At, int nf,
+__device__ __forceinline__ double dense_elementwise(const DenseArgs& P, const DenseSmem& S, int ms, const double* __restrict__ At, int nf,
                                                     int arow, bool valid) {
   const int t = threadIdx.x, r = t & 63, half = t >> 6, warp = t >> 5;
+  const int* s_feat = S.s_feat + ms * DN_TN;
+  const int* s_foff = S.s_foff + ms * (DN_TN + 2);
   double rowsum = 0.0;
   if (!COLSUM && !GRAD && !valid) return 0.0;               // compacted line search: positions past the active rows idle
   for (int p = half; p < nf; p += 2) {
-    const int f = S.s_feat[p], off = S.s_foff[p], D = S.s_foff[p + 1] - off;
+    const int f = s_feat[p], off = s_foff[p], D = s_foff[p + 1] - off;
     const double a = At[p * DN_TM + arow];
     const int code = LOSS ? LOSS : P.loss_code[f];
     const double* lp = P.loss_param + (int64_t)f * GLRMB200_LOSS_NPARAM;
@@ -292,7 +314,6 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
   double* Gg = P.gscratch + (int64_t)blockIdx.x * DN_TM * P.stride;
   const double l1 = (double)(P.n + 1);                                   // proxgrad.jl:134: length(observed_features[e]) + 1
   double* objold = S.rowv, *part = S.rowv + 64, *regnew = S.rowv + 128, *alpha = S.rowv + 192, *objrec = S.rowv + 256;
-  int chunk_loaded = -1;
   constexpr int NGW = 32 / TG;
   const int lg = lane % TG, gq = lane / TG;
   if (t == 0) { dn_mbar_init(S.bar, 1); dn_mbar_init(S.bar + 1, 1); }
@@ -304,13 +325,22 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
   // buffer of a step: with one or two chunks the tiles of A stay put for the whole tile (no refetch in the line search)
   auto bufof = [&](int c) { return ap.nbuf == 1 ? 0 : (nchunks <= 2 ? c : (int)(stepno & 1u)); };
   auto bufnext = [&](int c) { return ap.nbuf == 1 ? 0 : (nchunks <= 2 ? c : (int)((stepno + 1u) & 1u)); };
+  // the chunk of Y in shared memory (or on its way there) and the meta slot that describes it
+  int y_chunk = -1, y_ms = 0;
+  auto want_chunk = [&](int c) {           // Ys and the other meta slot must be free
+    if (y_chunk == c) return;
+    y_ms ^= 1;
+    dense_chunk_begin<KT>(P, S, c, y_ms);
+    y_chunk = c;
+  };
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t e0 = P.row0 + tile * DN_TM;
     const int nrows = (int)((P.row1 - e0) < DN_TM ? (P.row1 - e0) : DN_TM);
     __syncthreads();                                   // everybody is done with the previous tile's shared memory
     ap.fetch(P, S, bufof(0), e0, 0);
-    dense_load_x(P, S.Xs, e0, nrows);
+    dense_x_begin(P, S.Xs, e0, nrows);
+    want_chunk(0);
     double G[KT][8];
 #pragma unroll
     for (int q = 0; q < KT; ++q)
@@ -320,17 +350,17 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
     // ---- gradient pass (proxgrad.jl:119-135) ----
     for (int c = 0; c < nchunks; ++c) {
       const int b = bufof(c);
-      int ncols;
-      if (chunk_loaded != c) { ncols = dense_load_chunk<KT>(P, S, c); chunk_loaded = c; }
-      else { __syncthreads(); ncols = S.s_foff[P.chunk_ptr[c + 1] - P.chunk_ptr[c]]; }
+      if (y_chunk != c) { __syncthreads(); want_chunk(c); }      // Ys is busy until the previous step's G update is over
       const int nf = P.chunk_ptr[c + 1] - P.chunk_ptr[c];
       ap.fetch(P, S, b, e0, c);                        // normally a no-op: issued one step ahead
+      dn_async_wait();                                 // the chunk of Y (and, first step, the tile of X) has landed
+      const int ncols = S.s_foff[y_ms * (DN_TN + 2) + nf];
       dense_gemm_u<8>(S.Xs, S.Ys, S.Rs, k);
       __syncthreads();
       const int cn = c + 1 < nchunks ? c + 1 : 0;      // next step: the next chunk, or chunk 0 again (first trial round)
       if (ap.nbuf == 2) ap.fetch(P, S, bufnext(cn), e0, cn);
       ap.wait(S, b);
-      rowsum += dense_elementwise<LOSS, true, false>(P, S, S.As + (size_t)b * DN_TN * DN_TM, nf, t & 63, (t & 63) < nrows);
+      rowsum += dense_elementwise<LOSS, true, false>(P, S, y_ms, S.As + (size_t)b * DN_TN * DN_TM, nf, t & 63, (t & 63) < nrows);
       __syncthreads();
       if (ap.nbuf == 1) ap.fetch(P, S, 0, e0, cn);
       dense_gemm_gx<KT>(S.Ys, S.Rs, ncols, G);
@@ -349,7 +379,8 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
       }
     }
     if (t >= 64) part[t - 64] = rowsum;
-    __syncthreads();
+    __syncthreads();                                   // (also: the last G update has finished reading Ys)
+    if (nchunks > 1) want_chunk(0);                    // chunk 0 comes back while the line search is set up
     if (t < 64) part[t] = rowsum + part[t];                               // loss of row t over all features (fixed order)
     __syncthreads();
     // regularizer of the current rows + line-search state: a lane group per row
@@ -419,7 +450,6 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
           if (lg == 0) regnew[r] = rv;
         }
       }
-      __syncthreads();
       const int myslot = dense_slot_pos(t & 63);                           // the slot whose position this thread serves
       const bool mine = myslot < na;
       const int myrow = S.s_perm[mine ? myslot : 0];
@@ -427,15 +457,18 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
       double trialsum = 0.0;
       for (int c = 0; c < nchunks; ++c) {
         const int b = bufof(c);
-        if (chunk_loaded != c) { dense_load_chunk<KT>(P, S, c); chunk_loaded = c; }
+        want_chunk(c);                                 // normally on its way already
         const int nf = P.chunk_ptr[c + 1] - P.chunk_ptr[c];
         ap.fetch(P, S, b, e0, c);
+        dn_async_wait();                               // chunk of Y landed; trial points written (first chunk)
         dense_gemm_u_rows(nr, S.Xs, S.Ys, S.Rs, k);
         __syncthreads();
         const int cn = c + 1 < nchunks ? c + 1 : 0;
+        const int ms = y_ms;                           // the element-wise phase below still reads this chunk's meta slot
+        if (nchunks > 1) want_chunk(cn);               // Ys is free: the next chunk travels during the element-wise phase
         if (ap.nbuf == 2) ap.fetch(P, S, bufnext(cn), e0, cn);
         ap.wait(S, b);
-        trialsum += dense_elementwise<LOSS, false, false>(P, S, S.As + (size_t)b * DN_TN * DN_TM, nf, myrow, mine);
+        trialsum += dense_elementwise<LOSS, false, false>(P, S, ms, S.As + (size_t)b * DN_TN * DN_TM, nf, myrow, mine);
         __syncthreads();
         if (ap.nbuf == 1) ap.fetch(P, S, 0, e0, cn);
         ++stepno;
@@ -481,7 +514,8 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
     }
     if (ntrials && P.trial_counter) atomicAdd(P.trial_counter, (unsigned long long)ntrials);
   }
-  ap.wait(S, 0);                                       // no bulk copy may be in flight when the CTA exits
+  dn_async_wait();                                     // nothing may be in flight when the CTA exits
+  ap.wait(S, 0);
   ap.wait(S, 1);
 }
 
@@ -505,8 +539,11 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_y_pass_kernel(const Dense
   __syncthreads();
   APipe ap;
   ap.init(P.nbuf);
-  if (rb0 < rb1) ap.fetch(P, S, 0, rb0, c);
-  const int ncols = dense_load_chunk<KT>(P, S, c);
+  if (rb0 < rb1) {
+    ap.fetch(P, S, 0, rb0, c);
+    dense_x_begin(P, S.Xs, rb0, (int)((rb1 - rb0) < DN_TM ? (rb1 - rb0) : DN_TM));
+  }
+  dense_chunk_begin<KT>(P, S, c, 0);
   const int nf = P.chunk_ptr[c + 1] - P.chunk_ptr[c];
   // accumulators: thread (ti = t%16, tj = t/16) owns i = ti + 16 q, columns tj + 8 b2
   constexpr int CJ = DN_TN / 8;
@@ -523,16 +560,18 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_y_pass_kernel(const Dense
   for (int64_t e0 = rb0; e0 < rb1; e0 += DN_TM, ++j) {
     const int nrows = (int)((rb1 - e0) < DN_TM ? (rb1 - e0) : DN_TM);
     const int buf = ap.nbuf == 2 ? (j & 1) : 0;
-    __syncthreads();                       // the previous tile's readers of Xs / Rs / the other A buffer are done
-    dense_load_x(P, S.Xs, e0, nrows);
-    if (ap.nbuf == 2 && e0 + DN_TM < rb1) ap.fetch(P, S, buf ^ 1, e0 + DN_TM, c);
-    __syncthreads();
+    const bool more = e0 + DN_TM < rb1;
+    const int nrows_next = more ? (int)((rb1 - e0 - DN_TM) < DN_TM ? (rb1 - e0 - DN_TM) : DN_TM) : 0;
+    dn_async_wait();                       // this tile of X (first tile: and the chunk of Y) has landed; also the barrier
+                                           // after the previous tile's G_Y update / element-wise phase
+    if (ap.nbuf == 2 && more) ap.fetch(P, S, buf ^ 1, e0 + DN_TM, c);
     dense_gemm_u<8>(S.Xs, S.Ys, S.Rs, k);
     __syncthreads();
+    if (MODE == 1 && more) dense_x_begin(P, S.Xs, e0 + DN_TM, nrows_next);      // Xs is free: the next tile travels now
     ap.wait(S, buf);
-    dense_elementwise<LOSS, MODE == 0, true>(P, S, S.As + (size_t)buf * DN_TN * DN_TM, nf, t & 63, (t & 63) < nrows);
+    dense_elementwise<LOSS, MODE == 0, true>(P, S, 0, S.As + (size_t)buf * DN_TN * DN_TM, nf, t & 63, (t & 63) < nrows);
     __syncthreads();
-    if (ap.nbuf == 1 && e0 + DN_TM < rb1) ap.fetch(P, S, 0, e0 + DN_TM, c);
+    if (ap.nbuf == 1 && more) ap.fetch(P, S, 0, e0 + DN_TM, c);
     // per-feature sums of the tile, in a fixed order: rows 0-31 + rows 32-63 (feature p was handled by half p % 2)
     if (t < nf) {
       const int h = t & 1;
@@ -556,9 +595,11 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_y_pass_kernel(const Dense
           for (int q = 0; q < KT; ++q) GY[q][b2] = fma(x[q].y, rv.y, fma(x[q].x, rv.x, GY[q][b2]));
         }
       }
+      if (more) { __syncthreads(); dense_x_begin(P, S.Xs, e0 + DN_TM, nrows_next); }
     }
   }
-  __syncthreads();
+  dn_async_wait();
+  const int ncols = S.s_foff[nf];
   if (t < nf) P.objpart[(int64_t)b * P.n + S.s_feat[t]] = colacc[t];
   if (MODE == 0) {
     const int ti = t & 15, tj = t >> 4;

@@ -52,6 +52,8 @@ struct SweepArgs {
   double uparam[3];           // uniform loss parameters (scale, p1, p2) when LOSS != 0
   const int32_t* reg_code;    // [1] or [units_total]
   const double* reg_param;    // [1*4] or [units_total*4]
+  const int64_t* reg_payload_ptr;  // [1+1] or [units_total+1] offsets of the regularizers' vector payloads, or nullptr
+  const double* reg_payload;
   int32_t reg_uniform;
   int32_t flags;
   double* alpha;          // [units_total] step sizes (alpharow / alphacol, proxgrad.jl:69-70)
@@ -196,20 +198,29 @@ __device__ __forceinline__ ArgMax group_argmax(ArgMax m) {
   return m;
 }
 
+// `pay` / `npay`: the regularizer's vector payload (fixed_latent_features.y / fixed_last_latent_features.y: the pinned
+// values, RemQuadReg.m: the mean; regularizers.jl:193-231,412-423).  The inner regularizer sees the index range [klo, khi).
 template <int G, int R>
-__device__ __forceinline__ double reg_eval(int code, const double* __restrict__ rp, const double2 (&v)[R], int lg, int k) {
+__device__ __forceinline__ double reg_eval(int code, const double* __restrict__ rp, const double2 (&v)[R], int lg, int k,
+                                           const double* __restrict__ pay = nullptr, int npay = 0) {
   const int base = code & GLRMB200_REG_BASE_MASK;
   const bool wrapped = code & (GLRMB200_REG_LASTENTRY1 | GLRMB200_REG_LASTENTRY_UNPENALIZED);
-  const int kin = wrapped ? k - 1 : k;
-  // BODY is applied to every element the inner regularizer sees (index < kin); padded slots are skipped
-#define GLRM_EACH(BODY)                                                  \
-  _Pragma("unroll") for (int r = 0; r < R; ++r) {                        \
-    const int i0 = 2 * (lg + G * r);                                     \
-    { const double e = v[r].x; if (i0 < kin) { BODY; } }                  \
-    { const double e = v[r].y; if (i0 + 1 < kin) { BODY; } }              \
+  const int klo = (code & GLRMB200_REG_FIXED_FIRST) ? npay : 0;                                 // :208 evaluate(r.r, a[n+1:end])
+  const int khi = wrapped ? k - 1 : ((code & GLRMB200_REG_FIXED_LAST) ? k - npay : k);          // :230 evaluate(r.r, a[1:k-n])
+  // BODY is applied to every element the inner regularizer sees (klo <= index < khi); padded slots are skipped
+#define GLRM_EACH(BODY)                                                                   \
+  _Pragma("unroll") for (int r = 0; r < R; ++r) {                                         \
+    const int i0 = 2 * (lg + G * r);                                                      \
+    { const double e = v[r].x; const int i = i0; (void)i; if (i0 >= klo && i0 < khi) { BODY; } }              \
+    { const double e = v[r].y; const int i = i0 + 1; (void)i; if (i0 + 1 >= klo && i0 + 1 < khi) { BODY; } }  \
   }
   double res;
   switch (base) {
+    case GLRMB200_REG_REM_QUAD: {                                                               // :423
+      double s2 = 0.0;
+      GLRM_EACH(const double t = e - pay[i]; s2 = fma(t, t, s2))
+      res = rp[0] * group_sum<G>(s2);
+    } break;
     case GLRMB200_REG_ZERO: res = 0.0; break;                                                   // :95
     case GLRMB200_REG_QUAD: {                                                                   // :58
       double s2 = 0.0;
@@ -273,21 +284,70 @@ __device__ __forceinline__ double reg_eval(int code, const double* __restrict__ 
     }
     if (group_sum_i<G>(badlast)) res = INFINITY;
   }
+  if (code & (GLRMB200_REG_FIXED_FIRST | GLRMB200_REG_FIXED_LAST)) {                             // :208 / :230: pinned entries == y, else Inf
+    const int p0 = (code & GLRMB200_REG_FIXED_FIRST) ? 0 : k - npay;
+    int bad = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i0 = 2 * (lg + G * r);
+      if (i0 >= p0 && i0 < p0 + npay && v[r].x != pay[i0 - p0]) bad = 1;
+      if (i0 + 1 >= p0 && i0 + 1 < p0 + npay && v[r].y != pay[i0 + 1 - p0]) bad = 1;
+    }
+    if (group_sum_i<G>(bad)) res = INFINITY;
+  }
   return res;
 }
 
+// v'[j] = v[j + n] on a lane-distributed vector (elements shifted in past the end are zero): what
+// fixed_last_latent_features' prox feeds its inner regularizer (regularizers.jl:223, u[(r.n+1):end]).  Element j lives in
+// flattened slot p = j / 2 = lg + G * r; every source lane works out which of its slots its reader needs.
 template <int G, int R>
-__device__ __forceinline__ void reg_prox(int code, const double* __restrict__ rp, double2 (&v)[R], int lg, int k, double alpha) {
+__device__ __forceinline__ void shift_left(double2 (&v)[R], int n, int lg) {
+  const int q = n >> 1, o = n & 1;
+  const int gbase = (threadIdx.x & 31) - lg;
+  double2 out[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int dq = q + (h ? o : 0);                 // slots to the right of the reader
+      const int hs = h ? 1 - o : o;                   // half of the source slot
+      const int src_lg = (lg + dq) % G;               // lane (within the group) this reader fetches from
+      const int lg_t = ((lg - dq) % G + G) % G;       // the reader that fetches from THIS lane ...
+      const int rs = r + (lg_t + dq) / G;             // ... wants this slot of it
+      double supply = 0.0;
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr) if (rr == rs) supply = hs ? v[rr].y : v[rr].x;
+      const double got = __shfl_sync(FULLMASK, supply, gbase + src_lg);
+      if (h) out[r].y = got; else out[r].x = got;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = out[r];
+}
+
+template <int G, int R>
+__device__ __forceinline__ void reg_prox(int code, const double* __restrict__ rp, double2 (&v)[R], int lg, int k, double alpha,
+                                         const double* __restrict__ pay = nullptr, int npay = 0) {
   const int base = code & GLRMB200_REG_BASE_MASK;
   const bool wrapped = code & (GLRMB200_REG_LASTENTRY1 | GLRMB200_REG_LASTENTRY_UNPENALIZED);
-  const int kin = wrapped ? k - 1 : k;
+  // fixed_last_latent_features, literally (:223): [prox(r.r, u[(n+1):end], alpha); y] — the inner prox sees the LAST k-n
+  // entries, its result becomes the FIRST k-n
+  if (code & GLRMB200_REG_FIXED_LAST) shift_left<G, R>(v, npay, lg);
+  const int klo = (code & GLRMB200_REG_FIXED_FIRST) ? npay : 0;                                 // :203 prox(r.r, u[(n+1):end])
+  const int khi = wrapped ? k - 1 : ((code & GLRMB200_REG_FIXED_LAST) ? k - npay : k);
+  const int kin = khi - klo;                                                                    // length the inner regularizer sees
 #define GLRM_FOREACH(BODY)                                              \
   _Pragma("unroll") for (int r = 0; r < R; ++r) {                       \
     const int i0 = 2 * (lg + G * r);                                    \
-    { double& e = v[r].x; const int i = i0; if (i < kin) { BODY; } }     \
-    { double& e = v[r].y; const int i = i0 + 1; if (i < kin) { BODY; } } \
+    { double& e = v[r].x; const int i = i0; if (i >= klo && i < khi) { BODY; } }     \
+    { double& e = v[r].y; const int i = i0 + 1; if (i >= klo && i < khi) { BODY; } } \
   }
   switch (base) {
+    case GLRMB200_REG_REM_QUAD: {                                                               // :417-418
+      const double c2 = 2.0 * alpha * rp[0];
+      GLRM_FOREACH(e = (e + c2 * pay[i]) / (1.0 + c2))
+    } break;
     case GLRMB200_REG_ZERO: break;                                                              // :93
     case GLRMB200_REG_QUAD: {                                                                   // :56
       const double c = 1.0 / (1.0 + 2.0 * alpha * rp[0]);
@@ -322,8 +382,8 @@ __device__ __forceinline__ void reg_prox(int code, const double* __restrict__ rp
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const int i0 = 2 * (lg + G * r);
-          if (i0 < kin && !(keep >> (2 * r) & 1u) && am_better(fabs(v[r].x), i0, m.v, m.i)) { m.v = fabs(v[r].x); m.i = i0; }
-          if (i0 + 1 < kin && !(keep >> (2 * r + 1) & 1u) && am_better(fabs(v[r].y), i0 + 1, m.v, m.i)) { m.v = fabs(v[r].y); m.i = i0 + 1; }
+          if (i0 >= klo && i0 < khi && !(keep >> (2 * r) & 1u) && am_better(fabs(v[r].x), i0, m.v, m.i)) { m.v = fabs(v[r].x); m.i = i0; }
+          if (i0 + 1 >= klo && i0 + 1 < khi && !(keep >> (2 * r + 1) & 1u) && am_better(fabs(v[r].y), i0 + 1, m.v, m.i)) { m.v = fabs(v[r].y); m.i = i0 + 1; }
         }
         m = group_argmax<G>(m);
 #pragma unroll
@@ -336,8 +396,8 @@ __device__ __forceinline__ void reg_prox(int code, const double* __restrict__ rp
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int i0 = 2 * (lg + G * r);
-        if (i0 < kin && !(keep >> (2 * r) & 1u)) v[r].x = 0.0;
-        if (i0 + 1 < kin && !(keep >> (2 * r + 1) & 1u)) v[r].y = 0.0;
+        if (i0 >= klo && i0 < khi && !(keep >> (2 * r) & 1u)) v[r].x = 0.0;
+        if (i0 + 1 >= klo && i0 + 1 < khi && !(keep >> (2 * r + 1) & 1u)) v[r].y = 0.0;
       }
     } break;
     case GLRMB200_REG_SIMPLEX: {                                                                // :325-337
@@ -351,8 +411,8 @@ __device__ __forceinline__ void reg_prox(int code, const double* __restrict__ rp
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const int i0 = 2 * (lg + G * r);
-          if (i0 < kin && !(used >> (2 * r) & 1u) && am_better(v[r].x, i0, m.v, m.i)) { m.v = v[r].x; m.i = i0; }
-          if (i0 + 1 < kin && !(used >> (2 * r + 1) & 1u) && am_better(v[r].y, i0 + 1, m.v, m.i)) { m.v = v[r].y; m.i = i0 + 1; }
+          if (i0 >= klo && i0 < khi && !(used >> (2 * r) & 1u) && am_better(v[r].x, i0, m.v, m.i)) { m.v = v[r].x; m.i = i0; }
+          if (i0 + 1 >= klo && i0 + 1 < khi && !(used >> (2 * r + 1) & 1u) && am_better(v[r].y, i0 + 1, m.v, m.i)) { m.v = v[r].y; m.i = i0 + 1; }
         }
         m = group_argmax<G>(m);
 #pragma unroll
@@ -377,6 +437,15 @@ __device__ __forceinline__ void reg_prox(int code, const double* __restrict__ rp
       const int i0 = 2 * (lg + G * r);
       if (i0 == k - 1) v[r].x = 1.0;
       if (i0 + 1 == k - 1) v[r].y = 1.0;
+    }
+  }
+  if (code & (GLRMB200_REG_FIXED_FIRST | GLRMB200_REG_FIXED_LAST)) {                             // :203 / :223: the pinned entries
+    const int p0 = (code & GLRMB200_REG_FIXED_FIRST) ? 0 : k - npay;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i0 = 2 * (lg + G * r);
+      if (i0 >= p0 && i0 < p0 + npay) v[r].x = pay[i0 - p0];
+      if (i0 + 1 >= p0 && i0 + 1 < p0 + npay) v[r].y = pay[i0 + 1 - p0];
     }
   }
 }
@@ -736,6 +805,13 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
   }
   const int rcode = A.reg_code[A.reg_uniform ? 0 : unit];
   const double* rp = A.reg_param + (A.reg_uniform ? 0 : unit) * GLRMB200_REG_NPARAM;
+  const double* pay = nullptr;
+  int npay = 0;
+  if (A.reg_payload_ptr) {
+    const int64_t p0 = A.reg_payload_ptr[A.reg_uniform ? 0 : unit];
+    pay = A.reg_payload + p0;
+    npay = (int)(A.reg_payload_ptr[(A.reg_uniform ? 0 : unit) + 1] - p0);
+  }
   const bool use_reg = !(A.flags & FLAG_NO_REG);
 
   // ---- gradient pass (proxgrad.jl:119-135 / :163-178) ----------------------------------------
@@ -746,7 +822,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
   obj_old = cluster_sum_obj<CS>(obj_old, clbuf);
   unit_reduce_g<G, R, W>(g, red, lane, warp, lg);
   cluster_sum_g<G, R, CS>(g, reinterpret_cast<double2*>(clbuf + 2), gid, lg);
-  if (use_reg) obj_old += reg_eval<G, R>(rcode, rp, x, lg, k);
+  if (use_reg) obj_old += reg_eval<G, R>(rcode, rp, x, lg, k, pay, npay);
 
   const bool uncond = A.flags & FLAG_UNCONDITIONAL;
   double alpha = uncond ? A.global_alpha : A.alpha[unit];
@@ -773,7 +849,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
         const double2 xr = xs[r * G + lg], gr = gs[r * G + lg];
         xn[r].x = fma(-stepsize, gr.x, xr.x); xn[r].y = fma(-stepsize, gr.y, xr.y);                   // :140
       }
-      reg_prox<G, R>(rcode, rp, xn, lg, k, stepsize);                    // :142
+      reg_prox<G, R>(rcode, rp, xn, lg, k, stepsize, pay, npay);         // :142
       if (uncond) {                                                      // sparse_proxgrad.jl:73-78 / :93-98: no trial
         if (gid == 0 && crank == 0) {
           const int64_t off = own - A.own;
@@ -802,7 +878,7 @@ __device__ __forceinline__ void process_unit(const SweepArgs& A, int64_t unit, d
         obj_new = block_sum_obj<W>(obj_new, red, lane, warp);
         obj_new = cluster_sum_obj<CS>(obj_new, clbuf);
       }
-      obj_new += reg_eval<G, R>(rcode, rp, xn, lg, k);
+      obj_new += reg_eval<G, R>(rcode, rp, xn, lg, k, pay, npay);
       ++ntrials;
       if (obj_new < obj_old) {                                           // :143 (strict; NaN rejects)
         if (gid == 0 && crank == 0) {
@@ -876,23 +952,42 @@ __global__ void __launch_bounds__(WARPS_PER_CTA_HEAVY * 32, TileCfg<R>::HEAVY_CT
   process_unit<G, R, WARPS_PER_CTA_HEAVY, LOSS, (TileCfg<R>::HEAVY_DEPTH <= G ? TileCfg<R>::HEAVY_DEPTH : G), CS, TileCfg<R>::HEAVY_TRIAL_DEPTH>(A, A.order[blockIdx.x / CS], red, part, xg, clbuf);
 }
 
-// out[unit] = r(own[:, unit])  — the penalty terms of calc_penalty (evaluate_fit.jl:91-104)
+// out[unit] = r(own[:, unit])  — the penalty terms of calc_penalty (evaluate_fit.jl:91-104).  With one regularizer per
+// unit the codes of neighbouring units may differ, and the reductions inside reg_eval are warp-wide shuffles: the warp
+// then walks its units one at a time (every lane group evaluates the same unit), so the code stays warp-uniform.
 template <int G, int R>
 __global__ void __launch_bounds__(128) reg_eval_kernel(const double* __restrict__ own, int64_t units, int stride, int k,
                                                        const int32_t* reg_code, const double* reg_param,
-                                                       int reg_uniform, double* out) {
+                                                       int reg_uniform, double* out,
+                                                       const int64_t* reg_payload_ptr = nullptr, const double* reg_payload = nullptr) {
   const int lane = threadIdx.x & 31, lg = lane % G;
-  const int64_t unit = ((int64_t)blockIdx.x * 4 + (threadIdx.x >> 5)) * (32 / G) + lane / G;
-  const bool ok = unit < units;
-  double2 x[R];
+  const int64_t first = ((int64_t)blockIdx.x * 4 + (threadIdx.x >> 5)) * (32 / G);
+  if (reg_uniform) {
+    const int64_t unit = first + lane / G;
+    const bool ok = unit < units;
+    double2 x[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int i0 = 2 * (lg + G * r);
-    x[r] = ok ? *reinterpret_cast<const double2*>(own + unit * (int64_t)stride + i0) : make_double2(0.0, 0.0);
+    for (int r = 0; r < R; ++r) {
+      const int i0 = 2 * (lg + G * r);
+      x[r] = ok ? *reinterpret_cast<const double2*>(own + unit * (int64_t)stride + i0) : make_double2(0.0, 0.0);
+    }
+    const double* pay = reg_payload_ptr ? reg_payload + reg_payload_ptr[0] : nullptr;
+    const int npay = reg_payload_ptr ? (int)(reg_payload_ptr[1] - reg_payload_ptr[0]) : 0;
+    const double v = reg_eval<G, R>(reg_code[0], reg_param, x, lg, k, pay, npay);
+    if (ok && lg == 0) out[unit] = v;
+    return;
   }
-  const int64_t ru = (reg_uniform || !ok) ? 0 : unit;
-  const double v = reg_eval<G, R>(reg_code[ru], reg_param + ru * GLRMB200_REG_NPARAM, x, lg, k);
-  if (ok && lg == 0) out[unit] = v;
+  for (int j = 0; j < 32 / G; ++j) {
+    const int64_t unit = first + j;
+    if (unit >= units) break;
+    double2 x[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) x[r] = *reinterpret_cast<const double2*>(own + unit * (int64_t)stride + 2 * (lg + G * r));
+    const double* pay = reg_payload_ptr ? reg_payload + reg_payload_ptr[unit] : nullptr;
+    const int npay = reg_payload_ptr ? (int)(reg_payload_ptr[unit + 1] - reg_payload_ptr[unit]) : 0;
+    const double v = reg_eval<G, R>(reg_code[unit], reg_param + unit * GLRMB200_REG_NPARAM, x, lg, k, pay, npay);
+    if (lane == 0) out[unit] = v;
+  }
 }
 
 }  // namespace glrm

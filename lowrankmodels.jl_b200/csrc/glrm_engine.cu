@@ -101,6 +101,8 @@ struct Side {
   int64_t n_vec = 0;
   int32_t* d_reg_code = nullptr;
   double* d_reg_param = nullptr;
+  int64_t* d_reg_payload_ptr = nullptr;   // vector payloads of the regularizers (fixed_latent_features.y, RemQuadReg.m) or nullptr
+  double* d_reg_payload = nullptr;
   std::vector<double> h_reg_param;  // for set_reg_scale
   std::vector<int32_t> h_reg_code;
   int reg_uniform = 1;
@@ -170,8 +172,8 @@ struct glrmb200_engine {
   double* h_pinned = nullptr;               // [16] pinned, device-mapped scratch (pinned_get / pinned_put)
   volatile int* h_stop = nullptr;           // mapped flag written by record_kernel (inside h_pinned)
   cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;            // the warp-tier launch of a sweep runs here, concurrently with the CTA tier
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t tier_stream[3] = {nullptr, nullptr, nullptr};   // cluster-8 / cluster-4 / warp tier of a sweep (the CTA tier runs on `stream`)
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_base = nullptr, ev_aux = nullptr;
   std::vector<cudaEvent_t> evpool;           // EVENT_CHUNK x 5 per-iteration timing events
   ncclComm_t comm = nullptr;
@@ -336,22 +338,42 @@ static int build_schedule(glrmb200_engine* E, Side& S, const int64_t* ptr_global
   return upload(&S.d_order_vec, vec.data(), vec.size(), E->stream);
 }
 
-static int setup_regs(glrmb200_engine* E, Side& S, int64_t count, const int32_t* code, const double* param, bool allow_ordinal) {
+static int setup_regs(glrmb200_engine* E, Side& S, int64_t count, const int32_t* code, const double* param, bool allow_ordinal,
+                      const int64_t* payload_ptr, const double* payload) {
   if (count != 1 && count != S.units) return fail(GLRMB200_E_INVALID, "regularizer count must be 1 or the number of columns");
   S.reg_uniform = (count == 1);
   S.h_reg_code.assign(code, code + count);
   S.h_reg_param.assign(param, param + count * GLRMB200_REG_NPARAM);
+  constexpr int kFixed = GLRMB200_REG_FIXED_FIRST | GLRMB200_REG_FIXED_LAST;
+  constexpr int kOffset = GLRMB200_REG_LASTENTRY1 | GLRMB200_REG_LASTENTRY_UNPENALIZED;
+  constexpr int kBlock = GLRMB200_REG_ORDINAL | GLRMB200_REG_MNL_ORDINAL;
   for (int64_t i = 0; i < count; ++i) {
     const int base = code[i] & GLRMB200_REG_BASE_MASK;
-    const int ord = code[i] & (GLRMB200_REG_ORDINAL | GLRMB200_REG_MNL_ORDINAL);
-    if (ord && (!allow_ordinal || (code[i] & (GLRMB200_REG_LASTENTRY1 | GLRMB200_REG_LASTENTRY_UNPENALIZED))))
-      return fail(GLRMB200_E_UNSUPPORTED, "OrdinalReg / MNLOrdinalReg are column (ry) regularizers and are not combined with the offset wrappers");
-    if (base > GLRMB200_REG_SIMPLEX || (code[i] & ~(GLRMB200_REG_BASE_MASK | GLRMB200_REG_LASTENTRY1 | GLRMB200_REG_LASTENTRY_UNPENALIZED | GLRMB200_REG_ORDINAL | GLRMB200_REG_MNL_ORDINAL)))
+    const int ord = code[i] & kBlock;
+    if (ord && (!allow_ordinal || (code[i] & (kOffset | kFixed))))
+      return fail(GLRMB200_E_UNSUPPORTED, "OrdinalReg / MNLOrdinalReg are column (ry) regularizers and are not combined with other wrappers");
+    if (base > GLRMB200_REG_REM_QUAD || (code[i] & ~(GLRMB200_REG_BASE_MASK | kOffset | kBlock | kFixed)))
       return fail(GLRMB200_E_UNSUPPORTED, "regularizer code %d has no device implementation", code[i]);
+    const bool fixed = code[i] & kFixed;
+    if (fixed && ((code[i] & kOffset) || base == GLRMB200_REG_REM_QUAD || (code[i] & kFixed) == kFixed))
+      return fail(GLRMB200_E_UNSUPPORTED, "fixed_latent_features is not combined with the offset wrappers, RemQuadReg or its twin");
+    if (base == GLRMB200_REG_REM_QUAD && (code[i] & kOffset))
+      return fail(GLRMB200_E_UNSUPPORTED, "RemQuadReg inside an offset wrapper has no device implementation");
+    if (fixed || base == GLRMB200_REG_REM_QUAD) {
+      if (!payload_ptr || !payload) return fail(GLRMB200_E_INVALID, "regularizer %lld needs a vector payload (rx_payload / ry_payload)", (long long)i);
+      const int64_t len = payload_ptr[i + 1] - payload_ptr[i];
+      if (len < 0 || len > E->k || (base == GLRMB200_REG_REM_QUAD && !fixed && len != E->k))
+        return fail(GLRMB200_E_INVALID, "regularizer %lld: payload of length %lld with k = %lld", (long long)i, (long long)len, (long long)E->k);
+    }
   }
   int rc = upload(&S.d_reg_code, code, (size_t)count, E->stream);
   if (rc) return rc;
-  return upload(&S.d_reg_param, param, (size_t)count * GLRMB200_REG_NPARAM, E->stream);
+  if ((rc = upload(&S.d_reg_param, param, (size_t)count * GLRMB200_REG_NPARAM, E->stream))) return rc;
+  if (payload_ptr && payload) {
+    if ((rc = upload(&S.d_reg_payload_ptr, payload_ptr, (size_t)count + 1, E->stream))) return rc;
+    if ((rc = upload(&S.d_reg_payload, payload, (size_t)std::max<int64_t>(1, payload_ptr[count]), E->stream))) return rc;
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -362,8 +384,12 @@ static const Tile kTiles[] = {{4, 1}, {8, 1}, {8, 2}, {8, 3}, {8, 4}, {16, 2}, {
 
 static cudaError_t launch_sweep(const glrmb200_engine* E, const SweepArgs& A, const Side& S, int64_t* launches) {
   const TierCounts tc{S.n_cluster16, S.n_cluster, S.n_heavy, S.n_light};
-  static const bool two_streams = !(getenv("GLRMB200_ONE_STREAM") && atoi(getenv("GLRMB200_ONE_STREAM")));
-  const Streams st{E->stream, two_streams ? E->stream2 : nullptr, E->ev_fork, E->ev_join};
+  const bool two_streams = !(getenv("GLRMB200_ONE_STREAM") && atoi(getenv("GLRMB200_ONE_STREAM")));
+  Streams st;
+  st.main = E->stream;
+  st.fork = E->ev_fork;
+  const bool warp_only = getenv("GLRMB200_TIER_STREAMS") && atoi(getenv("GLRMB200_TIER_STREAMS")) == 1;   // A/B hook: round-1 layout
+  for (int i = 0; i < 3; ++i) { st.tier[i] = (two_streams && !(warp_only && i < 2)) ? E->tier_stream[i] : nullptr; st.join[i] = E->ev_join[i]; }
   const bool wide = E->tile_g >= 16;
   switch (E->loss_template) {
     case GLRMB200_LOSS_QUAD: return (wide ? launch_quad_wide : launch_quad_narrow)(E->tile_g, E->tile_r, A, tc, st, launches);
@@ -390,7 +416,7 @@ static cudaError_t launch_reg_eval(const glrmb200_engine* E, const double* own, 
   const int g = E->tile_g, r = E->tile_r;
   const int64_t per_cta = 4 * (32 / g);
   const unsigned grid = (unsigned)((S.units + per_cta - 1) / per_cta);
-#define T(GG, RR) if (g == GG && r == RR) { reg_eval_kernel<GG, RR><<<grid, 128, 0, E->stream>>>(own, S.units, E->stride, (int)E->k, S.d_reg_code, S.d_reg_param, S.reg_uniform, out); return cudaGetLastError(); }
+#define T(GG, RR) if (g == GG && r == RR) { reg_eval_kernel<GG, RR><<<grid, 128, 0, E->stream>>>(own, S.units, E->stride, (int)E->k, S.d_reg_code, S.d_reg_param, S.reg_uniform, out, S.d_reg_payload_ptr, S.d_reg_payload); return cudaGetLastError(); }
   T(4, 1) T(8, 1) T(8, 2) T(8, 3) T(8, 4) T(16, 2) T(16, 3) T(16, 4) T(32, 2) T(32, 3) T(32, 4)
 #undef T
   return cudaErrorInvalidValue;
@@ -417,6 +443,8 @@ static SweepArgs make_args(const glrmb200_engine* E, bool x_side, int flags, dou
   A.uparam[0] = E->uparam[0]; A.uparam[1] = E->uparam[1]; A.uparam[2] = E->uparam[2];
   A.reg_code = S.d_reg_code;
   A.reg_param = S.d_reg_param;
+  A.reg_payload_ptr = S.d_reg_payload_ptr;
+  A.reg_payload = S.d_reg_payload;
   A.reg_uniform = S.reg_uniform;
   A.flags = flags | ((x_side && E->loss_template == 0) ? FLAG_LOSS_BY_ENTRY : 0);
   A.alpha = S.d_alpha;
@@ -452,6 +480,7 @@ static bool dense_eligible(const glrmb200_engine* E, const glrmb200_problem* P) 
   if (getenv("GLRMB200_TILE")) return false;
   for (int64_t i = 0; i < P->ry_count; ++i)
     if (P->ry_code[i] & (GLRMB200_REG_ORDINAL | GLRMB200_REG_MNL_ORDINAL)) return false;
+  if (P->rx_payload_ptr || P->ry_payload_ptr) return false;      // regularizers with vector payloads run on the gather kernels
   return true;
 }
 
@@ -594,6 +623,11 @@ static int dense_sweep_x(glrmb200_engine* E, double min_stepsize, bool honour_st
   return 0;
 }
 
+static double dense_wait_limit_s() {
+  if (const char* t = getenv("GLRMB200_WAIT_LIMIT_S")) return std::max(1.0, atof(t));
+  return 120.0;
+}
+
 // losses of every feature at the current Y -> colobj (mode 0: and the gradient G_Y); then obj_by_col = loss + ry and the
 // search state (dense_y_begin_kernel)
 static int dense_eval_cols(glrmb200_engine* E, int flags, double min_stepsize, bool honour_stop, int mode, int64_t* launches) {
@@ -641,9 +675,11 @@ static int dense_sweep_y(glrmb200_engine* E, double min_stepsize, bool honour_st
       const int32_t k1 = D.h_nactive[1];
       if ((k1 >> 12) == D.seq && (k1 & 4095) >= round) break;
       if ((spin & 1023) == 1023) {
-        if (cudaStreamQuery(E->stream) == cudaSuccess) break;              // everything enqueued has run: the plan is there
-        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 600.0)
-          return fail(GLRMB200_E_STATE, "dense Y line search: the device did not publish its plan");
+        const cudaError_t q = cudaStreamQuery(E->stream);
+        if (q == cudaSuccess) break;                                       // everything enqueued has run: the plan is there
+        if (q != cudaErrorNotReady) return fail(GLRMB200_E_CUDA, "dense Y sweep: %s", cudaGetErrorString(q));
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > dense_wait_limit_s())
+          return fail(GLRMB200_E_STATE, "dense Y line search: the device did not publish its plan within %.0f s", dense_wait_limit_s());
       }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
@@ -671,6 +707,7 @@ static void free_lists(glrmb200_engine* E, Side& S) {
 static void free_side(glrmb200_engine* E, Side& S) {
   free_lists(E, S);
   dfree(S.d_reg_code, E->stream); dfree(S.d_reg_param, E->stream); dfree(S.d_alpha, E->stream); dfree(S.d_obj, E->stream);
+  dfree(S.d_reg_payload_ptr, E->stream); dfree(S.d_reg_payload, E->stream);
 }
 
 // Process-level cache of the exchange allocation and its peer mappings.  cudaIpcCloseMemHandle + cudaFree of an
@@ -720,8 +757,10 @@ extern "C" int glrmb200_destroy(glrmb200_handle E) {
   if (E->ev_base) cudaEventDestroy(E->ev_base);
   if (E->ev_aux) cudaEventDestroy(E->ev_aux);
   if (E->ev_fork) cudaEventDestroy(E->ev_fork);
-  if (E->ev_join) cudaEventDestroy(E->ev_join);
-  if (E->stream2) cudaStreamDestroy(E->stream2);
+  for (int i = 0; i < 3; ++i) {
+    if (E->ev_join[i]) cudaEventDestroy(E->ev_join[i]);
+    if (E->tier_stream[i]) cudaStreamDestroy(E->tier_stream[i]);
+  }
   if (E->stream) cudaStreamDestroy(E->stream);   // work already enqueued (the frees) still completes
   pinned_put(E->h_pinned);                       // the stream was synchronised above: no kernel still writes the flags
   delete E;
@@ -904,10 +943,20 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
   if ((rc = pool_setup(E->device))) return rc;
   if ((rc = pinned_get(&E->h_pinned))) return rc;
   E->h_stop = reinterpret_cast<volatile int*>(E->h_pinned + 8);
-  CUDA_OK(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
-  CUDA_OK(cudaStreamCreateWithFlags(&E->stream2, cudaStreamNonBlocking));
+  {
+    // stream priorities (lower number = higher priority): cluster tiers above the CTA tier above the warp tier, so the
+    // units on a sweep's critical path get their SMs first
+    int lo = 0, hi = 0;
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const bool prio = !(getenv("GLRMB200_NO_PRIORITY") && atoi(getenv("GLRMB200_NO_PRIORITY"))) && hi < lo;
+    const int p_cluster = prio ? hi : 0, p_cta = prio ? std::min(lo, hi + 1) : 0, p_warp = prio ? std::min(lo, hi + 2) : 0;
+    CUDA_OK(cudaStreamCreateWithPriority(&E->stream, cudaStreamNonBlocking, p_cta));
+    CUDA_OK(cudaStreamCreateWithPriority(&E->tier_stream[0], cudaStreamNonBlocking, p_cluster));
+    CUDA_OK(cudaStreamCreateWithPriority(&E->tier_stream[1], cudaStreamNonBlocking, p_cluster));
+    CUDA_OK(cudaStreamCreateWithPriority(&E->tier_stream[2], cudaStreamNonBlocking, p_warp));
+  }
   CUDA_OK(cudaEventCreateWithFlags(&E->ev_fork, cudaEventDisableTiming));
-  CUDA_OK(cudaEventCreateWithFlags(&E->ev_join, cudaEventDisableTiming));
+  for (int i = 0; i < 3; ++i) CUDA_OK(cudaEventCreateWithFlags(&E->ev_join[i], cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&E->ev_base));
   CUDA_OK(cudaEventCreate(&E->ev_aux));
   if ((rc = dalloc(&E->d_scalars, 4, E->stream))) return rc;
@@ -918,8 +967,10 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
 
   if ((rc = upload(&E->d_loss_code, P->loss_code, (size_t)n, E->stream))) return rc;
   if ((rc = upload(&E->d_loss_param, P->loss_param, (size_t)n * GLRMB200_LOSS_NPARAM, E->stream))) return rc;
-  if ((rc = setup_regs(E, R, P->rx_count, P->rx_code, P->rx_param, false))) return rc;
-  if ((rc = setup_regs(E, C, P->ry_count, P->ry_code, P->ry_param, true))) return rc;
+  if ((rc = setup_regs(E, R, P->rx_count, P->rx_code, P->rx_param, false, P->rx_payload_ptr, P->rx_payload))) return rc;
+  if ((rc = setup_regs(E, C, P->ry_count, P->ry_code, P->ry_param, true, P->ry_payload_ptr, P->ry_payload))) return rc;
+  if (E->has_vec && (R.d_reg_payload_ptr || C.d_reg_payload_ptr))
+    return fail(GLRMB200_E_UNSUPPORTED, "fixed_latent_features / RemQuadReg together with vector-valued losses have no device implementation");
   E->all_rows_vec.assign(E->has_vec ? (size_t)m : 0, 1);   // with block columns every row takes the vector path
   std::vector<char>& all_rows_vec = E->all_rows_vec;
   if (E->has_vec || want_dense) {
@@ -1576,7 +1627,7 @@ extern "C" int glrmb200_set_reg_scale(glrmb200_handle E, double newscale) {
   for (Side* S : {&E->rows, &E->cols}) {
     for (size_t i = 0; i < S->h_reg_code.size(); ++i) {
       const int base = S->h_reg_code[i] & GLRMB200_REG_BASE_MASK;
-      if (base == GLRMB200_REG_QUAD || base == GLRMB200_REG_ONE) S->h_reg_param[i * GLRMB200_REG_NPARAM] = newscale;
+      if (base == GLRMB200_REG_QUAD || base == GLRMB200_REG_ONE || base == GLRMB200_REG_REM_QUAD) S->h_reg_param[i * GLRMB200_REG_NPARAM] = newscale;
     }
     CUDA_OK(cudaMemcpyAsync(S->d_reg_param, S->h_reg_param.data(), S->h_reg_param.size() * sizeof(double), cudaMemcpyHostToDevice, E->stream));
   }

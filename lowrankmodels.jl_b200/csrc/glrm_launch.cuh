@@ -6,7 +6,9 @@
 
 namespace glrm {
 
-struct Streams { cudaStream_t main, side; cudaEvent_t fork, join; };
+// main: where the sweep is ordered; tier[0..2]: streams of the cluster-8 / cluster-4 / warp tiers (nullptr: run on main);
+// join[i] pairs with tier[i]
+struct Streams { cudaStream_t main; cudaStream_t tier[3]; cudaEvent_t fork; cudaEvent_t join[3]; };
 
 // tier sizes of one sweep: schedule = [cluster8 | cluster4 | CTA | warp] (degree-sorted, heaviest first)
 struct TierCounts { int64_t n_cluster16, n_cluster4, n_heavy, n_light; };

@@ -29,21 +29,29 @@ static cudaError_t launch_cluster(const SweepArgs& K, int64_t n_units, cudaStrea
   return cudaLaunchKernelEx(&cfg, kern, K);
 }
 
-// the tiers of a sweep touch disjoint units: the warp tier is forked onto the side stream so it fills the SMs the
-// CTA / cluster tiers leave idle in their tails, and joined back before anything else is enqueued
+// The tiers of a sweep touch disjoint units, so each tier is launched on its own stream and they all start together: the
+// heaviest units (cluster tiers, LPT) no longer delay the CTA tier behind them, and the warp tier fills the SMs the others
+// leave idle.  The side streams carry descending priorities (cluster tiers first) so that, when CTAs of several tiers
+// compete for an SM, the units on the critical path are placed first.  Everything is joined back into `main`.
 template <int G, int R, int LOSS>
 static cudaError_t launch_tile(const SweepArgs& A0, const TierCounts& tc, const Streams& st, int64_t* launches) {
-  const int64_t n_big = tc.n_cluster16 + tc.n_cluster4 + tc.n_heavy;
-  const bool both = n_big > 0 && tc.n_light > 0 && st.side;
-  if (both) {
-    cudaEventRecord(st.fork, st.main);
-    cudaStreamWaitEvent(st.side, st.fork, 0);
+  const int64_t counts[4] = {tc.n_cluster16, tc.n_cluster4, tc.n_heavy, tc.n_light};
+  // stream of each tier: the CTA tier stays on main; a tier with no side stream, or alone in the sweep, runs on main too
+  cudaStream_t where[4] = {st.tier[0], st.tier[1], st.main, st.tier[2]};
+  int n_tiers = 0;
+  for (int i = 0; i < 4; ++i) n_tiers += counts[i] > 0;
+  bool forked[4] = {false, false, false, false};
+  for (int i = 0; i < 4; ++i) {
+    if (where[i] == nullptr || n_tiers < 2) where[i] = st.main;
+    forked[i] = counts[i] > 0 && where[i] != st.main;
   }
+  if (forked[0] || forked[1] || forked[3]) cudaEventRecord(st.fork, st.main);
+  for (int i = 0; i < 4; ++i) if (forked[i]) cudaStreamWaitEvent(where[i], st.fork, 0);
   const int32_t* order = A0.order;
   if (tc.n_cluster16 > 0) {                  // heaviest units first (LPT): a cluster of 8 CTAs per unit
     SweepArgs K = A0;
     K.order = order; K.n_units = tc.n_cluster16;
-    cudaError_t ce = launch_cluster<G, R, LOSS, CLUSTER_CTAS_BIG>(K, tc.n_cluster16, st.main);
+    cudaError_t ce = launch_cluster<G, R, LOSS, CLUSTER_CTAS_BIG>(K, tc.n_cluster16, where[0]);
     if (ce != cudaSuccess) return ce;
     ++*launches;
     order += tc.n_cluster16;
@@ -51,7 +59,7 @@ static cudaError_t launch_tile(const SweepArgs& A0, const TierCounts& tc, const 
   if (tc.n_cluster4 > 0) {
     SweepArgs K = A0;
     K.order = order; K.n_units = tc.n_cluster4;
-    cudaError_t ce = launch_cluster<G, R, LOSS, CLUSTER_CTAS>(K, tc.n_cluster4, st.main);
+    cudaError_t ce = launch_cluster<G, R, LOSS, CLUSTER_CTAS>(K, tc.n_cluster4, where[1]);
     if (ce != cudaSuccess) return ce;
     ++*launches;
     order += tc.n_cluster4;
@@ -59,7 +67,7 @@ static cudaError_t launch_tile(const SweepArgs& A0, const TierCounts& tc, const 
   if (tc.n_heavy > 0) {
     SweepArgs H = A0;
     H.order = order; H.n_units = tc.n_heavy;
-    sweep_cta_kernel<G, R, LOSS><<<(unsigned)tc.n_heavy, WARPS_PER_CTA_HEAVY * 32, 0, st.main>>>(H);
+    sweep_cta_kernel<G, R, LOSS><<<(unsigned)tc.n_heavy, WARPS_PER_CTA_HEAVY * 32, 0, where[2]>>>(H);
     ++*launches;
     order += tc.n_heavy;
   }
@@ -67,12 +75,14 @@ static cudaError_t launch_tile(const SweepArgs& A0, const TierCounts& tc, const 
     SweepArgs L = A0;
     L.order = order; L.n_units = tc.n_light;
     const int64_t grid = (tc.n_light + WARPS_PER_CTA_LIGHT - 1) / WARPS_PER_CTA_LIGHT;
-    sweep_warp_kernel<G, R, LOSS><<<(unsigned)grid, WARPS_PER_CTA_LIGHT * 32, 0, both ? st.side : st.main>>>(L);
+    sweep_warp_kernel<G, R, LOSS><<<(unsigned)grid, WARPS_PER_CTA_LIGHT * 32, 0, where[3]>>>(L);
     ++*launches;
   }
-  if (both) {
-    cudaEventRecord(st.join, st.side);
-    cudaStreamWaitEvent(st.main, st.join, 0);
+  const int jn[4] = {0, 1, -1, 2};
+  for (int i = 0; i < 4; ++i) {
+    if (!forked[i]) continue;
+    cudaEventRecord(st.join[jn[i]], where[i]);
+    cudaStreamWaitEvent(st.main, st.join[jn[i]], 0);
   }
   return cudaGetLastError();
 }

@@ -16,7 +16,7 @@ import numpy as np
 from . import _abi
 from .glrm import GLRM, Repeated
 from .losses import encode_losses, get_yidxs
-from .regularizers import encode_regs
+from .regularizers import encode_payloads, encode_regs
 
 
 class EncodedProblem:
@@ -37,10 +37,14 @@ class EncodedProblem:
 
 
 def _encode_reg_list(regs):
+    """-> (codes, params, payload_ptr | None, payload | None)"""
     if isinstance(regs, Repeated):
         code, p = regs.item.encode()
-        return np.array([code], dtype=np.int32), p.reshape(1, -1).copy()
-    return encode_regs(regs)
+        return (np.array([code], dtype=np.int32), p.reshape(1, -1).copy()) + encode_payloads([regs.item])
+    codes, params = encode_regs(regs)
+    if len(codes) == 1 and len(regs) > 1:
+        return (codes, params, None, None)
+    return (codes, params) + encode_payloads(regs)
 
 
 def _check_labels(glrm: GLRM, cols, vals):
@@ -78,13 +82,23 @@ def encode_problem(glrm: GLRM, validate=True) -> EncodedProblem:
         lcodes, lparams = encode_losses(glrm.losses)
     ep.set("loss_code", np.ascontiguousarray(lcodes), _abi.i32ptr)
     ep.set("loss_param", np.ascontiguousarray(lparams), _abi.dptr)
-    rxc, rxp = _encode_reg_list(glrm.rx)
-    ryc, ryp = _encode_reg_list(glrm.ry)
+    rxc, rxp, rxpp, rxpv = _encode_reg_list(glrm.rx)
+    ryc, ryp, rypp, rypv = _encode_reg_list(glrm.ry)
     s.rx_count, s.ry_count = len(rxc), len(ryc)
     ep.set("rx_code", rxc, _abi.i32ptr)
     ep.set("rx_param", np.ascontiguousarray(rxp), _abi.dptr)
     ep.set("ry_code", ryc, _abi.i32ptr)
     ep.set("ry_param", np.ascontiguousarray(ryp), _abi.dptr)
+    # vector payloads (fixed_latent_features.y, RemQuadReg.m): their lengths are checked like the reference's indexing would
+    for side, ptr, vals, regs in (("rx", rxpp, rxpv, glrm.rx), ("ry", rypp, rypv, glrm.ry)):
+        if ptr is None:
+            continue
+        for r in (regs.item,) if isinstance(regs, Repeated) else regs:
+            pay = r.payload()
+            if pay is not None and (len(pay) > glrm.k or (type(r).__name__ == "RemQuadReg" and len(pay) != glrm.k)):
+                raise ValueError(f"DimensionMismatch: {type(r).__name__} payload of length {len(pay)} with k = {glrm.k}")
+        ep.set(side + "_payload_ptr", ptr, _abi.i64ptr)
+        ep.set(side + "_payload", vals if len(vals) else np.zeros(1), _abi.dptr)
 
     feats, exs = glrm.observed_features, glrm.observed_examples
     if feats.full is not None and exs.full is not None:

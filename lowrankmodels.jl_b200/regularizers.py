@@ -12,9 +12,10 @@ from dataclasses import dataclass
 import numpy as np
 
 REG_ZERO, REG_QUAD, REG_QUAD_CONSTRAINT, REG_ONE, REG_NONNEG, REG_NONNEG_ONE = 0, 1, 2, 3, 4, 5
-REG_ONE_SPARSE, REG_KSPARSE, REG_UNIT_ONE_SPARSE, REG_SIMPLEX = 6, 7, 8, 9
+REG_ONE_SPARSE, REG_KSPARSE, REG_UNIT_ONE_SPARSE, REG_SIMPLEX, REG_REM_QUAD = 6, 7, 8, 9, 10
 REG_LASTENTRY1, REG_LASTENTRY_UNPENALIZED = 0x100, 0x200
 REG_ORDINAL, REG_MNL_ORDINAL = 0x400, 0x800
+REG_FIXED_FIRST, REG_FIXED_LAST = 0x1000, 0x2000
 REG_NPARAM = 4
 
 
@@ -31,6 +32,10 @@ class Regularizer:  # abstract type Regularizer (regularizers.jl:30)
         p = np.zeros(REG_NPARAM)
         p[0] = self._p0()
         return int(self.code), p
+
+    def payload(self):
+        """Vector payload travelling next to the descriptor row (fixed_latent_features.y, RemQuadReg.m), or None."""
+        return None
 
     def copy(self):
         return _copy.deepcopy(self)
@@ -152,19 +157,44 @@ class lastentry_unpenalized(_Wrapper):  # regularizers.jl:178-189
     flag = REG_LASTENTRY_UNPENALIZED
 
 
-# Present in the reference but without a device implementation yet:
-class _Unsupported(Regularizer):
-    def __init__(self, *a, **kw):
-        self.args = a
-        self.kwargs = kw
+class _FixedWrapper(_Wrapper):
+    """fixed_latent_features / fixed_last_latent_features (regularizers.jl:193-231): n = len(y) entries of the factor column
+    are pinned to y, the inner regularizer r sees the rest."""
+
+    def __init__(self, r, y=None):
+        if y is None:                       # FixedLatentFeaturesConstraint(y): standalone use, inner = ZeroReg (:199,220)
+            r, y = ZeroReg(), r
+        super().__init__(r)
+        self.y = np.ascontiguousarray(y, dtype=np.float64).ravel()
+        self.n = len(self.y)
+
+    def encode(self):
+        if isinstance(self.r, _Wrapper) or self.r.payload() is not None:
+            raise ValueError(f"{type(self).__name__} around {type(self.r).__name__} has no device implementation")
+        code, p = self.r.encode()
+        return code | self.flag, p
+
+    def payload(self):
+        return self.y
+
+    def __repr__(self):
+        return f"{type(self).__name__}({self.r!r}, n={self.n})"
 
 
-class fixed_latent_features(_Unsupported):  # regularizers.jl:193-210
-    pass
+class fixed_latent_features(_FixedWrapper):  # regularizers.jl:193-210
+    flag = REG_FIXED_FIRST
 
 
-class fixed_last_latent_features(_Unsupported):  # regularizers.jl:214-231
-    pass
+class fixed_last_latent_features(_FixedWrapper):  # regularizers.jl:214-231
+    flag = REG_FIXED_LAST
+
+
+def FixedLatentFeaturesConstraint(y):  # regularizers.jl:199
+    return fixed_latent_features(ZeroReg(), y)
+
+
+def FixedLastLatentFeaturesConstraint(y):  # regularizers.jl:220
+    return fixed_last_latent_features(ZeroReg(), y)
 
 
 class OrdinalReg(_Wrapper):  # regularizers.jl:356-380 (block regularizer of the ordinal losses; ry only)
@@ -175,8 +205,23 @@ class MNLOrdinalReg(_Wrapper):  # regularizers.jl:385-407
     flag = REG_MNL_ORDINAL
 
 
-class RemQuadReg(_Unsupported):  # regularizers.jl:412-423
-    pass
+class RemQuadReg(Regularizer):  # regularizers.jl:412-423: quadratic regularization around a non-zero mean m
+    code = REG_REM_QUAD
+
+    def __init__(self, scale_or_m, m=None):
+        if m is None:                       # RemQuadReg(m) = RemQuadReg(1, m) (:416)
+            scale_or_m, m = 1.0, scale_or_m
+        self.scale = float(scale_or_m)
+        self.m = np.ascontiguousarray(m, dtype=np.float64).ravel()
+
+    def _p0(self):
+        return self.scale
+
+    def payload(self):
+        return self.m
+
+    def __repr__(self):
+        return f"RemQuadReg({self.scale}, len(m)={len(self.m)})"
 
 
 def encode_regs(regs):
@@ -192,6 +237,19 @@ def encode_regs(regs):
         rows.append(cache[key])
     codes = np.fromiter((c for c, _ in rows), dtype=np.int32, count=cnt)
     params = np.stack([p for _, p in rows]) if cnt else np.zeros((0, REG_NPARAM))
-    if cnt > 1 and np.all(codes == codes[0]) and np.all(params == params[0]):
+    has_payload = any(r.payload() is not None for r in regs)
+    if cnt > 1 and not has_payload and np.all(codes == codes[0]) and np.all(params == params[0]):
         return codes[:1].copy(), params[:1].copy()
     return codes, params
+
+
+def encode_payloads(regs):
+    """-> (ptr int64[count+1], values float64[...]) or (None, None) when no regularizer carries a vector payload."""
+    pays = [r.payload() for r in regs]
+    if all(p is None for p in pays):
+        return None, None
+    lens = np.fromiter((0 if p is None else len(p) for p in pays), dtype=np.int64, count=len(pays))
+    ptr = np.zeros(len(pays) + 1, dtype=np.int64)
+    np.cumsum(lens, out=ptr[1:])
+    vals = np.concatenate([p for p in pays if p is not None]) if ptr[-1] else np.zeros(0)
+    return ptr, np.ascontiguousarray(vals, dtype=np.float64)

@@ -189,9 +189,10 @@ def config3(scale=1, seed=1, k=50):
                 X0=normal_matrix(seed, 3, k, m), Y0=normal_matrix(seed, 4, k, n))
 
 
-def config4(scale=1, seed=1, k=20, levels=5):
-    """C4: heterogeneous columns, fully observed: 50 % QuadLoss, 30 % HingeLoss, 20 % MultinomialLoss(5)."""
-    m = 1_000_000 // scale
+def config4(scale=1, seed=1, k=20, levels=5, rows=None):
+    """C4: heterogeneous columns, fully observed: 50 % QuadLoss, 30 % HingeLoss, 20 % MultinomialLoss(5).
+    `rows`: number of rows instead of 1e6 / scale (same generator, same columns) — the parity twin of the full-size run."""
+    m = rows if rows is not None else 1_000_000 // scale
     n = 1_000 // scale
     nq, nh = n // 2, (n * 3) // 10
     nm = n - nq - nh
@@ -208,9 +209,10 @@ def config4(scale=1, seed=1, k=20, levels=5):
                 levels=levels, d=d, X0=normal_matrix(seed, 3, k, m), Y0=normal_matrix(seed, 4, k, d))
 
 
-def config5(scale=1, seed=1, k=100, n=128, centroids=100):
-    """C5: k-means path, A_i = c_{z_i} + 0.1 eps; QuadLoss, rx = UnitOneSparseConstraint, ry = ZeroReg."""
-    m = 10_000_000 // scale
+def config5(scale=1, seed=1, k=100, n=128, centroids=100, rows=None):
+    """C5: k-means path, A_i = c_{z_i} + 0.1 eps; QuadLoss, rx = UnitOneSparseConstraint, ry = ZeroReg.
+    `rows`: number of rows instead of 1e7 / scale (same generator and centroids)."""
+    m = rows if rows is not None else 10_000_000 // scale
     Cn = normal_matrix(seed, 41, centroids, n)
     z = np.minimum((uniform(seed, 42, np.arange(m)) * centroids).astype(np.int64), centroids - 1)
     A = np.empty((m, n), order="F")

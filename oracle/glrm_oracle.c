@@ -459,9 +459,23 @@ static void base_reg_prox(int base, const double* p, double* v, int64_t L, doubl
 }
 
 /* wrappers lastentry1 / lastentry_unpenalized (regularizers.jl:163-189): the inner regularizer
- * sees rows 1..k-1 of every column of the block. */
-static double reg_eval(int code, const double* p, const double* v, int64_t k, int64_t D) {
+ * sees rows 1..k-1 of every column of the block.  pay / npay: the regularizer's vector payload (fixed_latent_features.y,
+ * fixed_last_latent_features.y, RemQuadReg.m), NULL / 0 otherwise. */
+static double reg_eval_p(int code, const double* p, const double* v, int64_t k, int64_t D, const double* pay, int64_t npay) {
   const int base = code & GLRMB200_REG_BASE_MASK;
+  if (code & GLRMB200_REG_FIXED_FIRST) {                                        /* :208: a[1:n]==y ? evaluate(r.r, a[n+1:end]) : Inf */
+    for (int64_t i = 0; i < npay; ++i) if (v[i] != pay[i]) return INFINITY;
+    return base_reg_eval(base, p, v + npay, k - npay);
+  }
+  if (code & GLRMB200_REG_FIXED_LAST) {                                         /* :230: a[k-n+1:end]==y ? evaluate(r.r, a[1:k-n]) : Inf */
+    for (int64_t i = 0; i < npay; ++i) if (v[k - npay + i] != pay[i]) return INFINITY;
+    return base_reg_eval(base, p, v, k - npay);
+  }
+  if (base == GLRMB200_REG_REM_QUAD) {                                          /* :423: scale * sum(abs2, a - m) */
+    double s = 0;
+    for (int64_t i = 0; i < k * D; ++i) { const double t = v[i] - pay[i]; s += t * t; }
+    return p[0] * s;
+  }
   if (code & (GLRMB200_REG_ORDINAL | GLRMB200_REG_MNL_ORDINAL))                 /* regularizers.jl:378,405 */
     return base_reg_eval(base, p, v, k - 1);                                    /* evaluate(r.r, a[1:end-1,1]) */
   if (code & (GLRMB200_REG_LASTENTRY1 | GLRMB200_REG_LASTENTRY_UNPENALIZED)) {
@@ -476,8 +490,26 @@ static double reg_eval(int code, const double* p, const double* v, int64_t k, in
   return base_reg_eval(base, p, v, k * D);
 }
 
-static void reg_prox(int code, const double* p, double* v, int64_t k, int64_t D, double alpha) {
+static void reg_prox_p(int code, const double* p, double* v, int64_t k, int64_t D, double alpha, const double* pay, int64_t npay) {
   const int base = code & GLRMB200_REG_BASE_MASK;
+  if (code & GLRMB200_REG_FIXED_FIRST) {                                        /* :203: [r.y; prox(r.r, u[n+1:end], alpha)] */
+    base_reg_prox(base, p, v + npay, k - npay, alpha);
+    for (int64_t i = 0; i < npay; ++i) v[i] = pay[i];
+    return;
+  }
+  if (code & GLRMB200_REG_FIXED_LAST) {                                         /* :223: [prox(r.r, u[n+1:end], alpha); r.y]  (sic) */
+    double* tmp = (double*)malloc(sizeof(double) * (size_t)(k - npay + 1));
+    memcpy(tmp, v + npay, sizeof(double) * (size_t)(k - npay));
+    base_reg_prox(base, p, tmp, k - npay, alpha);
+    memcpy(v, tmp, sizeof(double) * (size_t)(k - npay));
+    for (int64_t i = 0; i < npay; ++i) v[k - npay + i] = pay[i];
+    free(tmp);
+    return;
+  }
+  if (base == GLRMB200_REG_REM_QUAD) {                                          /* :417-418: (u + 2 alpha scale m) / (1 + 2 alpha scale) */
+    for (int64_t i = 0; i < k * D; ++i) v[i] = (v[i] + 2 * alpha * p[0] * pay[i]) / (1 + 2 * alpha * p[0]);
+    return;
+  }
   if (code & (GLRMB200_REG_ORDINAL | GLRMB200_REG_MNL_ORDINAL)) {               /* regularizers.jl:361-377,390-404 */
     double* um = (double*)malloc(sizeof(double) * (size_t)k);
     for (int64_t i = 0; i < k - 1; ++i) {                                       /* um = mean(u[1:end-1,:], dims=2) */
@@ -516,11 +548,17 @@ double oracle_loss_eval(int code, const double* p, const double* u, int D, doubl
 void oracle_loss_grad(int code, const double* p, const double* u, int D, double a, double* g, int* err) {
   int e = 0; loss_grad(code, p, u, D, a, g, &e); if (err) *err = e;
 }
+double oracle_reg_eval_payload(int code, const double* p, const double* v, int64_t k, int64_t D, const double* pay, int64_t npay) {
+  return reg_eval_p(code, p, v, k, D, pay, npay);
+}
+void oracle_reg_prox_payload(int code, const double* p, double* v, int64_t k, int64_t D, double alpha, const double* pay, int64_t npay) {
+  reg_prox_p(code, p, v, k, D, alpha, pay, npay);
+}
 double oracle_reg_eval(int code, const double* p, const double* v, int64_t k, int64_t D) {
-  return reg_eval(code, p, v, k, D);
+  return reg_eval_p(code, p, v, k, D, NULL, 0);
 }
 void oracle_reg_prox(int code, const double* p, double* v, int64_t k, int64_t D, double alpha) {
-  reg_prox(code, p, v, k, D, alpha);
+  reg_prox_p(code, p, v, k, D, alpha, NULL, 0);
 }
 
 /* ---- problem view --------------------------------------------------------------------------- */
@@ -569,6 +607,21 @@ static inline const int32_t* rx_code(const view_t* V, int64_t e) { return V->P->
 static inline const double* rx_par(const view_t* V, int64_t e) { return V->P->rx_param + (V->P->rx_count == 1 ? 0 : e) * GLRMB200_REG_NPARAM; }
 static inline const int32_t* ry_code(const view_t* V, int64_t f) { return V->P->ry_code + (V->P->ry_count == 1 ? 0 : f); }
 static inline const double* ry_par(const view_t* V, int64_t f) { return V->P->ry_param + (V->P->ry_count == 1 ? 0 : f) * GLRMB200_REG_NPARAM; }
+/* vector payloads (fixed_latent_features.y, RemQuadReg.m): regularizers.jl:193-231,412-423 */
+static inline const double* rx_pay(const view_t* V, int64_t e) {
+  return V->P->rx_payload_ptr ? V->P->rx_payload + V->P->rx_payload_ptr[V->P->rx_count == 1 ? 0 : e] : NULL;
+}
+static inline int64_t rx_npay(const view_t* V, int64_t e) {
+  const int64_t i = V->P->rx_count == 1 ? 0 : e;
+  return V->P->rx_payload_ptr ? V->P->rx_payload_ptr[i + 1] - V->P->rx_payload_ptr[i] : 0;
+}
+static inline const double* ry_pay(const view_t* V, int64_t f) {
+  return V->P->ry_payload_ptr ? V->P->ry_payload + V->P->ry_payload_ptr[V->P->ry_count == 1 ? 0 : f] : NULL;
+}
+static inline int64_t ry_npay(const view_t* V, int64_t f) {
+  const int64_t i = V->P->ry_count == 1 ? 0 : f;
+  return V->P->ry_payload_ptr ? V->P->ry_payload_ptr[i + 1] - V->P->ry_payload_ptr[i] : 0;
+}
 
 static inline double dotk(const double* a, const double* b, int64_t k) {
   double s = 0;
@@ -587,19 +640,21 @@ static cblas_dgemm64_fn g_dgemm = NULL;
 void oracle_set_dgemm(void* fn) { g_dgemm = (cblas_dgemm64_fn)fn; }
 int oracle_has_dgemm(void) { return g_dgemm != NULL; }
 
-static void gemm_xty(const view_t* V, const double* X, const double* Y, double* XY) {
-  const int64_t m = V->m, d = V->d, k = V->k;
+/* out[(e - e0) * (c1 - c0) + (c - c0)] = x_e . y_c for rows e0 <= e < e1, embedding columns c0 <= c < c1 */
+static void gemm_part(const view_t* V, const double* X, const double* Y, double* out, int64_t e0, int64_t e1, int64_t c0, int64_t c1) {
+  const int64_t k = V->k, nc = c1 - c0, nr = e1 - e0;
+  if (nc <= 0 || nr <= 0) return;
   if (g_dgemm) {
-    /* XY (row-major m x d) == column-major d x m == Y' X: CblasColMajor=102, CblasTrans=112, CblasNoTrans=111 */
-    g_dgemm(102, 112, 111, d, m, k, 1.0, Y, k, X, k, 0.0, XY, d);
+    /* out (row-major nr x nc) == column-major nc x nr == Y[:,c0:c1]' X[:,e0:e1]: CblasColMajor=102, CblasTrans=112, CblasNoTrans=111 */
+    g_dgemm(102, 112, 111, nc, nr, k, 1.0, Y + c0 * k, k, X + e0 * k, k, 0.0, out, nc);
     return;
   }
 #pragma omp parallel for schedule(static)
-  for (int64_t eb = 0; eb < m; eb += 8) {
-    const int64_t e1 = eb + 8 < m ? eb + 8 : m;
-    for (int64_t c = 0; c < d; ++c) {
+  for (int64_t eb = e0; eb < e1; eb += 8) {
+    const int64_t ee = eb + 8 < e1 ? eb + 8 : e1;
+    for (int64_t c = c0; c < c1; ++c) {
       const double* y = Y + c * k;
-      for (int64_t e = eb; e < e1; ++e) XY[e * d + c] = dotk(X + e * k, y, k);
+      for (int64_t e = eb; e < ee; ++e) out[(e - e0) * nc + (c - c0)] = dotk(X + e * k, y, k);
     }
   }
 }
@@ -624,7 +679,7 @@ static double row_objective(const view_t* V, int64_t e, const double* x, const d
       obj += loss_eval(V->P->loss_code[f], lp, u, D, a, err);
     }
   }
-  obj += reg_eval(*rx_code(V, e), rx_par(V, e), x, k, 1);
+  obj += reg_eval_p(*rx_code(V, e), rx_par(V, e), x, k, 1, rx_pay(V, e), rx_npay(V, e));
   return obj;
 }
 
@@ -650,7 +705,7 @@ static double col_objective(const view_t* V, int64_t f, const double* yblk, cons
       obj += loss_eval(V->P->loss_code[f], lp, u, D, a, err);
     }
   }
-  obj += reg_eval(*ry_code(V, f), ry_par(V, f), yblk, k, D);
+  obj += reg_eval_p(*ry_code(V, f), ry_par(V, f), yblk, k, D, ry_pay(V, f), ry_npay(V, f));
   return obj;
 }
 
@@ -674,14 +729,14 @@ static double full_objective(const view_t* V, const double* X, const double* Y, 
       for (int c = 0; c < D; ++c) u[c] = dotk(X + e * k, yblk + c * k, k);
       acc += loss_eval(V->P->loss_code[f], lp, u, D, a, &le);
     }
-    if (include_reg) acc += reg_eval(*ry_code(V, f), ry_par(V, f), yblk, k, D);
+    if (include_reg) acc += reg_eval_p(*ry_code(V, f), ry_par(V, f), yblk, k, D, ry_pay(V, f), ry_npay(V, f));
     total += acc;
     errs |= le;
   }
   if (include_reg) {
     double pen = 0.0;
 #pragma omp parallel for schedule(static) reduction(+ : pen)
-    for (int64_t e = 0; e < V->m; ++e) pen += reg_eval(*rx_code(V, e), rx_par(V, e), X + e * k, k, 1);
+    for (int64_t e = 0; e < V->m; ++e) pen += reg_eval_p(*rx_code(V, e), rx_par(V, e), X + e * k, k, 1, rx_pay(V, e), rx_npay(V, e));
     total += pen;
   }
   if (errs) *err = errs;
@@ -703,12 +758,15 @@ double oracle_objective(const glrmb200_problem* P, const double* X, const double
  * alpharow/alphacol (optional, may be NULL) receive the final step sizes; trials[2] (optional)
  * the number of line-search trial evaluations in X and Y sweeps.
  * returns 0, or 1 label error, 2 unknown loss, 3 dim too large, 4 bad problem, 5 cap too small. */
-int oracle_fit(const glrmb200_problem* P, const glrmb200_params* prm, double* X, double* Y,
-               double* ch_objective, double* ch_seconds, int32_t cap, int32_t* n_recorded,
-               int32_t mode, int32_t nthreads, double* alpharow_out, double* alphacol_out,
-               int64_t* trials) {
+static int fit_impl(const glrmb200_problem* P, const glrmb200_params* prm, double* X, double* Y,
+                    double* ch_objective, double* ch_seconds, int32_t cap, int32_t* n_recorded,
+                    int32_t mode, int32_t nthreads, double* alpharow_out, double* alphacol_out,
+                    int64_t* trials, int64_t rb, int64_t re, int64_t cb, int64_t ce) {
   view_t V;
   if (view_init(&V, P)) return 4;
+  if (rb < 0) { rb = 0; re = V.m; cb = 0; ce = V.n; }
+  if (rb > re || re > V.m || cb > ce || ce > V.n) { view_free(&V); return 4; }
+  const int full = (rb == 0 && re == V.m && cb == 0 && ce == V.n);
   if (cap < prm->max_iter + 1) { view_free(&V); return 5; }
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
@@ -721,12 +779,21 @@ int oracle_fit(const glrmb200_problem* P, const glrmb200_params* prm, double* X,
   int err = 0;
   int64_t tx = 0, ty = 0;
 
-  double* XY = NULL;
+  /* the product X'Y (:65-66).  Unit sample (bench.py's bounded CPU step): only the rows [rb,re) are swept in X and the
+   * columns [cb,ce) in Y, so only its rows rb:re (XYr) and its columns of cb:ce (XYc) are ever read; each is refreshed
+   * where the reference refreshes the whole product (:157 after the X sweep feeds the Y sweep, :202 the next X sweep). */
+  double* XYr = NULL; double* XYc = NULL;
+  const int64_t coff = full ? 0 : V.ystart[cb];
+  const int64_t ldc = full ? d : (V.ystart[ce] - V.ystart[cb]);
   if (faithful) {
-    XY = (double*)malloc(sizeof(double) * (size_t)m * (size_t)d);
-    if (!XY) { view_free(&V); return 4; }
-    gemm_xty(&V, X, Y, XY);                                                    /* :65-66 */
+    XYr = (double*)malloc(sizeof(double) * (size_t)(re - rb > 0 ? re - rb : 1) * (size_t)d);
+    XYc = full ? XYr : (double*)malloc(sizeof(double) * (size_t)m * (size_t)(ldc > 0 ? ldc : 1));
+    if (!XYr || !XYc) { view_free(&V); return 4; }
+    gemm_part(&V, X, Y, XYr, rb, re, 0, d);
+    if (!full) gemm_part(&V, X, Y, XYc, 0, m, coff, coff + ldc);
   }
+#define XR(e, col) XYr[((e) - rb) * d + (col)]
+#define XC(e, col) XYc[(e) * ldc + (col) - coff]
   double* alpharow = (double*)malloc(sizeof(double) * (size_t)m);
   double* alphacol = (double*)malloc(sizeof(double) * (size_t)n);
   for (int64_t e = 0; e < m; ++e) alpharow[e] = prm->stepsize;                 /* :69 */
@@ -737,7 +804,7 @@ int oracle_fit(const glrmb200_problem* P, const glrmb200_params* prm, double* X,
   for (int64_t f = 0; f < n; ++f) if (V.dim[f] > maxD) maxD = V.dim[f];
 
   int nrec = 0;
-  ch_objective[nrec] = full_objective(&V, X, Y, 1, &err);                      /* :76 */
+  ch_objective[nrec] = full ? full_objective(&V, X, Y, 1, &err) : 0.0;         /* :76 */
   ch_seconds[nrec++] = 0.0;
   double t0 = now_s();
 
@@ -760,7 +827,7 @@ int oracle_fit(const glrmb200_problem* P, const glrmb200_params* prm, double* X,
     /* STEP 1: X update ------------------------------------------------------------- :117-158 */
     for (int inner = 0; inner < prm->inner_iter_X; ++inner) {
 #pragma omp parallel for schedule(static) reduction(+ : tx) reduction(| : err)
-      for (int64_t e = 0; e < m; ++e) {
+      for (int64_t e = rb; e < re; ++e) {
 #ifdef _OPENMP
         const int tid = omp_get_thread_num();
 #else
@@ -778,7 +845,7 @@ int oracle_fit(const glrmb200_problem* P, const glrmb200_params* prm, double* X,
           const int D = V.dim[f];
           const double* lp = P->loss_param + f * GLRMB200_LOSS_NPARAM;
           double u[ORACLE_MAX_D], cg[ORACLE_MAX_D];
-          if (faithful) for (int c = 0; c < D; ++c) u[c] = XY[e * d + V.ystart[f] + c];
+          if (faithful) for (int c = 0; c < D; ++c) u[c] = XR(e, V.ystart[f] + c);
           else for (int c = 0; c < D; ++c) u[c] = dotk(xe, Y + (V.ystart[f] + c) * k, k);
           loss_grad(P->loss_code[f], lp, u, D, a, cg, &le);                    /* :125 */
           for (int c = 0; c < D; ++c) {                                        /* :127 / :130 */
@@ -793,7 +860,7 @@ int oracle_fit(const glrmb200_problem* P, const glrmb200_params* prm, double* X,
         while (alpharow[e] > prm->min_stepsize) {                              /* :136 */
           const double stepsize = alpharow[e] / l;                             /* :137 */
           for (int64_t r = 0; r < k; ++r) newx[r] += -stepsize * g[r];         /* :140 */
-          reg_prox(*rx_code(&V, e), rx_par(&V, e), newx, k, 1, stepsize);      /* :142 */
+          reg_prox_p(*rx_code(&V, e), rx_par(&V, e), newx, k, 1, stepsize, rx_pay(&V, e), rx_npay(&V, e));      /* :142 */
           tx++;
           if (row_objective(&V, e, newx, Y, faithful, scr_xy[tid], &le) < obj_old) { /* :143 */
             memcpy(xe, newx, sizeof(double) * (size_t)k);                      /* :144 */
@@ -810,12 +877,12 @@ int oracle_fit(const glrmb200_problem* P, const glrmb200_params* prm, double* X,
         }
         err |= le;
       }
-      if (faithful) gemm_xty(&V, X, Y, XY);                                    /* :157 */
+      if (faithful) { if (full) gemm_part(&V, X, Y, XYr, 0, m, 0, d); else gemm_part(&V, X, Y, XYc, 0, m, coff, coff + ldc); }   /* :157 */
     }
     /* STEP 2: Y update ------------------------------------------------------------- :160-203 */
     for (int inner = 0; inner < prm->inner_iter_Y; ++inner) {
 #pragma omp parallel for schedule(static) reduction(+ : ty) reduction(| : err)
-      for (int64_t f = 0; f < n; ++f) {
+      for (int64_t f = cb; f < ce; ++f) {
 #ifdef _OPENMP
         const int tid = omp_get_thread_num();
 #else
@@ -834,7 +901,7 @@ int oracle_fit(const glrmb200_problem* P, const glrmb200_params* prm, double* X,
           col_entry(&V, f, t, &e, &a);
           const double* xe = X + e * k;
           double u[ORACLE_MAX_D], cg[ORACLE_MAX_D];
-          if (faithful) for (int c = 0; c < D; ++c) u[c] = XY[e * d + V.ystart[f] + c];
+          if (faithful) for (int c = 0; c < D; ++c) u[c] = XC(e, V.ystart[f] + c);
           else for (int c = 0; c < D; ++c) u[c] = dotk(xe, yf + c * k, k);
           loss_grad(P->loss_code[f], lp, u, D, a, cg, &le);                    /* :168 */
           for (int c = 0; c < D; ++c) {                                        /* :170 / :173 */
@@ -848,7 +915,7 @@ int oracle_fit(const glrmb200_problem* P, const glrmb200_params* prm, double* X,
         while (alphacol[f] > prm->min_stepsize) {                              /* :179 */
           const double stepsize = alphacol[f] / l;                             /* :180 */
           for (int64_t r = 0; r < k * D; ++r) newy[r] += -stepsize * G[r];     /* :183 */
-          reg_prox(*ry_code(&V, f), ry_par(&V, f), newy, k, D, stepsize);      /* :185 */
+          reg_prox_p(*ry_code(&V, f), ry_par(&V, f), newy, k, D, stepsize, ry_pay(&V, f), ry_npay(&V, f));      /* :185 */
           ty++;
           const double new_obj = col_objective(&V, f, newy, X, faithful, scr_xy[tid], &le); /* :186 */
           if (new_obj < obj_by_col[f]) {                                       /* :187 */
@@ -867,11 +934,11 @@ int oracle_fit(const glrmb200_problem* P, const glrmb200_params* prm, double* X,
         }
         err |= le;
       }
-      if (faithful) gemm_xty(&V, X, Y, XY);                                    /* :202 */
+      if (faithful) gemm_part(&V, X, Y, XYr, rb, re, 0, d);                    /* :202 */
     }
     /* STEP 3: record objective ------------------------------------------------------ :204-208 */
     double obj = 0.0;
-    for (int64_t f = 0; f < n; ++f) obj += obj_by_col[f];                      /* :205 */
+    for (int64_t f = cb; f < ce; ++f) obj += obj_by_col[f];                    /* :205 */
     const double t1 = now_s();
     ch_objective[nrec] = obj;
     ch_seconds[nrec++] = t1 - t0;                                              /* :206-207 */
@@ -887,9 +954,30 @@ int oracle_fit(const glrmb200_problem* P, const glrmb200_params* prm, double* X,
   if (trials) { trials[0] = tx; trials[1] = ty; }
   for (int t = 0; t < nth; ++t) { free(scr_g[t]); free(scr_new[t]); free(scr_xy[t]); }
   free(scr_g); free(scr_new); free(scr_xy);
-  free(alpharow); free(alphacol); free(obj_by_col); free(XY);
+  free(alpharow); free(alphacol); free(obj_by_col);
+  if (XYc != XYr) free(XYc);
+  free(XYr);
+#undef XR
+#undef XC
   view_free(&V);
   return err;
+}
+
+int oracle_fit(const glrmb200_problem* P, const glrmb200_params* prm, double* X, double* Y,
+               double* ch_objective, double* ch_seconds, int32_t cap, int32_t* n_recorded,
+               int32_t mode, int32_t nthreads, double* alpharow_out, double* alphacol_out,
+               int64_t* trials) {
+  return fit_impl(P, prm, X, Y, ch_objective, ch_seconds, cap, n_recorded, mode, nthreads, alpharow_out, alphacol_out,
+                  trials, -1, -1, -1, -1);
+}
+
+/* The same loop over a sample of the units only: rows [rb, re) in the X sweeps, columns [cb, ce) in the Y sweeps; all
+ * other columns of X and Y stay frozen.  bench.py's reference arm times this on the full-size problem (a bounded sample of
+ * the workload); the recorded "objective" is the sampled columns' share and ch_objective[0] is 0. */
+int oracle_fit_units(const glrmb200_problem* P, const glrmb200_params* prm, double* X, double* Y,
+                     double* ch_objective, double* ch_seconds, int32_t cap, int32_t* n_recorded,
+                     int32_t mode, int32_t nthreads, int64_t rb, int64_t re, int64_t cb, int64_t ce, int64_t* trials) {
+  return fit_impl(P, prm, X, Y, ch_objective, ch_seconds, cap, n_recorded, mode, nthreads, NULL, NULL, trials, rb, re, cb, ce);
 }
 
 /* One half-sweep over the units [begin, end) only (sparse-evaluated form): which = 0 updates rows of X
@@ -929,7 +1017,7 @@ int oracle_half_sweep(const glrmb200_problem* P, const glrmb200_params* prm, dou
       while (alpha[e] > prm->min_stepsize) {
         const double stepsize = alpha[e] / l;
         for (int64_t r = 0; r < k; ++r) nw[r] += -stepsize * g[r];
-        reg_prox(*rx_code(&V, e), rx_par(&V, e), nw, k, 1, stepsize);
+        reg_prox_p(*rx_code(&V, e), rx_par(&V, e), nw, k, 1, stepsize, rx_pay(&V, e), rx_npay(&V, e));
         if (row_objective(&V, e, nw, Y, 0, &xy_dummy, &err) < obj_old) {
           memcpy(xe, nw, sizeof(double) * (size_t)k);
           alpha[e] *= 1.05;
@@ -961,7 +1049,7 @@ int oracle_half_sweep(const glrmb200_problem* P, const glrmb200_params* prm, dou
       while (alpha[f] > prm->min_stepsize) {
         const double stepsize = alpha[f] / l;
         for (int64_t r = 0; r < k * D; ++r) nw[r] += -stepsize * g[r];
-        reg_prox(*ry_code(&V, f), ry_par(&V, f), nw, k, D, stepsize);
+        reg_prox_p(*ry_code(&V, f), ry_par(&V, f), nw, k, D, stepsize, ry_pay(&V, f), ry_npay(&V, f));
         const double new_obj = col_objective(&V, f, nw, X, 0, &xy_dummy, &err);
         if (new_obj < obj_by_unit[f]) {
           memcpy(yf, nw, sizeof(double) * (size_t)(k * D));
@@ -1021,7 +1109,7 @@ int oracle_fit_sparse(const glrmb200_problem* P, const glrmb200_sparse_params* s
         const double l = (double)(len + 1);                                    /* :74 */
         for (int64_t r = 0; r < k; ++r) g[r] *= -alpha / l;                    /* :75 */
         for (int64_t r = 0; r < k; ++r) xe[r] += g[r];                         /* :77 */
-        reg_prox(*rx_code(&V, e), rx_par(&V, e), xe, k, 1, alpha / l);         /* :79 */
+        reg_prox_p(*rx_code(&V, e), rx_par(&V, e), xe, k, 1, alpha / l, rx_pay(&V, e), rx_npay(&V, e));         /* :79 */
       }
     }
     for (int inner = 0; inner < sp->inner_iter; ++inner) {                     /* :83 */
@@ -1039,7 +1127,7 @@ int oracle_fit_sparse(const glrmb200_problem* P, const glrmb200_sparse_params* s
         const double l = (double)(len + 1);                                    /* :94 */
         for (int64_t r = 0; r < k; ++r) g[r] *= -alpha / l;                    /* :95 */
         for (int64_t r = 0; r < k; ++r) yf[r] += g[r];                         /* :97 */
-        reg_prox(*ry_code(&V, f), ry_par(&V, f), yf, k, 1, alpha / l);         /* :99 */
+        reg_prox_p(*ry_code(&V, f), ry_par(&V, f), yf, k, 1, alpha / l, ry_pay(&V, f), ry_npay(&V, f));         /* :99 */
       }
     }
     const double obj = full_objective(&V, X, Y, 1, &err);                      /* :102 */

@@ -40,6 +40,9 @@ def lib():
                                  C.POINTER(C.c_int32), C.c_int32, C.c_int32, _dp, _dp,
                                  C.POINTER(C.c_int64)]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_fit_units.restype = C.c_int
+        L.oracle_fit_units.argtypes = [C.c_void_p, C.c_void_p, _dp, _dp, _dp, _dp, C.c_int32, C.POINTER(C.c_int32),
+                                       C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]
         L.oracle_fit_sparse.restype = C.c_int
         L.oracle_fit_sparse.argtypes = [C.c_void_p, C.c_void_p, _dp, _dp, _dp, _dp, C.c_int32, C.POINTER(C.c_int32), _dp]
         L.oracle_half_sweep.restype = C.c_int
@@ -148,6 +151,22 @@ def fit(ep, params_struct, X, Y, mode=1, nthreads=0):
         raise ValueError(f"oracle_fit error {rc}")
     return dict(objective=obj[:nrec.value].copy(), seconds=sec[:nrec.value].copy(), alpharow=ar, alphacol=ac,
                 trials=(trials[0], trials[1]))
+
+
+def fit_units(ep, params_struct, X, Y, rows, cols, mode=0, nthreads=0):
+    """The restated fit! over a sample of the units only: rows [rows[0], rows[1]) in the X sweeps, columns
+    [cols[0], cols[1]) in the Y sweeps, everything else frozen (bench.py's bounded CPU step on the full-size problem).
+    Returns dict(objective, seconds, trials); objective[t] is the sampled columns' share, objective[0] is 0."""
+    assert X.flags.f_contiguous and Y.flags.f_contiguous
+    cap = params_struct.max_iter + 1
+    obj, sec = np.zeros(cap), np.zeros(cap)
+    nrec = C.c_int32(0)
+    trials = (C.c_int64 * 2)()
+    rc = lib().oracle_fit_units(C.addressof(ep.struct), C.addressof(params_struct), _d(X), _d(Y), _d(obj), _d(sec), cap,
+                                C.byref(nrec), mode, nthreads, int(rows[0]), int(rows[1]), int(cols[0]), int(cols[1]), trials)
+    if rc:
+        raise ValueError(f"oracle_fit_units error {rc}")
+    return dict(objective=obj[:nrec.value].copy(), seconds=sec[:nrec.value].copy(), trials=(trials[0], trials[1]))
 
 
 def half_sweep(ep, params_struct, X, Y, alpha, which, begin, end, obj_by_unit):

@@ -260,6 +260,14 @@ def reg_evaluate(r, a):
         return reg_evaluate(r.r, a[:-1, :]) if (a[-1, :] == 1).all() else math.inf
     if name == "lastentry_unpenalized":                                          # :184,187
         return reg_evaluate(r.r, a[:-1] if a.ndim == 1 else a[:-1, :])
+    if name == "fixed_latent_features":                                          # :208
+        n = len(r.y)
+        return reg_evaluate(r.r, a[n:]) if (a[:n] == r.y).all() else math.inf
+    if name == "fixed_last_latent_features":                                     # :230
+        n = len(r.y)
+        return reg_evaluate(r.r, a[:len(a) - n]) if (a[len(a) - n:] == r.y).all() else math.inf
+    if name == "RemQuadReg":                                                     # :423
+        return r.scale * np.sum((a - r.m) ** 2)
     raise NotImplementedError(name)
 
 
@@ -326,6 +334,14 @@ def prox(r, u, alpha):
         if u.ndim == 1:
             return np.concatenate([prox(r.r, u[:-1], alpha), [u[-1]]])
         return np.vstack([prox(r.r, u[:-1, :], alpha), u[-1:, :]])
+    if name == "fixed_latent_features":                                          # :203  [r.y; prox(r.r, u[(r.n+1):end], alpha)]
+        n = len(r.y)
+        return np.concatenate([r.y, prox(r.r, u[n:], alpha)])
+    if name == "fixed_last_latent_features":                                     # :223  [prox(r.r, u[(r.n+1):end], alpha); r.y]  (sic)
+        n = len(r.y)
+        return np.concatenate([prox(r.r, u[n:], alpha), r.y])
+    if name == "RemQuadReg":                                                     # :417-418
+        return (u + 2 * alpha * r.scale * r.m) / (1 + 2 * alpha * r.scale)
     raise NotImplementedError(name)
 
 

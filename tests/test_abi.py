@@ -27,12 +27,12 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/glrm_b200.h but not exported"
     assert sorted(n for n, _, _ in _abi.SYMBOLS) == declared      # the ctypes table mirrors the header
-    assert L.glrmb200_version() == 100
+    assert L.glrmb200_version() == 101
 
 
 def test_struct_layouts_match_header():
     assert C.sizeof(_abi.Params) == 48
-    assert C.sizeof(_abi.Problem) == 8 * 4 + 8 * 2 + 3 * 8 * 2 + 8 + 8 + 6 * 8
+    assert C.sizeof(_abi.Problem) == 8 * 4 + 8 * 2 + 3 * 8 * 2 + 8 + 8 + 6 * 8 + 4 * 8   # + the four payload pointers
     assert C.sizeof(_abi.Profile) == 6 * 8 + 5 * 8 + 8
 
 
@@ -94,6 +94,8 @@ def test_host_mirror_constructor_checks():
     assert g.X.shape == (2, 5)
     p = lrm.ProxGradParams(2.0, inner_iter=3)
     assert (p.inner_iter_X, p.inner_iter_Y, p.min_stepsize, p.max_iter) == (3, 3, 0.02, 100)
-    with pytest.raises(ValueError):
-        lrm.GLRM(A, lrm.QuadLoss(), lrm.RemQuadReg(), lrm.ZeroReg(), 2) and lrm.encode_problem(
-            lrm.GLRM(A, lrm.QuadLoss(), lrm.RemQuadReg(), lrm.ZeroReg(), 2))
+    with pytest.raises(ValueError, match="DimensionMismatch"):                    # RemQuadReg.m must have k entries
+        lrm.encode_problem(lrm.GLRM(A, lrm.QuadLoss(), lrm.RemQuadReg(1.0, np.zeros(3)), lrm.ZeroReg(), 2))
+    with pytest.raises(ValueError):                                              # nested wrappers: no device implementation
+        lrm.encode_problem(lrm.GLRM(A, lrm.QuadLoss(), lrm.fixed_latent_features(lrm.lastentry1(lrm.QuadReg()), [1.0]),
+                                    lrm.ZeroReg(), 2))

@@ -437,6 +437,8 @@ def dense_problem(m=150, n=90, k=7, seed=40, losses=None, rx=None, ry=None, labe
     A = P @ Q + 0.1 * synth.normal_matrix(seed, 3, m, n)
     if labels == "bool":
         A = np.where(A >= 0, 1.0, -1.0)
+    elif labels == "bool01":
+        A = np.where(A >= 0, 1.0, 0.0)
     elif labels == "count":
         A = np.floor(np.abs(A) * 2)
     elif isinstance(labels, int):
@@ -503,6 +505,24 @@ def test_dense_path_heterogeneous_and_vector_losses(orc):
         check(orc, g, lrm.ProxGradParams(max_iter=5), rtol=1e-6, factors=False)
 
 
+@pytest.mark.parametrize("k,m,n", [(20, 40000, 21), (100, 24000, 70), (8, 50000, 130), (33, 30011, 64)])
+def test_dense_path_persistent_tiles(orc, k, m, n):
+    """More row tiles than resident CTAs (every CTA walks several tiles: the A-tile pipeline carries over from one tile to the
+    next), mixed scalar / vector losses, one and two tile buffers, one and two CTAs per SM, a ragged last tile."""
+    lv = 5
+    base = synth.normal_matrix(49, 1, m, 3) @ synth.normal_matrix(49, 2, 3, n) + 0.3 * synth.normal_matrix(49, 3, m, n)
+    nq, nh = n // 2, n // 4
+    A = np.empty((m, n), order="F")
+    A[:, :nq] = base[:, :nq]
+    A[:, nq:nq + nh] = np.where(base[:, nq:nq + nh] >= 0, 1.0, -1.0)
+    A[:, nq + nh:] = np.clip(np.floor(np.abs(base[:, nq + nh:]) * 2) + 1, 1, lv)
+    losses = [lrm.QuadLoss()] * nq + [lrm.HingeLoss()] * nh + [lrm.MultinomialLoss(lv)] * (n - nq - nh)
+    d = sum(l.embedding_dim() for l in losses)
+    g = lrm.GLRM(A, losses, lrm.QuadReg(0.1), lrm.QuadReg(0.1), k, X=0.3 * synth.normal_matrix(49, 4, k, m),
+                 Y=0.3 * synth.normal_matrix(49, 5, k, d))
+    check(orc, g, lrm.ProxGradParams(max_iter=3), rtol=1e-6, factors=False)
+
+
 def test_dense_path_many_chunks_and_inner_iterations(orc):
     """d = 5 * 64 + 7 columns (six chunks), inner_iter = 2, offset wrappers."""
     g = dense_problem(m=70, n=327, k=9, seed=45)
@@ -530,3 +550,76 @@ def test_dense_handle_objective_and_set_obs(orc):
         obj, _ = eng.fit(lrm.ProxGradParams(max_iter=5), X, Y)
         want = run_oracle(orc, sub, lrm.ProxGradParams(max_iter=5))
         assert_traj_close(obj, want["objective"], TIGHT, "dense handle after set_obs")
+
+
+# ---- regularizers with vector payloads (regularizers.jl:193-231,412-423) ---------------------------------------------------
+def test_rem_quad_reg_mult_reg_shape(orc):
+    """test/mult_reg.jl:5-29: one RemQuadReg(50, mean) per row and per column; trajectory vs oracle and the reference's own
+    recovery thresholds."""
+    n = m = 200
+    r, eta, delta = 5, 0.01, 1e-3
+    Um, Vm = synth.normal_matrix(71, 1, r, n), synth.normal_matrix(71, 2, r, m)
+    U = Um + np.sqrt(eta) * synth.normal_matrix(71, 3, r, n)
+    V = Vm + np.sqrt(eta) * synth.normal_matrix(71, 4, r, m)
+    Yobs = U.T @ V + np.sqrt(delta) * synth.normal_matrix(71, 5, n, m)
+    g = lrm.GLRM(np.asfortranarray(Yobs), lrm.QuadLoss(), [lrm.RemQuadReg(50, Um[:, i]) for i in range(n)],
+                 [lrm.RemQuadReg(50, Vm[:, j]) for j in range(m)], r,
+                 X=synth.normal_matrix(71, 6, r, n), Y=synth.normal_matrix(71, 7, r, m))
+    got, _ = check(orc, g, lrm.ProxGradParams(max_iter=100))
+    assert np.mean((U - got["X"]) ** 2) < 1e-3 and np.mean((V - got["Y"]) ** 2) < 1e-3
+
+
+@pytest.mark.parametrize("k,nfix", [(4, 1), (5, 2), (7, 3), (20, 5), (20, 8), (50, 1), (50, 17), (100, 33), (100, 64)])
+def test_fixed_latent_features_every_tile(orc, k, nfix):
+    """fixed_latent_features on the columns and fixed_last_latent_features (restated with the reference's own indexing,
+    regularizers.jl:223) on the rows, for every register tile shape and odd / even pinned lengths; the pinned entries
+    never move (test/fixedfeatures_test.jl asserts exactly that)."""
+    A, obs, X0 = small_sparse(m=70, n=40, k=k, seed=8)
+    Y0 = 0.5 * synth.normal_matrix(72, 1, k, 40)
+    X0 = 0.5 * X0
+    ry = [lrm.fixed_latent_features(lrm.QuadReg(0.1), Y0[:nfix, j].copy()) for j in range(40)]
+    rx = [lrm.fixed_last_latent_features(lrm.QuadReg(0.05), X0[k - nfix:, i].copy()) for i in range(70)]
+    g = lrm.GLRM(A, lrm.QuadLoss(), rx, ry, k, obs=obs, X=X0.copy(), Y=Y0.copy())
+    got, _ = check(orc, g, lrm.ProxGradParams(max_iter=8))
+    assert (got["Y"][:nfix, :] == Y0[:nfix, :]).all() and (got["X"][k - nfix:, :] == X0[k - nfix:, :]).all()
+
+
+@pytest.mark.parametrize("inner", [lrm.ZeroReg(), lrm.NonNegConstraint(), lrm.OneSparseConstraint(), lrm.UnitOneSparseConstraint(),
+                                   lrm.KSparseConstraint(2), lrm.SimplexConstraint(), lrm.QuadConstraint(2.0), lrm.OneReg(0.1)],
+                         ids=lambda r: type(r).__name__)
+def test_fixed_latent_features_inner_regularizers(orc, inner):
+    """The inner regularizer sees only the free entries (reductions, arg-max and sorting run over that sub-range)."""
+    k = 6
+    A, obs, X0 = small_sparse(m=50, n=30, k=k, seed=9)
+    Y0 = np.abs(synth.normal_matrix(73, 1, k, 30))
+    shared = lrm.FixedLatentFeaturesConstraint(np.array([0.25, 0.5]))            # one shared regularizer, inner = ZeroReg
+    ry = [lrm.fixed_latent_features(inner.copy(), Y0[:2, j].copy()) for j in range(30)]
+    g = lrm.GLRM(np.abs(A), lrm.QuadLoss(), shared, ry, k, obs=obs, X=np.abs(X0), Y=Y0.copy())
+    g.X[:2, :] = np.array([[0.25], [0.5]])
+    check(orc, g, lrm.ProxGradParams(max_iter=8), rtol=1e-6, factors=False)
+    rx = [lrm.fixed_last_latent_features(inner.copy(), np.abs(X0[4:, i]).copy()) for i in range(50)]
+    g = lrm.GLRM(np.abs(A), lrm.QuadLoss(), rx, lrm.QuadReg(0.1), k, obs=obs, X=np.abs(X0), Y=Y0.copy())
+    check(orc, g, lrm.ProxGradParams(max_iter=8), rtol=1e-6, factors=False)
+
+
+def test_payload_regularizers_objective_and_reg_scale(orc):
+    """glrmb200_objective with payload regularizers (the penalty kernel walks mixed codes unit by unit) and
+    scale_regularizer! reaching RemQuadReg / the inner regularizer of the fixed wrappers."""
+    k = 5
+    A, obs, X0 = small_sparse(m=40, n=25, k=k, seed=10)
+    Y0 = synth.normal_matrix(74, 1, k, 25)
+    rx = [lrm.RemQuadReg(0.3, X0[:, i] + 0.1) if i % 2 else lrm.QuadReg(0.2) for i in range(40)]
+    ry = [lrm.fixed_latent_features(lrm.OneReg(0.1), Y0[:2, j].copy()) if j % 3 else lrm.NonNegOneReg(0.1) for j in range(25)]
+    g = lrm.GLRM(A, lrm.QuadLoss(), rx, ry, k, obs=obs, X=X0.copy(), Y=np.abs(Y0))
+    ep = lrm.encode_problem(g)
+    with lrm.Engine(g) as eng:
+        want = orc.objective(ep, g.X, g.Y, include_reg=True)
+        got = eng.objective(g.X, g.Y, include_regularization=True)
+        assert abs(got - want) <= 1e-12 * abs(want)
+        eng.set_reg_scale(0.7)
+        lrm.scale_regularizer(g, 0.7)
+        ep2 = lrm.encode_problem(g)
+        want2 = orc.objective(ep2, g.X, g.Y, include_reg=True)
+        got2 = eng.objective(g.X, g.Y, include_regularization=True)
+        assert abs(got2 - want2) <= 1e-12 * abs(want2) and abs(want2 - want) > 1e-6 * abs(want)
+    check(orc, g, lrm.ProxGradParams(max_iter=6), rtol=1e-6, factors=False)

@@ -146,3 +146,63 @@ def test_stopping_rule_fires_after_ten(orc):
     g = glrm_from_config(synth.config1(), lrm.QuadLoss(), lrm.QuadReg(0.1), lrm.QuadReg(0.1))
     res = run_oracle(orc, g, lrm.ProxGradParams(max_iter=100, rel_tol=1e-2))
     assert 12 <= len(res["objective"]) < 101          # i>10 && decrease/obj < rel_tol (proxgrad.jl:211)
+
+
+def test_unit_sample_fit_matches_both_forms_and_freezes_the_rest(orc):
+    """oracle_fit_units (bench.py's bounded CPU step): faithful and sparse-evaluated forms agree on the sampled units,
+    every other column of X and Y is untouched, and the full ranges reproduce oracle_fit."""
+    A, obs, X0 = small_sparse(seed=6)
+    m, n = A.shape
+    g = lrm.GLRM(A, lrm.QuadLoss(), lrm.QuadReg(0.05), lrm.QuadReg(0.05), 4, obs=obs, X=X0,
+                 Y=synth.normal_matrix(9, 3, 4, n))
+    ep = lrm.encode_problem(g)
+    p = lrm.encode_params(lrm.ProxGradParams(max_iter=6, abs_tol=0, rel_tol=0))
+    rows, cols = (m // 4, m // 2), (n // 3, n // 3 + max(2, n // 4))
+    out = {}
+    for mode in (0, 1):
+        X, Y = g.X.copy(order="F"), g.Y.copy(order="F")
+        res = orc.fit_units(ep, p, X, Y, rows, cols, mode=mode, nthreads=2)
+        out[mode] = (X, Y, res)
+        frozen_r = np.r_[0:rows[0], rows[1]:m]
+        frozen_c = np.r_[0:cols[0], cols[1]:n]
+        assert (X[:, frozen_r] == g.X[:, frozen_r]).all() and (Y[:, frozen_c] == g.Y[:, frozen_c]).all()
+        assert not (X[:, rows[0]:rows[1]] == g.X[:, rows[0]:rows[1]]).all()
+    assert_traj_close(out[0][2]["objective"][1:], out[1][2]["objective"][1:], 1e-9, "unit sample: faithful vs sparse")
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=1e-7, atol=1e-10)
+    assert out[0][2]["trials"] == out[1][2]["trials"]
+    X, Y = g.X.copy(order="F"), g.Y.copy(order="F")
+    full = orc.fit_units(ep, p, X, Y, (0, m), (0, n), mode=0)
+    want = run_oracle(orc, g, lrm.ProxGradParams(max_iter=6, abs_tol=0, rel_tol=0), mode=0)
+    assert (full["objective"] == want["objective"]).all() and (X == want["X"]).all()
+
+
+def test_rem_quad_reg_recovers_the_means(orc):
+    """test/mult_reg.jl:5-29: QuadLoss with RemQuadReg(50, mean) per row / column pulls the factors to their means; the
+    reference asserts mse(U), mse(V) < 1e-3 after fit!(glrm) with default parameters."""
+    n = m = 200
+    r, eta, delta = 5, 0.01, 1e-3
+    Um, Vm = synth.normal_matrix(71, 1, r, n), synth.normal_matrix(71, 2, r, m)
+    U = Um + np.sqrt(eta) * synth.normal_matrix(71, 3, r, n)
+    V = Vm + np.sqrt(eta) * synth.normal_matrix(71, 4, r, m)
+    Yobs = U.T @ V + np.sqrt(delta) * synth.normal_matrix(71, 5, n, m)
+    g = lrm.GLRM(np.asfortranarray(Yobs), lrm.QuadLoss(), [lrm.RemQuadReg(50, Um[:, i]) for i in range(n)],
+                 [lrm.RemQuadReg(50, Vm[:, j]) for j in range(m)], r,
+                 X=synth.normal_matrix(71, 6, r, n), Y=synth.normal_matrix(71, 7, r, m))
+    res = check_all_forms(orc, g, lrm.ProxGradParams(max_iter=100))
+    assert np.mean((U - res["X"]) ** 2) < 1e-3 and np.mean((V - res["Y"]) ** 2) < 1e-3
+
+
+@pytest.mark.parametrize("inner", [lrm.ZeroReg(), lrm.QuadReg(0.1), lrm.NonNegConstraint(), lrm.OneSparseConstraint()],
+                         ids=lambda r: type(r).__name__)
+def test_fixed_latent_features_both_sides(orc, inner):
+    """test/fixedfeatures_test.jl shape: ry = fixed_latent_features(...) per column; plus the 'last' variant on the rows,
+    restated with the reference's own indexing (regularizers.jl:223 feeds u[n+1:end] to the inner prox)."""
+    A, obs, X0 = small_sparse(m=40, n=30, k=5, seed=8)
+    k = 5
+    Y0 = synth.normal_matrix(72, 1, k, 30)
+    ry = [lrm.fixed_latent_features(inner.copy(), Y0[:2, j].copy()) for j in range(30)]
+    rx = [lrm.fixed_last_latent_features(inner.copy(), X0[3:, i].copy()) for i in range(40)]
+    g = lrm.GLRM(A, lrm.QuadLoss(), rx, ry, k, obs=obs, X=X0.copy(), Y=Y0.copy())
+    res = check_all_forms(orc, g, lrm.ProxGradParams(max_iter=10))
+    assert (res["Y"][:2, :] == Y0[:2, :]).all() and (res["X"][3:, :] == X0[3:, :]).all()     # pinned entries never move
+    assert np.isfinite(res["objective"][1:]).all()
