@@ -85,11 +85,25 @@ __device__ __forceinline__ uint32_t dn_smem_u32(const void* p) { return (uint32_
 __device__ __forceinline__ void dn_mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dn_smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void dn_mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n.reg .pred p;\nDN_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DN_DONE_%=;\nbra DN_WAIT_%=;\nDN_DONE_%=:\n}" ::"r"(dn_smem_u32(bar)), "r"(parity) : "memory");
+// Watchdog: a wait that outlasts any plausible copy (2^32 clocks, ~2 s) records where it happened and lets the kernel run
+// on (the results are then meaningless; the engine reports the record as an error instead of hanging the device).
+__device__ __noinline__ void dn_give_up(int32_t* diag, int code, int a, int b, int c) {
+  if (diag != nullptr && atomicCAS(diag, 0, code) == 0) {
+    diag[1] = (int)blockIdx.x; diag[2] = (int)blockIdx.y; diag[3] = (int)threadIdx.x;
+    diag[4] = a; diag[5] = b; diag[6] = c;
+    __threadfence();
+  }
+}
+__device__ __forceinline__ bool dn_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = dn_smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return true;
+    if (clock64() - t0 > (1ll << 32)) return false;
+  }
 }
 
 // State of the tile buffers; every thread of the CTA carries the same copy (all control flow around it is CTA-uniform).
@@ -99,19 +113,34 @@ struct APipe {
   uint32_t par[2];
   int64_t held_e0[2];
   int held_c[2];
-  __device__ __forceinline__ void init(int nb) {
-    nbuf = nb;
-    pend[0] = pend[1] = false; par[0] = par[1] = 0;
+  __device__ __forceinline__ void init(int nb, int32_t* dg) {
+    nbuf = nb; diag = dg;
+    pend[0] = pend[1] = false; par[0] = par[1] = 0; nfetch[0] = nfetch[1] = 0;
     held_e0[0] = held_e0[1] = -1; held_c[0] = held_c[1] = -1;
   }
-  __device__ __forceinline__ void wait(const DenseSmem& S, int b) {
-    if (pend[b]) { dn_mbar_wait(S.bar + b, par[b]); par[b] ^= 1u; pend[b] = false; }
+  int32_t* diag;
+  int nfetch[2];
+  __device__ __forceinline__ void wait(const DenseSmem& S, int b, int site = 0) {
+    if (pend[b]) {
+      if (!dn_mbar_wait(S.bar + b, par[b]))
+        dn_give_up(diag, 1, b | (site << 4) | ((int)par[b] << 8) | (nfetch[b] << 12), held_c[b], (int)(held_e0[b] >> 6));
+      par[b] ^= 1u; pend[b] = false;
+    }
   }
-  // rows [e0, e0 + 64) of the features of chunk c -> buffer b.  The caller guarantees (by a __syncthreads since the last
-  // element-wise phase that read buffer b) that nobody still reads it.  A copy in flight to b is drained first.
+  // rows [e0, e0 + 64) of the features of chunk c -> buffer b.  Called by all threads of the CTA (it may synchronise them).
+  // The caller guarantees (by a __syncthreads since the last element-wise phase that read buffer b) that nobody still
+  // reads it.
   __device__ __forceinline__ void fetch(const DenseArgs& P, const DenseSmem& S, int b, int64_t e0, int c) {
     if (held_e0[b] == e0 && held_c[b] == c) return;
-    wait(S, b);
+    if (pend[b]) {
+      // a copy nobody consumed (the speculative "same tile again" of a line search that has ended) is drained first.  The
+      // barrier must not be re-armed before EVERY thread has seen that phase complete: a warp that re-arms early lets the
+      // new phase complete as well, and a thread still waiting for the old parity would then wait on a phase that only
+      // the next fetch can start — forever.
+      wait(S, b, 7);
+      __syncthreads();
+    }
+    ++nfetch[b];
     if (threadIdx.x < 32) {
       const int lane = threadIdx.x;
       const int p0 = P.chunk_ptr[c], nf = P.chunk_ptr[c + 1] - p0;
@@ -320,7 +349,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   APipe ap;
-  ap.init(P.nbuf);
+  ap.init(P.nbuf, P.diag);
   unsigned stepno = 0;
   // buffer of a step: with one or two chunks the tiles of A stay put for the whole tile (no refetch in the line search)
   auto bufof = [&](int c) { return ap.nbuf == 1 ? 0 : (nchunks <= 2 ? c : (int)(stepno & 1u)); };
@@ -359,7 +388,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
       __syncthreads();
       const int cn = c + 1 < nchunks ? c + 1 : 0;      // next step: the next chunk, or chunk 0 again (first trial round)
       if (ap.nbuf == 2) ap.fetch(P, S, bufnext(cn), e0, cn);
-      ap.wait(S, b);
+      ap.wait(S, b, 1);
       rowsum += dense_elementwise<LOSS, true, false>(P, S, y_ms, S.As + (size_t)b * DN_TN * DN_TM, nf, t & 63, (t & 63) < nrows);
       __syncthreads();
       if (ap.nbuf == 1) ap.fetch(P, S, 0, e0, cn);
@@ -417,9 +446,12 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
       na = S.s_cnt[0] + S.s_cnt[1];
       __syncthreads();
     }
-    int ntrials = 0;
+    int ntrials = 0, rounds = 0;
     // ---- line search (proxgrad.jl:136-155): all searching rows of the tile try their step together ----
+    // (a step size shrinks by 0.7 per rejected trial, so a search ends within ~log(stepsize / min_stepsize) / log(1 / 0.7)
+    // rounds; the cap only trips on a corrupted state, and is reported through the watchdog record)
     while (na > 0) {
+      if (++rounds > 4096) { dn_give_up(P.diag, 2, na, (int)tile, rounds); break; }
       // trial points x_new = prox(x - (alpha/l) g) of the active slots -> Xs[.][position of the slot]; a lane group per slot
       for (int base = 0; base < na; base += 4 * NGW) {
         const int s = base + warp * NGW + gq;
@@ -467,7 +499,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
         const int ms = y_ms;                           // the element-wise phase below still reads this chunk's meta slot
         if (nchunks > 1) want_chunk(cn);               // Ys is free: the next chunk travels during the element-wise phase
         if (ap.nbuf == 2) ap.fetch(P, S, bufnext(cn), e0, cn);
-        ap.wait(S, b);
+        ap.wait(S, b, 2);
         trialsum += dense_elementwise<LOSS, false, false>(P, S, ms, S.As + (size_t)b * DN_TN * DN_TM, nf, myrow, mine);
         __syncthreads();
         if (ap.nbuf == 1) ap.fetch(P, S, 0, e0, cn);
@@ -538,7 +570,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_y_pass_kernel(const Dense
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   APipe ap;
-  ap.init(P.nbuf);
+  ap.init(P.nbuf, P.diag);
   if (rb0 < rb1) {
     ap.fetch(P, S, 0, rb0, c);
     dense_x_begin(P, S.Xs, rb0, (int)((rb1 - rb0) < DN_TM ? (rb1 - rb0) : DN_TM));
@@ -568,7 +600,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_y_pass_kernel(const Dense
     dense_gemm_u<8>(S.Xs, S.Ys, S.Rs, k);
     __syncthreads();
     if (MODE == 1 && more) dense_x_begin(P, S.Xs, e0 + DN_TM, nrows_next);      // Xs is free: the next tile travels now
-    ap.wait(S, buf);
+    ap.wait(S, buf, 3);
     dense_elementwise<LOSS, MODE == 0, true>(P, S, 0, S.As + (size_t)buf * DN_TN * DN_TM, nf, t & 63, (t & 63) < nrows);
     __syncthreads();
     if (ap.nbuf == 1 && more) ap.fetch(P, S, 0, e0 + DN_TM, c);

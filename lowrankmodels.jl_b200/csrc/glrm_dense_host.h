@@ -17,6 +17,7 @@ struct DenseArgs {
   const double* A;            // column-major m x n as Julia stores it, leading dimension lda (multiple of 64, zero rows past m)
   int64_t m, n, lda;
   int32_t nbuf;               // tile buffers of A in shared memory (1 or 2)
+  int32_t* diag;              // [8] device-side watchdog record: [0] != 0 means a kernel gave up waiting (see dn_give_up)
   int64_t row0, row1;         // rows this launch covers
   double* X;                  // k x m factor (device layout: `stride` doubles per column)
   const double* Ymat;         // k x d matrix the pass contracts with (Y, or the trial blocks Ynew)

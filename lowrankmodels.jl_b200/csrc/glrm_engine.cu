@@ -124,6 +124,7 @@ struct DenseHost {
   int32_t *d_chunk_ptr = nullptr, *d_feat_list = nullptr, *d_feat_off = nullptr, *d_nchunks = nullptr;
   int32_t *d_chunk_ptr2 = nullptr, *d_feat_list2 = nullptr, *d_feat_off2 = nullptr, *d_nchunks2 = nullptr;
   int32_t *d_nactive = nullptr, *d_active = nullptr;
+  int32_t* d_diag = nullptr;                // [8] watchdog record of the dense kernels (glrm_dense.cuh: dn_give_up)
   int max_chunks = 1;
   double *d_gscratch = nullptr, *d_gpart = nullptr, *d_objpart = nullptr, *d_G = nullptr, *d_Ynew = nullptr;
   double *d_colobj = nullptr, *d_objold = nullptr, *d_regnew = nullptr;
@@ -466,7 +467,7 @@ static void dense_free(glrmb200_engine* E) {
   dfree(D.d_A, E->stream);
   dfree(D.d_chunk_ptr, E->stream); dfree(D.d_feat_list, E->stream); dfree(D.d_feat_off, E->stream); dfree(D.d_nchunks, E->stream);
   dfree(D.d_chunk_ptr2, E->stream); dfree(D.d_feat_list2, E->stream); dfree(D.d_feat_off2, E->stream); dfree(D.d_nchunks2, E->stream);
-  dfree(D.d_nactive, E->stream); dfree(D.d_active, E->stream);
+  dfree(D.d_nactive, E->stream); dfree(D.d_active, E->stream); dfree(D.d_diag, E->stream);
   dfree(D.d_gscratch, E->stream); dfree(D.d_gpart, E->stream); dfree(D.d_objpart, E->stream); dfree(D.d_G, E->stream);
   dfree(D.d_Ynew, E->stream); dfree(D.d_colobj, E->stream); dfree(D.d_objold, E->stream); dfree(D.d_regnew, E->stream);
   D.on = false;
@@ -513,6 +514,7 @@ static int dense_setup(glrmb200_engine* E, const glrmb200_problem* P) {
     else if (s2 <= cap) { D.nbuf = 2; D.ctas_per_sm = 1; }
     else { D.nbuf = 1; D.ctas_per_sm = 1; }
     if (const char* t = getenv("GLRMB200_DENSE_NBUF")) { const int v = atoi(t); if (v == 1 || (v == 2 && s2 <= cap)) { D.nbuf = v; D.ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, cap / (v == 1 ? s1 : s2))); } }
+    if (const char* t = getenv("GLRMB200_DENSE_CTAS")) { const int v = atoi(t); if (v == 1) D.ctas_per_sm = 1; }
   }
   // static plan: all features in order, chunks of <= DN_TN columns made of whole features
   std::vector<int32_t> chunk_ptr{0}, feat_list, feat_off;
@@ -538,6 +540,8 @@ static int dense_setup(glrmb200_engine* E, const glrmb200_problem* P) {
   if ((rc = dalloc(&D.d_nchunks2, 1, E->stream))) return rc;
   if ((rc = dalloc(&D.d_nactive, 1, E->stream))) return rc;
   if ((rc = dalloc(&D.d_active, (size_t)n, E->stream))) return rc;
+  if ((rc = dalloc(&D.d_diag, 8, E->stream))) return rc;
+  CUDA_OK(cudaMemsetAsync(D.d_diag, 0, 8 * sizeof(int32_t), E->stream));
   CUDA_OK(cudaMemsetAsync(D.d_active, 0, (size_t)n * sizeof(int32_t), E->stream));
   CUDA_OK(cudaMemsetAsync(D.d_nactive, 0, sizeof(int32_t), E->stream));
   CUDA_OK(cudaMemsetAsync(D.d_nchunks2, 0, sizeof(int32_t), E->stream));
@@ -568,7 +572,7 @@ static DenseArgs dense_args(const glrmb200_engine* E, bool static_plan, const do
   const DenseHost& D = E->dn;
   DenseArgs P;
   memset(&P, 0, sizeof(P));
-  P.A = D.d_A; P.m = E->m; P.n = E->n; P.lda = D.lda; P.nbuf = D.nbuf;
+  P.A = D.d_A; P.m = E->m; P.n = E->n; P.lda = D.lda; P.nbuf = D.nbuf; P.diag = D.d_diag;
   P.row0 = 0; P.row1 = E->m;
   P.X = E->d_X; P.Ymat = Ymat;
   P.stride = E->stride; P.k = (int)E->k; P.kp = E->kp;
@@ -614,11 +618,35 @@ static DenseYState dense_ystate(glrmb200_engine* E, int flags, double min_stepsi
     if (ce__ != cudaSuccess) return fail(GLRMB200_E_CUDA, "%s: %s", #call, cudaGetErrorString(ce__));                  \
   } while (0)
 
+// the dense kernels' watchdog record (synchronises the stream)
+static int dense_check_diag(glrmb200_engine* E) {
+  if (!E->dn.on || !E->dn.d_diag) return 0;
+  int32_t dg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  CUDA_OK(cudaMemcpyAsync(dg, E->dn.d_diag, sizeof(dg), cudaMemcpyDeviceToHost, E->stream));
+  CUDA_OK(cudaStreamSynchronize(E->stream));
+  if (dg[0] == 0) return 0;
+  cudaMemsetAsync(E->dn.d_diag, 0, sizeof(dg), E->stream);
+  return fail(GLRMB200_E_STATE, "dense kernel watchdog: %s (block %d,%d thread %d; %d %d %d)",
+              dg[0] == 1 ? "a tile of A never arrived" : "the line search did not end", dg[1], dg[2], dg[3], dg[4], dg[5], dg[6]);
+}
+// GLRMB200_DENSE_DEBUG=1: synchronise after every dense launch and say which one it was (hang hunting)
+static int dense_debug(glrmb200_engine* E, const char* what) {
+  static const bool on = getenv("GLRMB200_DENSE_DEBUG") && atoi(getenv("GLRMB200_DENSE_DEBUG"));
+  if (!on) return 0;
+  fprintf(stderr, "[dense] %s ...", what); fflush(stderr);
+  const cudaError_t ce = cudaStreamSynchronize(E->stream);
+  fprintf(stderr, " %s\n", ce == cudaSuccess ? "done" : cudaGetErrorString(ce)); fflush(stderr);
+  if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "%s: %s", what, cudaGetErrorString(ce));
+  return dense_check_diag(E);
+}
+#define DN_DBG(what) do { int drc__ = dense_debug(E, what); if (drc__) return drc__; } while (0)
+
 static int dense_sweep_x(glrmb200_engine* E, double min_stepsize, bool honour_stop, int64_t* launches) {
   const DenseHost& D = E->dn;
   const int loss = E->loss_template == GLRMB200_LOSS_QUAD ? GLRMB200_LOSS_QUAD : 0;
   DenseArgs P = dense_args(E, true, E->d_Y, 0, min_stepsize, honour_stop);
   DN_OK(dense_launch_x(D.kt, E->tile_g, E->tile_r, loss, P, D.x_grid, E->stream));
+  DN_DBG("dense_x_kernel");
   ++*launches;
   return 0;
 }
@@ -635,10 +663,13 @@ static int dense_eval_cols(glrmb200_engine* E, int flags, double min_stepsize, b
   const int loss = E->loss_template == GLRMB200_LOSS_QUAD ? GLRMB200_LOSS_QUAD : 0;
   DenseArgs P = dense_args(E, true, E->d_Y, flags, min_stepsize, honour_stop);
   DN_OK(dense_launch_y_pass(D.kt, loss, mode, P, D.n_blocks, D.max_chunks, E->stream));
+  DN_DBG(mode == 0 ? "dense_y_pass_kernel (gradient)" : "dense_y_pass_kernel (evaluation)");
   if (mode == 0) DN_OK(dense_launch_reduce(D.d_gpart, D.n_blocks, E->d * (int64_t)E->stride, D.d_G, nullptr, P.stop, E->stream));
   DN_OK(dense_launch_reduce(D.d_objpart, D.n_blocks, E->n, D.d_colobj, nullptr, P.stop, E->stream));
+  DN_DBG("dense_reduce_kernel");
   DenseYState Q = dense_ystate(E, flags, min_stepsize, honour_stop);
   DN_OK(dense_launch_begin(E->tile_g, E->tile_r, Q, E->stream));
+  DN_DBG("dense_y_begin_kernel");
   *launches += mode == 0 ? 4 : 3;
   return 0;
 }
@@ -662,9 +693,12 @@ static int dense_sweep_y(glrmb200_engine* E, double min_stepsize, bool honour_st
   for (int round = 0;; ++round) {
     if (round >= 4095) return fail(GLRMB200_E_STATE, "dense Y line search did not terminate");
     DN_OK(dense_launch_step(E->tile_g, E->tile_r, Q, E->stream));
+    DN_DBG("dense_y_step_kernel");
     DN_OK(dense_launch_y_pass(D.kt, loss, 1, P, D.n_blocks, D.max_chunks, E->stream));
+    DN_DBG("dense_y_pass_kernel (trial)");
     DN_OK(dense_launch_reduce(D.d_objpart, D.n_blocks, E->n, D.d_colobj, D.d_nactive, P.stop, E->stream));
     DN_OK(dense_launch_decide(Q, E->stream));
+    DN_DBG("dense_y_decide_kernel");
     Q.seq = key(round + 1);
     DN_OK(dense_launch_plan(Q, E->stream));
     *launches += 5;
@@ -1495,6 +1529,7 @@ extern "C" int glrmb200_fit_resident(glrmb200_handle E, const glrmb200_params* p
   prof.loop_ms = std::chrono::duration<double, std::milli>(clk::now() - t_loop).count();
   harvest(enqueued);
   if ((rc = check_barrier_timeout(E))) return rc;
+  if ((rc = dense_check_diag(E))) return rc;
   int stop_it = 0;
   CUDA_OK(cudaMemcpy(&stop_it, E->d_stop, sizeof(int), cudaMemcpyDeviceToHost));
   const int last = stop_it > 0 ? stop_it : enqueued;          // iterations actually executed
