@@ -229,6 +229,15 @@ int         glrmb200_device_count(int32_t* count);          /* 0 devices => GLRM
 int glrmb200_create(glrmb200_handle* out, const glrmb200_problem* problem,
                     int32_t device, int32_t rank, int32_t nranks);
 
+/* glrmb200_create_ex: the same with creation flags.
+ *   GLRMB200_CREATE_GATHER_ONLY  a fully observed problem is encoded with (implicit) observation lists for the gather
+ *                                kernels instead of the streaming kernels of the fully observed path — what
+ *                                fit!(glrm, ::SparseProxGradParams) on a dense A needs (glrmb200_fit_sparse runs on the
+ *                                gather kernels only). */
+enum { GLRMB200_CREATE_GATHER_ONLY = 1 };
+int glrmb200_create_ex(glrmb200_handle* out, const glrmb200_problem* problem,
+                       int32_t device, int32_t rank, int32_t nranks, int32_t flags);
+
 /* Multi-GPU plumbing (one process per GPU).  Rank 0 calls glrmb200_comm_unique_id and the host
  * side (torch.distributed / Julia Distributed) broadcasts the 128 bytes; every rank then calls
  * glrmb200_comm_init.  The communicator is cached per process: later handles of the same (rank, nranks, device)

@@ -62,6 +62,7 @@ SYMBOLS = [
     ("glrmb200_last_error", C.c_char_p, []),
     ("glrmb200_device_count", C.c_int, [c_int32_p]),
     ("glrmb200_create", C.c_int, [C.POINTER(Handle), C.POINTER(Problem), C.c_int32, C.c_int32, C.c_int32]),
+    ("glrmb200_create_ex", C.c_int, [C.POINTER(Handle), C.POINTER(Problem), C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("glrmb200_comm_unique_id", C.c_int, [C.POINTER(C.c_uint8)]),
     ("glrmb200_comm_init", C.c_int, [Handle, C.POINTER(C.c_uint8)]),
     ("glrmb200_ipc_export", C.c_int, [Handle, C.POINTER(C.c_uint8)]),

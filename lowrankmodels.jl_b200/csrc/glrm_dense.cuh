@@ -173,11 +173,9 @@ __device__ __forceinline__ void dn_async_wait() {
   __syncthreads();
 }
 
-// chunk set-up into meta slot `ms`: feature list, local column map; then the chunk of Y ([i][jj], rows >= k zero) is put in
-// flight.  The caller guarantees that nobody reads Ys or meta slot `ms` any more, and calls dn_async_wait before using Ys.
-template <int KT>
-__device__ __forceinline__ void dense_chunk_begin(const DenseArgs& P, const DenseSmem& S, int c, int ms) {
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+// chunk set-up into meta slot `ms`: feature list and local column map of chunk c.  Nobody may still read slot `ms`.
+__device__ __forceinline__ void dense_chunk_meta(const DenseArgs& P, const DenseSmem& S, int c, int ms) {
+  const int t = threadIdx.x;
   const int p0 = P.chunk_ptr[c], nf = P.chunk_ptr[c + 1] - p0;
   int* s_col = S.s_col + ms * DN_TN;
   int* s_feat = S.s_feat + ms * DN_TN;
@@ -195,7 +193,14 @@ __device__ __forceinline__ void dense_chunk_begin(const DenseArgs& P, const Dens
   }
   if (nf == 0 && t == 0) s_foff[0] = 0;
   __syncthreads();
-  // a warp per column, lanes over i: 256-byte coalesced reads, conflict-free transposed writes (pitch 65)
+}
+// the chunk of Y described by meta slot `ms` ([i][jj], rows >= k zero) is put in flight.  The caller guarantees that nobody
+// reads Ys any more, and calls dn_async_wait before using it.  A warp per column, lanes over i: 256-byte coalesced reads,
+// conflict-free transposed writes (pitch 65).
+template <int KT>
+__device__ __forceinline__ void dense_chunk_copy(const DenseArgs& P, const DenseSmem& S, int ms) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int* s_col = S.s_col + ms * DN_TN;
   for (int jj = warp; jj < DN_TN; jj += DN_THREADS / 32) {
     const int col = s_col[jj];
     const double* src = P.Ymat + (int64_t)(col >= 0 ? col : 0) * P.stride;
@@ -203,6 +208,11 @@ __device__ __forceinline__ void dense_chunk_begin(const DenseArgs& P, const Dens
     for (int i = lane; i < KT * 16; i += 32) dn_cp_async8(S.Ys + i * DN_YP + jj, src + (i < P.k ? i : 0), col >= 0 && i < P.k);
   }
   dn_async_commit();
+}
+template <int KT>
+__device__ __forceinline__ void dense_chunk_begin(const DenseArgs& P, const DenseSmem& S, int c, int ms) {
+  dense_chunk_meta(P, S, c, ms);
+  dense_chunk_copy<KT>(P, S, ms);
 }
 
 // tile of X -> Xs[i][r] (zero rows past the end): a warp per row, lanes over i (coalesced)
@@ -229,7 +239,9 @@ __device__ __forceinline__ void dense_gemm_u(const double* __restrict__ Xt, cons
     for (int b = 0; b < DN_CT; ++b) acc[a][b] = 0.0;
   const double* xp = Xt + trow * 8;
   const double* yp = Ys + tcol;
-#pragma unroll 2
+  // few rows per thread = few independent FMA chains: unroll deeper so that the shared-memory loads of several steps are in
+  // flight together (one warp per scheduler: nothing else hides their latency)
+#pragma unroll (NR <= 2 ? 8 : (NR <= 4 ? 4 : 2))
   for (int i = 0; i < k; ++i) {
     double x[NR];
 #pragma unroll
@@ -354,12 +366,16 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
   // buffer of a step: with one or two chunks the tiles of A stay put for the whole tile (no refetch in the line search)
   auto bufof = [&](int c) { return ap.nbuf == 1 ? 0 : (nchunks <= 2 ? c : (int)(stepno & 1u)); };
   auto bufnext = [&](int c) { return ap.nbuf == 1 ? 0 : (nchunks <= 2 ? c : (int)((stepno + 1u) & 1u)); };
-  // the chunk of Y in shared memory (or on its way there) and the meta slot that describes it
+  // the chunk of Y in shared memory (or on its way there) and the meta slot that describes it.  With one or two chunks
+  // each chunk keeps its own meta slot for the whole kernel (built once); otherwise the slots alternate.
   int y_chunk = -1, y_ms = 0;
-  auto want_chunk = [&](int c) {           // Ys and the other meta slot must be free
+  int meta_of[2] = {-1, -1};
+  auto want_chunk = [&](int c) {           // Ys and (if it has to be rebuilt) the target meta slot must be free
     if (y_chunk == c) return;
-    y_ms ^= 1;
-    dense_chunk_begin<KT>(P, S, c, y_ms);
+    const int slot = nchunks <= 2 ? c : (y_ms ^ 1);
+    if (meta_of[slot] != c) { dense_chunk_meta(P, S, c, slot); meta_of[slot] = c; }
+    y_ms = slot;
+    dense_chunk_copy<KT>(P, S, slot);
     y_chunk = c;
   };
 
@@ -452,34 +468,47 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_x_kernel(const DenseArgs 
     // rounds; the cap only trips on a corrupted state, and is reported through the watchdog record)
     while (na > 0) {
       if (++rounds > 4096) { dn_give_up(P.diag, 2, na, (int)tile, rounds); break; }
-      // trial points x_new = prox(x - (alpha/l) g) of the active slots -> Xs[.][position of the slot]; a lane group per slot
-      for (int base = 0; base < na; base += 4 * NGW) {
-        const int s = base + warp * NGW + gq;
-        const bool ok = s < na;
-        const int r = S.s_perm[ok ? s : 0];
-        const int64_t e = e0 + r;
-        const int rcode = P.reg_code[P.reg_uniform ? 0 : e];
-        const double* rp = P.reg_param + (P.reg_uniform ? 0 : e) * GLRMB200_REG_NPARAM;
-        const double stepsize = alpha[r] / l1;                            // :137
-        double2 xn[TR];
-#pragma unroll
-        for (int rr = 0; rr < TR; ++rr) {
-          const int i0 = 2 * (lg + TG * rr);
-          const double2 x0 = *reinterpret_cast<const double2*>(P.X + e * P.stride + i0);      // padding past k is zero
-          const double2 g = *reinterpret_cast<const double2*>(Gg + (int64_t)r * P.stride + i0);
-          xn[rr].x = fma(-stepsize, g.x, x0.x); xn[rr].y = fma(-stepsize, g.y, x0.y);          // :140
-        }
-        reg_prox<TG, TR>(rcode, rp, xn, lg, k, stepsize);                  // :142
-        const double rv = reg_eval<TG, TR>(rcode, rp, xn, lg, k);
-        if (ok) {
-          const int pos = dense_slot_pos(s);
+      // trial points x_new = prox(x - (alpha/l) g) of the active slots -> Xs[.][position of the slot]; a lane group per slot.
+      // The row and gradient of the next slot are fetched (L2) while the current one goes through prox / evaluate.
+      {
+        double2 x0n[TR], gn[TR];
+        auto fetch_slot = [&](int base) {
+          const int s = base + warp * NGW + gq;
+          const int r = S.s_perm[s < na ? s : 0];
 #pragma unroll
           for (int rr = 0; rr < TR; ++rr) {
             const int i0 = 2 * (lg + TG * rr);
-            if (i0 < k) S.Xs[i0 * DN_RP + pos] = xn[rr].x;
-            if (i0 + 1 < k) S.Xs[(i0 + 1) * DN_RP + pos] = xn[rr].y;
+            x0n[rr] = *reinterpret_cast<const double2*>(P.X + (e0 + r) * P.stride + i0);        // padding past k is zero
+            gn[rr] = *reinterpret_cast<const double2*>(Gg + (int64_t)r * P.stride + i0);
           }
-          if (lg == 0) regnew[r] = rv;
+        };
+        fetch_slot(0);
+        for (int base = 0; base < na; base += 4 * NGW) {
+          const int s = base + warp * NGW + gq;
+          const bool ok = s < na;
+          const int r = S.s_perm[ok ? s : 0];
+          const int64_t e = e0 + r;
+          const int rcode = P.reg_code[P.reg_uniform ? 0 : e];
+          const double* rp = P.reg_param + (P.reg_uniform ? 0 : e) * GLRMB200_REG_NPARAM;
+          const double stepsize = alpha[r] / l1;                            // :137
+          double2 xn[TR];
+#pragma unroll
+          for (int rr = 0; rr < TR; ++rr) {
+            xn[rr].x = fma(-stepsize, gn[rr].x, x0n[rr].x); xn[rr].y = fma(-stepsize, gn[rr].y, x0n[rr].y);   // :140
+          }
+          if (base + 4 * NGW < na) fetch_slot(base + 4 * NGW);
+          reg_prox<TG, TR>(rcode, rp, xn, lg, k, stepsize);                  // :142
+          const double rv = reg_eval<TG, TR>(rcode, rp, xn, lg, k);
+          if (ok) {
+            const int pos = dense_slot_pos(s);
+#pragma unroll
+            for (int rr = 0; rr < TR; ++rr) {
+              const int i0 = 2 * (lg + TG * rr);
+              if (i0 < k) S.Xs[i0 * DN_RP + pos] = xn[rr].x;
+              if (i0 + 1 < k) S.Xs[(i0 + 1) * DN_RP + pos] = xn[rr].y;
+            }
+            if (lg == 0) regnew[r] = rv;
+          }
         }
       }
       const int myslot = dense_slot_pos(t & 63);                           // the slot whose position this thread serves

@@ -882,7 +882,7 @@ static int load_lists(glrmb200_engine* E, const int64_t* row_ptr, const int32_t*
   return 0;
 }
 
-static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
+static int create_impl(glrmb200_engine* E, const glrmb200_problem* P, int flags) {
   const int64_t m = P->m, n = P->n, k = P->k;
   if (m <= 0 || n <= 0 || k <= 0) return fail(GLRMB200_E_INVALID, "m, n, k must be positive");
   if (m >= INT32_MAX || n >= INT32_MAX) return fail(GLRMB200_E_INVALID, "m, n must fit int32");
@@ -945,7 +945,7 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
     }
   }
   E->stride = 2 * E->tile_g * E->tile_r;
-  const bool want_dense = dense_eligible(E, P);
+  const bool want_dense = dense_eligible(E, P) && !(flags & GLRMB200_CREATE_GATHER_ONLY);
   if (E->has_vec && E->tile_r > 2 && !want_dense)
     return fail(GLRMB200_E_UNSUPPORTED, "vector-valued losses are supported on the device for k <= 32 this round (k = %lld)", (long long)k);
   if (const char* t = getenv("GLRMB200_HEAVY")) E->heavy_threshold = std::max<long long>(1, atoll(t));
@@ -1127,12 +1127,17 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P) {
 
 extern "C" int glrmb200_create(glrmb200_handle* out, const glrmb200_problem* problem, int32_t device,
                                int32_t rank, int32_t nranks) {
+  return glrmb200_create_ex(out, problem, device, rank, nranks, 0);
+}
+
+extern "C" int glrmb200_create_ex(glrmb200_handle* out, const glrmb200_problem* problem, int32_t device,
+                                  int32_t rank, int32_t nranks, int32_t flags) {
   if (!out || !problem) return fail(GLRMB200_E_INVALID, "null argument");
   *out = nullptr;
   if (nranks < 1 || rank < 0 || rank >= nranks) return fail(GLRMB200_E_INVALID, "bad rank %d / nranks %d", rank, nranks);
   glrmb200_engine* E = new glrmb200_engine();
   E->device = device; E->rank = rank; E->nranks = nranks;
-  const int rc = create_impl(E, problem);
+  const int rc = create_impl(E, problem, flags);
   if (rc) { glrmb200_destroy(E); return rc; }
   *out = E;
   return 0;
@@ -1566,7 +1571,7 @@ extern "C" int glrmb200_fit_sparse(glrmb200_handle E, const glrmb200_sparse_para
                                    glrmb200_profile* profile) {
   if (!E || !prm || !X || !Y || !ch_objective || !ch_seconds || !n_recorded) return fail(GLRMB200_E_INVALID, "null argument");
   if (E->has_vec) return fail(GLRMB200_E_UNSUPPORTED, "SparseProxGradParams handles scalar-embedding losses only (sparse_proxgrad.jl:70 uses dot(x_e, y_f))");
-  if (E->dn.on) return fail(GLRMB200_E_UNSUPPORTED, "SparseProxGradParams on a fully observed handle: create it with GLRMB200_DENSE=0 (gather kernels) or pass observation lists");
+  if (E->dn.on) return fail(GLRMB200_E_UNSUPPORTED, "SparseProxGradParams on a fully observed handle: create it with glrmb200_create_ex(..., GLRMB200_CREATE_GATHER_ONLY)");
   if (cap < prm->max_iter + 2) return fail(GLRMB200_E_INVALID, "cap %d < max_iter+2", cap);
   if (prm->inner_iter < 1) return fail(GLRMB200_E_INVALID, "inner_iter must be >= 1");
   bool allzero = true;

@@ -18,12 +18,15 @@ from .params import ProxGradParams, SparseProxGradParams
 
 
 class Engine:
-    def __init__(self, glrm_or_problem, device=0, rank=0, nranks=1, validate=True):
+    GATHER_ONLY = 1          # GLRMB200_CREATE_GATHER_ONLY
+
+    def __init__(self, glrm_or_problem, device=0, rank=0, nranks=1, validate=True, gather_only=False):
         self.ep = (glrm_or_problem if isinstance(glrm_or_problem, EncodedProblem)
                    else encode_problem(glrm_or_problem, validate=validate))
         self.h = _abi.Handle()
         L = _abi.lib()
-        _abi.check(L.glrmb200_create(C.byref(self.h), C.byref(self.ep.struct), device, rank, nranks))
+        _abi.check(L.glrmb200_create_ex(C.byref(self.h), C.byref(self.ep.struct), device, rank, nranks,
+                                        self.GATHER_ONLY if gather_only else 0))
         s = self.ep.struct
         self.m, self.n, self.k, self.d = int(s.m), int(s.n), int(s.k), int(s.d)
         self.nranks = nranks
@@ -172,7 +175,7 @@ def fit_inplace(glrm: GLRM, params: ProxGradParams = None, *, ch: ConvergenceHis
         ch = ConvergenceHistory("B200ProxGradGLRM")
     own = engine is None
     if own:
-        engine = Engine(glrm, device=getattr(params, "device", 0))
+        engine = Engine(glrm, device=getattr(params, "device", 0), gather_only=isinstance(params, SparseProxGradParams))
     try:
         if verbose:
             print("Fitting GLRM")                                              # proxgrad.jl:75

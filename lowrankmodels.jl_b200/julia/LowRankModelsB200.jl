@@ -226,11 +226,12 @@ mutable struct B200Handle
     h::Ptr{Cvoid}
     device::Int; rank::Int; nranks::Int
 end
-function B200Handle(glrm::GLRM; device::Int=0, rank::Int=0, nranks::Int=1)
+const CREATE_GATHER_ONLY = Int32(1)     # GLRMB200_CREATE_GATHER_ONLY: what glrmb200_fit_sparse needs for a fully observed A
+function B200Handle(glrm::GLRM; device::Int=0, rank::Int=0, nranks::Int=1, gather_only::Bool=false)
     handle = Ref{Ptr{Cvoid}}(C_NULL)
     with_problem(encode(glrm)) do prob
-        check(ccall((:glrmb200_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{CProblem}, Int32, Int32, Int32),
-                    handle, prob, device, rank, nranks))
+        check(ccall((:glrmb200_create_ex, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{CProblem}, Int32, Int32, Int32, Int32),
+                    handle, prob, device, rank, nranks, gather_only ? CREATE_GATHER_ONLY : Int32(0)))
     end
     hd = B200Handle(handle[], device, rank, nranks)
     finalizer(close, hd)
@@ -343,7 +344,7 @@ function fit!(hd::B200Handle, glrm::GLRM, params::B200SparseProxGradParams;
 end
 function fit!(glrm::GLRM, params::B200SparseProxGradParams;
               ch::ConvergenceHistory=ConvergenceHistory("B200SparseProxGradGLRM"), verbose=true, kwargs...)
-    hd = B200Handle(glrm; device=params.device)
+    hd = B200Handle(glrm; device=params.device, gather_only=true)
     try
         return fit!(hd, glrm, params; ch=ch, verbose=verbose, kwargs...)
     finally

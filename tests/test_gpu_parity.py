@@ -292,7 +292,7 @@ def test_sparse_proxgrad_params_semantics(orc, stepsize):
         Xo, Yo = g.X.copy(order="F"), g.Y.copy(order="F")
         want = orc.fit_sparse(ep, lrm.encode_sparse_params(p), Xo, Yo)
         X, Y = g.X.copy(order="F"), g.Y.copy(order="F")
-        with lrm.Engine(ep) as eng:
+        with lrm.Engine(ep, gather_only=True) as eng:
             obj, sec = eng.fit_sparse(p, X, Y)
         assert_traj_close(obj, want["objective"], 1e-7, name)
         np.testing.assert_allclose(X, Xo, rtol=1e-5, atol=1e-8)
