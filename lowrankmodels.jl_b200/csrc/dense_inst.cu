@@ -58,9 +58,17 @@ cudaError_t dense_launch_y_pass(int kt, int loss, int mode, const DenseArgs& P, 
   return cudaErrorInvalidValue;
 }
 
-cudaError_t dense_launch_reduce(const double* part, int n_blocks, int64_t len, double* out, const int32_t* nactive, const int* stop, cudaStream_t st) {
+cudaError_t dense_launch_reduce_groups(const double* part, int bg, int g0, int g1, int64_t len, double* gsum, const int32_t* nactive,
+                                       const int* stop, cudaStream_t st) {
+  if (len <= 0 || g1 <= g0) return cudaSuccess;
+  const dim3 grid((unsigned)((len + 255) / 256), (unsigned)(g1 - g0), 1);
+  dense_reduce_groups_kernel<<<grid, 256, 0, st>>>(part, bg, g0, g1, len, gsum, nactive, stop);
+  return cudaGetLastError();
+}
+
+cudaError_t dense_launch_reduce_total(const double* gsum, int64_t len, double* out, const int32_t* nactive, const int* stop, cudaStream_t st) {
   if (len <= 0) return cudaSuccess;
-  dense_reduce_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(part, n_blocks, len, out, nactive, stop);
+  dense_reduce_total_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(gsum, len, out, nactive, stop);
   return cudaGetLastError();
 }
 
@@ -93,5 +101,25 @@ cudaError_t dense_launch_decide(const DenseYState& Q, cudaStream_t st) {
 }
 
 size_t dense_smem_needed(int k, int kt, int nbuf) { return dense_smem_bytes(k, kt, nbuf); }
+
+// tensor-core kernels: one translation unit per factor width (dense_mma_inst.cu)
+#define MM_DECL(NT)                                                                                                  \
+  cudaError_t dense_mma_x_nt##NT(int tg, int tr, int loss, const DenseArgs& P, int grid, cudaStream_t st);           \
+  cudaError_t dense_mma_y_nt##NT(int loss, int mode, const DenseArgs& P, int n_blocks, int max_units, cudaStream_t st);
+MM_DECL(1) MM_DECL(2) MM_DECL(3) MM_DECL(4) MM_DECL(6) MM_DECL(8) MM_DECL(10) MM_DECL(12) MM_DECL(13)
+#undef MM_DECL
+
+cudaError_t dense_mma_launch_x(int nt, int tg, int tr, int loss, const DenseArgs& P, int grid, cudaStream_t st) {
+#define T(NT) if (nt == NT) return dense_mma_x_nt##NT(tg, tr, loss, P, grid, st);
+  T(1) T(2) T(3) T(4) T(6) T(8) T(10) T(12) T(13)
+#undef T
+  return cudaErrorInvalidValue;
+}
+cudaError_t dense_mma_launch_y(int nt, int loss, int mode, const DenseArgs& P, int n_blocks, int max_units, cudaStream_t st) {
+#define T(NT) if (nt == NT) return dense_mma_y_nt##NT(loss, mode, P, n_blocks, max_units, st);
+  T(1) T(2) T(3) T(4) T(6) T(8) T(10) T(12) T(13)
+#undef T
+  return cudaErrorInvalidValue;
+}
 
 }  // namespace glrm

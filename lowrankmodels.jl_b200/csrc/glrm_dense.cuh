@@ -87,7 +87,7 @@ __device__ __forceinline__ void dn_mbar_init(uint64_t* bar, int count) {
 }
 // Watchdog: a wait that outlasts any plausible copy (2^32 clocks, ~2 s) records where it happened and lets the kernel run
 // on (the results are then meaningless; the engine reports the record as an error instead of hanging the device).
-__device__ __noinline__ void dn_give_up(int32_t* diag, int code, int a, int b, int c) {
+static __device__ __noinline__ void dn_give_up(int32_t* diag, int code, int a, int b, int c) {
   if (diag != nullptr && atomicCAS(diag, 0, code) == 0) {
     diag[1] = (int)blockIdx.x; diag[2] = (int)blockIdx.y; diag[3] = (int)threadIdx.x;
     diag[4] = a; diag[5] = b; diag[6] = c;
@@ -592,8 +592,8 @@ __global__ void __launch_bounds__(DN_THREADS, 1) dense_y_pass_kernel(const Dense
   const DenseSmem S = dense_carve(dn_smem, P.k, KT, P.nbuf);
   const int t = threadIdx.x;
   const int k = P.k;
-  const int b = blockIdx.x;
-  const int64_t rb0 = P.row0 + (int64_t)b * P.rows_per_block;
+  const int b = (int)blockIdx.x + P.block0;              // global row block (a rank launches only the blocks it owns)
+  const int64_t rb0 = (int64_t)b * P.rows_per_block;
   const int64_t rb1 = (rb0 + P.rows_per_block) < P.row1 ? (rb0 + P.rows_per_block) : P.row1;
   if (t == 0) { dn_mbar_init(S.bar, 1); dn_mbar_init(S.bar + 1, 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -688,15 +688,31 @@ __device__ __forceinline__ bool dense_stopped(const int* stop) {
   return stop != nullptr && *reinterpret_cast<const volatile int*>(stop) != 0;
 }
 
-// out[x] = sum over row blocks (fixed order) of part[b][x]
-__global__ void dense_reduce_kernel(const double* __restrict__ part, int32_t n_blocks, int64_t len, double* __restrict__ out,
-                                    const int32_t* nactive, const int* stop) {
+#ifndef GLRM_DENSE_HELPERS_ONLY   // (non-template kernels: defined once, in dense_inst.cu)
+// Two-level fixed-order reduction over the row blocks.  The DN_GROUPS groups are the same whatever the number of GPUs (a
+// rank owns whole groups), so the sums — and everything downstream — are bit-identical for 1, 2, 4 and 8 ranks.
+// gsum[g][x] = sum over the `bg` blocks of group g (sequential), for the groups g0 <= g < g1
+__global__ void dense_reduce_groups_kernel(const double* __restrict__ part, int32_t bg, int32_t g0, int32_t g1, int64_t len,
+                                           double* __restrict__ gsum, const int32_t* nactive, const int* stop) {
+  if (dense_stopped(stop)) return;
+  if (nactive != nullptr && *nactive == 0) return;
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = g0 + (int)blockIdx.y;
+  if (x >= len || g >= g1) return;
+  double s = 0.0;
+  for (int b = g * bg; b < (g + 1) * bg; ++b) s += part[(int64_t)b * len + x];
+  gsum[(int64_t)g * len + x] = s;
+}
+// out[x] = sum over the DN_GROUPS groups (sequential)
+__global__ void dense_reduce_total_kernel(const double* __restrict__ gsum, int64_t len, double* __restrict__ out,
+                                          const int32_t* nactive, const int* stop) {
   if (dense_stopped(stop)) return;
   if (nactive != nullptr && *nactive == 0) return;
   const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= len) return;
   double s = 0.0;
-  for (int b = 0; b < n_blocks; ++b) s += part[(int64_t)b * len + x];
+#pragma unroll
+  for (int g = 0; g < DN_GROUPS; ++g) s += gsum[(int64_t)g * len + x];
   out[x] = s;
 }
 
@@ -705,25 +721,40 @@ __global__ void dense_y_plan_kernel(DenseYState Q) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int nact = 0, nch = 0, used = 0;
   if (!dense_stopped(Q.stop)) {
+    const int tn = Q.unit_cols;
     Q.chunk_ptr[0] = 0;
     for (int64_t f = 0; f < Q.n; ++f) {
       if (!Q.active[f]) continue;
-      const int D = (int)(Q.ystart[f + 1] - Q.ystart[f]);
-      if (used + D > DN_TN) { ++nch; Q.chunk_ptr[nch] = nact; used = 0; }
+      const int64_t y0 = Q.ystart[f];
+      const int D = (int)(Q.ystart[f + 1] - y0);
+      if (used + D > tn) {
+        if (Q.ucol_feat != nullptr) for (int c = used; c < tn; ++c) { Q.ucol_feat[nch * tn + c] = -1; Q.ucol_y[nch * tn + c] = -1; }
+        ++nch; Q.chunk_ptr[nch] = nact; used = 0;
+      }
       Q.feat_list[nact] = (int32_t)f;
       Q.feat_off[nact] = used;
+      if (Q.ucol_feat != nullptr) for (int c = 0; c < D; ++c) { Q.ucol_feat[nch * tn + used + c] = (int32_t)f; Q.ucol_y[nch * tn + used + c] = (int32_t)(y0 + c); }
       used += D;
       ++nact;
     }
-    if (nact > 0) { ++nch; Q.chunk_ptr[nch] = nact; }
+    if (nact > 0) {
+      if (Q.ucol_feat != nullptr) for (int c = used; c < tn; ++c) { Q.ucol_feat[nch * tn + c] = -1; Q.ucol_y[nch * tn + c] = -1; }
+      ++nch; Q.chunk_ptr[nch] = nact;
+    }
   }
   *Q.nchunks = nch;
   *Q.nactive = nact;
-  Q.h_nactive[0] = nact;               // the host stops enqueuing line-search rounds once it reads (0, this sweep's number)
+  // published to the host in a ring of 4 (count, key) slots indexed by the round: the host reads the plan of exactly the
+  // round it waits for (never a later one), so that several ranks — whose devices run at different paces — all take the
+  // same decision at the same round and keep enqueuing their collectives in lockstep
+  volatile int32_t* slot = Q.h_nactive + 2 * (Q.seq & 3);
+  slot[0] = nact;                      // the host stops enqueuing line-search rounds once it reads (0, key of this plan)
   __threadfence_system();
-  Q.h_nactive[1] = Q.seq;
+  slot[1] = Q.seq;
   __threadfence_system();
 }
+
+#endif  // GLRM_DENSE_HELPERS_ONLY
 
 // after the gradient pass: obj_old = loss + ry(y_f), search state (proxgrad.jl:177-179); one lane group per feature column
 template <int TG, int TR>
@@ -798,6 +829,7 @@ __global__ void __launch_bounds__(128) dense_y_step_kernel(DenseYState Q) {
   if (ok && lg == 0) Q.regnew[f] = rv;
 }
 
+#ifndef GLRM_DENSE_HELPERS_ONLY
 // accept / reject per feature (proxgrad.jl:186-199)
 __global__ void dense_y_decide_kernel(DenseYState Q) {
   if (dense_stopped(Q.stop)) return;
@@ -820,5 +852,7 @@ __global__ void dense_y_decide_kernel(DenseYState Q) {
   Q.alpha[f] = a;
   if (Q.trial_counter) atomicAdd(Q.trial_counter, 1ull);
 }
+
+#endif  // GLRM_DENSE_HELPERS_ONLY
 
 }  // namespace glrm

@@ -128,9 +128,18 @@ struct DenseHost {
   int max_chunks = 1;
   double *d_gscratch = nullptr, *d_gpart = nullptr, *d_objpart = nullptr, *d_G = nullptr, *d_Ynew = nullptr;
   double *d_colobj = nullptr, *d_objold = nullptr, *d_regnew = nullptr;
-  int n_blocks = 1;
+  int n_blocks = 1;                         // DN_GROUPS * bg row blocks (fixed by m alone)
+  int bg = 1;                               // row blocks per group
   int64_t rows_per_block = 0;
+  int64_t row0 = 0, row1 = 0;               // rows this rank owns (multi-GPU: whole groups of row blocks; else all rows)
+  int g0 = 0, g1 = DN_GROUPS;               // its groups
+  double *d_gsum_G = nullptr, *d_gsum_o = nullptr, *d_gsum_x = nullptr;   // per-group partial sums [DN_GROUPS][...]
   int x_grid = 1;
+  // tensor-core kernels (glrm_dense_mma.cuh): factor width in n-tiles, pipeline stages, per-unit column tables of both plans
+  bool mma = false;
+  int nt = 0, nst = 0;
+  int unit_cols = DN_TN;
+  int32_t *d_ucol_feat = nullptr, *d_ucol_y = nullptr, *d_ucol_feat2 = nullptr, *d_ucol_y2 = nullptr;
   volatile int32_t* h_nactive = nullptr;    // mapped pinned [2]: (features still searching, sweep sequence number)
   int32_t seq = 0;
 };
@@ -207,8 +216,8 @@ static int check_device() {
   return 0;
 }
 
-// Pinned, device-mapped scratch of a handle: [0..7] doubles for scalar read-backs, [8] the stop flag, [10] the dense path's
-// (features still searching, sweep number) pair.  cudaHostAlloc / cudaFreeHost are slow and synchronising, so blocks are
+// Pinned, device-mapped scratch of a handle: [0..7] doubles for scalar read-backs, [8] the stop flag, [10..13] the dense path's
+// ring of 4 (features still searching, plan key) pairs.  cudaHostAlloc / cudaFreeHost are slow and synchronising, so blocks are
 // recycled through a process-level free list (distinct handles never share a block: they may run on different threads).
 static std::mutex g_pinned_mu;
 static std::vector<double*> g_pinned_free;
@@ -470,19 +479,33 @@ static void dense_free(glrmb200_engine* E) {
   dfree(D.d_nactive, E->stream); dfree(D.d_active, E->stream); dfree(D.d_diag, E->stream);
   dfree(D.d_gscratch, E->stream); dfree(D.d_gpart, E->stream); dfree(D.d_objpart, E->stream); dfree(D.d_G, E->stream);
   dfree(D.d_Ynew, E->stream); dfree(D.d_colobj, E->stream); dfree(D.d_objold, E->stream); dfree(D.d_regnew, E->stream);
+  dfree(D.d_gsum_G, E->stream); dfree(D.d_gsum_o, E->stream); dfree(D.d_gsum_x, E->stream);
+  dfree(D.d_ucol_feat, E->stream); dfree(D.d_ucol_y, E->stream); dfree(D.d_ucol_feat2, E->stream); dfree(D.d_ucol_y2, E->stream);
   D.on = false;
 }
 
 // can this problem take the dense kernels?  fully observed, rank within the register-tile range, regularizers that act
 // element-wise on block columns (the ordinal block regularizers stay on the gather path), one rank
 static bool dense_eligible(const glrmb200_engine* E, const glrmb200_problem* P) {
-  if (!E->obs_full || E->k > 104 || E->nranks != 1) return false;
+  if (!E->obs_full || E->k > 104) return false;
+  // several GPUs (mode B): rows are sharded by whole groups of row blocks, Y is replicated; needs the
+  // group count to divide evenly and enough rows for every rank to own some
+  if (E->nranks != 1 && !((E->nranks == 2 || E->nranks == 4 || E->nranks == 8) && E->m >= 512 * (int64_t)E->nranks)) return false;
   if (const char* t = getenv("GLRMB200_DENSE")) { if (atoi(t) == 0) return false; }
   if (getenv("GLRMB200_TILE")) return false;
   for (int64_t i = 0; i < P->ry_count; ++i)
     if (P->ry_code[i] & (GLRMB200_REG_ORDINAL | GLRMB200_REG_MNL_ORDINAL)) return false;
   if (P->rx_payload_ptr || P->ry_payload_ptr) return false;      // regularizers with vector payloads run on the gather kernels
   return true;
+}
+
+// row blocks of the Y sweep: DN_GROUPS groups of up to 37 blocks (two CTA waves of 148), fixed by m alone so that neither
+// the reduction order nor the multi-GPU row shards depend on the launch
+static void dense_blocks(int64_t m, int* bg, int64_t* rows_per_block) {
+  const int64_t tiles = (m + DN_TM - 1) / DN_TM;
+  *bg = (int)std::min<int64_t>(37, std::max<int64_t>(1, (tiles + DN_GROUPS - 1) / DN_GROUPS));
+  const int64_t nb = (int64_t)DN_GROUPS * *bg;
+  *rows_per_block = ((m + nb - 1) / nb + DN_TM - 1) / DN_TM * DN_TM;
 }
 
 static int dense_setup(glrmb200_engine* E, const glrmb200_problem* P) {
@@ -493,19 +516,43 @@ static int dense_setup(glrmb200_engine* E, const glrmb200_problem* P) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, E->device);
   D.sms = sms;
-  // A as Julia stores it (column-major), columns padded to whole 64-row tiles: every tile column is one aligned
-  // 512-byte bulk copy, and the rows past m read as zero
-  D.lda = (m + DN_TM - 1) / DN_TM * DN_TM;
+  // row blocks / groups, and the rows this rank owns (whole groups)
+  dense_blocks(m, &D.bg, &D.rows_per_block);
+  D.n_blocks = DN_GROUPS * D.bg;
+  D.g0 = E->rank * DN_GROUPS / E->nranks;
+  D.g1 = (E->rank + 1) * DN_GROUPS / E->nranks;
+  D.row0 = std::min<int64_t>(m, (int64_t)D.g0 * D.bg * D.rows_per_block);
+  D.row1 = std::min<int64_t>(m, (int64_t)D.g1 * D.bg * D.rows_per_block);
+  const int64_t mloc = D.row1 - D.row0;
+  // A as Julia stores it (column-major), this rank's rows only, columns padded to whole 64-row tiles: every tile column is
+  // one aligned 512-byte bulk copy, and the rows past the end read as zero.  (row0 is a multiple of the tile height.)
+  D.lda = std::max<int64_t>(DN_TM, (mloc + DN_TM - 1) / DN_TM * DN_TM);
   if ((rc = dalloc(&D.d_A, (size_t)(D.lda * n), E->stream))) return rc;
   if (D.lda == m) {
     CUDA_OK(cudaMemcpyAsync(D.d_A, P->dense_A, (size_t)(m * n) * sizeof(double), cudaMemcpyHostToDevice, E->stream));
   } else {
     CUDA_OK(cudaMemsetAsync(D.d_A, 0, (size_t)(D.lda * n) * sizeof(double), E->stream));
-    CUDA_OK(cudaMemcpy2DAsync(D.d_A, (size_t)D.lda * sizeof(double), P->dense_A, (size_t)m * sizeof(double), (size_t)m * sizeof(double),
-                              (size_t)n, cudaMemcpyHostToDevice, E->stream));
+    if (mloc > 0)
+      CUDA_OK(cudaMemcpy2DAsync(D.d_A, (size_t)D.lda * sizeof(double), P->dense_A + D.row0, (size_t)m * sizeof(double),
+                                (size_t)mloc * sizeof(double), (size_t)n, cudaMemcpyHostToDevice, E->stream));
+  }
+  // tensor-core kernels (default): as many pipeline stages as fit next to the own tile; GLRMB200_DENSE_MMA=0 keeps the
+  // FP64-FMA kernels of glrm_dense.cuh
+  {
+    const bool generic = E->loss_template != GLRMB200_LOSS_QUAD;
+    D.nt = mm_nt_for_k((int)E->k);
+    D.mma = D.nt > 0 && 8 * D.nt <= E->stride && !(getenv("GLRMB200_DENSE_MMA") && atoi(getenv("GLRMB200_DENSE_MMA")) == 0);
+    D.nst = 0;
+    if (D.mma) {
+      for (int s = MM_MAX_STAGES; s >= 2 && D.nst == 0; --s)
+        if (mm_smem_bytes(D.nt, s, generic) <= (size_t)227 * 1024) D.nst = s;
+      if (const char* t = getenv("GLRMB200_MMA_STAGES")) { const int v = atoi(t); if (v >= 2 && v <= D.nst) D.nst = v; }
+      if (D.nst == 0) D.mma = false;
+    }
+    D.unit_cols = D.mma ? MM_UNIT : DN_TN;
   }
   // shared memory: two tile buffers of A when a CTA fills the SM anyway, one when that lets two CTAs share the SM
-  {
+  if (!D.mma) {
     const size_t cap = 227 * 1024;
     const size_t s1 = dense_smem_needed((int)E->k, D.kt, 1) + 1024, s2 = dense_smem_needed((int)E->k, D.kt, 2) + 1024;
     if (s1 > cap) return fail(GLRMB200_E_UNSUPPORTED, "dense path: k = %lld needs too much shared memory", (long long)E->k);
@@ -516,20 +563,33 @@ static int dense_setup(glrmb200_engine* E, const glrmb200_problem* P) {
     if (const char* t = getenv("GLRMB200_DENSE_NBUF")) { const int v = atoi(t); if (v == 1 || (v == 2 && s2 <= cap)) { D.nbuf = v; D.ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, cap / (v == 1 ? s1 : s2))); } }
     if (const char* t = getenv("GLRMB200_DENSE_CTAS")) { const int v = atoi(t); if (v == 1) D.ctas_per_sm = 1; }
   }
-  // static plan: all features in order, chunks of <= DN_TN columns made of whole features
-  std::vector<int32_t> chunk_ptr{0}, feat_list, feat_off;
+  // static plan: all features in order, chunks of <= unit_cols columns made of whole features
+  const int tn = D.unit_cols;
+  std::vector<int32_t> chunk_ptr{0}, feat_list, feat_off, ucol_feat, ucol_y;
   int used = 0;
   for (int64_t f = 0; f < n; ++f) {
     const int dim = (int)(E->ystart[(size_t)f + 1] - E->ystart[(size_t)f]);
-    if (used + dim > DN_TN) { chunk_ptr.push_back((int32_t)feat_list.size()); used = 0; }
+    if (used + dim > tn) {
+      chunk_ptr.push_back((int32_t)feat_list.size());
+      ucol_feat.resize(ucol_feat.size() + (size_t)(tn - used), -1); ucol_y.resize(ucol_y.size() + (size_t)(tn - used), -1);
+      used = 0;
+    }
     feat_list.push_back((int32_t)f);
     feat_off.push_back(used);
+    for (int c = 0; c < dim; ++c) { ucol_feat.push_back((int32_t)f); ucol_y.push_back((int32_t)(E->ystart[(size_t)f] + c)); }
     used += dim;
   }
   chunk_ptr.push_back((int32_t)feat_list.size());
+  ucol_feat.resize(ucol_feat.size() + (size_t)(tn - used), -1); ucol_y.resize(ucol_y.size() + (size_t)(tn - used), -1);
   const int32_t nchunks = (int32_t)chunk_ptr.size() - 1;
-  D.max_chunks = 2 * (int)((d + DN_TN - 1) / DN_TN) + 1;           // next-fit bound for any subset of the features
+  D.max_chunks = 2 * (int)((d + tn - 1) / tn) + 1;                 // next-fit bound for any subset of the features
   if (D.max_chunks < nchunks) D.max_chunks = nchunks;
+  if (D.mma) {
+    if ((rc = upload(&D.d_ucol_feat, ucol_feat.data(), ucol_feat.size(), E->stream))) return rc;
+    if ((rc = upload(&D.d_ucol_y, ucol_y.data(), ucol_y.size(), E->stream))) return rc;
+    if ((rc = dalloc(&D.d_ucol_feat2, (size_t)D.max_chunks * MM_UNIT, E->stream))) return rc;
+    if ((rc = dalloc(&D.d_ucol_y2, (size_t)D.max_chunks * MM_UNIT, E->stream))) return rc;
+  }
   if ((rc = upload(&D.d_chunk_ptr, chunk_ptr.data(), chunk_ptr.size(), E->stream))) return rc;
   if ((rc = upload(&D.d_feat_list, feat_list.data(), feat_list.size(), E->stream))) return rc;
   if ((rc = upload(&D.d_feat_off, feat_off.data(), feat_off.size(), E->stream))) return rc;
@@ -545,21 +605,24 @@ static int dense_setup(glrmb200_engine* E, const glrmb200_problem* P) {
   CUDA_OK(cudaMemsetAsync(D.d_active, 0, (size_t)n * sizeof(int32_t), E->stream));
   CUDA_OK(cudaMemsetAsync(D.d_nactive, 0, sizeof(int32_t), E->stream));
   CUDA_OK(cudaMemsetAsync(D.d_nchunks2, 0, sizeof(int32_t), E->stream));
-  // row blocks of the Y sweep: 8 groups of up to 37 blocks (two CTA waves of 148), fixed by m alone so that the
-  // reduction order never depends on the launch
-  const int64_t tiles = (m + DN_TM - 1) / DN_TM;
-  const int bg = (int)std::min<int64_t>(37, std::max<int64_t>(1, (tiles + 7) / 8));
-  D.n_blocks = 8 * bg;
-  D.rows_per_block = ((m + D.n_blocks - 1) / D.n_blocks + DN_TM - 1) / DN_TM * DN_TM;
-  D.x_grid = (int)std::min<int64_t>(tiles, (int64_t)sms * D.ctas_per_sm);
-  if ((rc = dalloc(&D.d_gscratch, (size_t)D.x_grid * DN_TM * E->stride, E->stream))) return rc;
-  CUDA_OK(cudaMemsetAsync(D.d_gscratch, 0, (size_t)D.x_grid * DN_TM * E->stride * sizeof(double), E->stream));   // lanes past the register tiles stay zero
+  const int tile_rows = D.mma ? MM_TM : DN_TM;
+  const int64_t tiles = std::max<int64_t>(1, (mloc + tile_rows - 1) / tile_rows);
+  D.x_grid = (int)std::min<int64_t>(tiles, D.mma ? (int64_t)sms : (int64_t)sms * D.ctas_per_sm);
+  if ((rc = dalloc(&D.d_gscratch, (size_t)D.x_grid * tile_rows * E->stride, E->stream))) return rc;
+  CUDA_OK(cudaMemsetAsync(D.d_gscratch, 0, (size_t)D.x_grid * tile_rows * E->stride * sizeof(double), E->stream));   // lanes past the register tiles stay zero
   if ((rc = dalloc(&D.d_gpart, (size_t)D.n_blocks * (size_t)d * E->stride, E->stream))) return rc;
+  CUDA_OK(cudaMemsetAsync(D.d_gpart, 0, (size_t)D.n_blocks * (size_t)d * E->stride * sizeof(double), E->stream));   // (the same)
   if ((rc = dalloc(&D.d_objpart, (size_t)D.n_blocks * (size_t)n, E->stream))) return rc;
   CUDA_OK(cudaMemsetAsync(D.d_objpart, 0, (size_t)D.n_blocks * (size_t)n * sizeof(double), E->stream));
   if ((rc = dalloc(&D.d_G, (size_t)d * E->stride, E->stream))) return rc;
   if ((rc = dalloc(&D.d_Ynew, (size_t)d * E->stride, E->stream))) return rc;
   CUDA_OK(cudaMemsetAsync(D.d_Ynew, 0, (size_t)d * E->stride * sizeof(double), E->stream));
+  if ((rc = dalloc(&D.d_gsum_G, (size_t)DN_GROUPS * (size_t)d * E->stride, E->stream))) return rc;
+  if ((rc = dalloc(&D.d_gsum_o, (size_t)DN_GROUPS * (size_t)n, E->stream))) return rc;
+  if ((rc = dalloc(&D.d_gsum_x, DN_GROUPS, E->stream))) return rc;
+  CUDA_OK(cudaMemsetAsync(D.d_gsum_G, 0, (size_t)DN_GROUPS * (size_t)d * E->stride * sizeof(double), E->stream));
+  CUDA_OK(cudaMemsetAsync(D.d_gsum_o, 0, (size_t)DN_GROUPS * (size_t)n * sizeof(double), E->stream));
+  CUDA_OK(cudaMemsetAsync(D.d_gsum_x, 0, DN_GROUPS * sizeof(double), E->stream));
   if ((rc = dalloc(&D.d_colobj, (size_t)n, E->stream))) return rc;
   if ((rc = dalloc(&D.d_objold, (size_t)n, E->stream))) return rc;
   if ((rc = dalloc(&D.d_regnew, (size_t)n, E->stream))) return rc;
@@ -572,8 +635,10 @@ static DenseArgs dense_args(const glrmb200_engine* E, bool static_plan, const do
   const DenseHost& D = E->dn;
   DenseArgs P;
   memset(&P, 0, sizeof(P));
-  P.A = D.d_A; P.m = E->m; P.n = E->n; P.lda = D.lda; P.nbuf = D.nbuf; P.diag = D.d_diag;
-  P.row0 = 0; P.row1 = E->m;
+  P.A = D.d_A - D.row0;                         // indexed by the global row: A[f * lda + e], e in [row0, row1)
+  P.m = E->m; P.n = E->n; P.lda = D.lda; P.nbuf = D.nbuf; P.diag = D.d_diag;
+  P.row0 = D.row0; P.row1 = D.row1;
+  P.block0 = D.g0 * D.bg;
   P.X = E->d_X; P.Ymat = Ymat;
   P.stride = E->stride; P.k = (int)E->k; P.kp = E->kp;
   P.ystart = E->d_ystart;
@@ -590,6 +655,10 @@ static DenseArgs dense_args(const glrmb200_engine* E, bool static_plan, const do
   P.flags = flags;
   P.gpart = D.d_gpart; P.objpart = D.d_objpart;
   P.rows_per_block = D.rows_per_block; P.n_blocks = D.n_blocks;
+  P.ucol_feat = static_plan ? D.d_ucol_feat : D.d_ucol_feat2;
+  P.ucol_y = static_plan ? D.d_ucol_y : D.d_ucol_y2;
+  P.nst = D.nst;
+  P.uparam[0] = E->uparam[0]; P.uparam[1] = E->uparam[1]; P.uparam[2] = E->uparam[2];
   return P;
 }
 static DenseYState dense_ystate(glrmb200_engine* E, int flags, double min_stepsize, bool honour_stop) {
@@ -610,6 +679,8 @@ static DenseYState dense_ystate(glrmb200_engine* E, int flags, double min_stepsi
   Q.stop = honour_stop ? E->d_stop : nullptr;
   Q.flags = flags;
   Q.seq = D.seq;
+  Q.unit_cols = D.unit_cols;
+  Q.ucol_feat = D.d_ucol_feat2; Q.ucol_y = D.d_ucol_y2;
   return Q;
 }
 #define DN_OK(call)                                                                                                   \
@@ -645,11 +716,15 @@ static int dense_sweep_x(glrmb200_engine* E, double min_stepsize, bool honour_st
   const DenseHost& D = E->dn;
   const int loss = E->loss_template == GLRMB200_LOSS_QUAD ? GLRMB200_LOSS_QUAD : 0;
   DenseArgs P = dense_args(E, true, E->d_Y, 0, min_stepsize, honour_stop);
-  DN_OK(dense_launch_x(D.kt, E->tile_g, E->tile_r, loss, P, D.x_grid, E->stream));
+  if (D.mma) DN_OK(dense_mma_launch_x(D.nt, E->tile_g, E->tile_r, loss, P, D.x_grid, E->stream));
+  else DN_OK(dense_launch_x(D.kt, E->tile_g, E->tile_r, loss, P, D.x_grid, E->stream));
   DN_DBG("dense_x_kernel");
   ++*launches;
   return 0;
 }
+
+// all-gather of per-group partial sums ([DN_GROUPS][len], every rank owns the groups [g0, g1)); no-op on one rank
+static int dense_gather_groups(glrmb200_engine* E, double* gsum, int64_t len);
 
 static double dense_wait_limit_s() {
   if (const char* t = getenv("GLRMB200_WAIT_LIMIT_S")) return std::max(1.0, atof(t));
@@ -662,15 +737,24 @@ static int dense_eval_cols(glrmb200_engine* E, int flags, double min_stepsize, b
   DenseHost& D = E->dn;
   const int loss = E->loss_template == GLRMB200_LOSS_QUAD ? GLRMB200_LOSS_QUAD : 0;
   DenseArgs P = dense_args(E, true, E->d_Y, flags, min_stepsize, honour_stop);
-  DN_OK(dense_launch_y_pass(D.kt, loss, mode, P, D.n_blocks, D.max_chunks, E->stream));
+  const int local_blocks = (D.g1 - D.g0) * D.bg;
+  int rc;
+  if (D.mma) DN_OK(dense_mma_launch_y(D.nt, loss, mode, P, local_blocks, D.max_chunks, E->stream));
+  else DN_OK(dense_launch_y_pass(D.kt, loss, mode, P, local_blocks, D.max_chunks, E->stream));
   DN_DBG(mode == 0 ? "dense_y_pass_kernel (gradient)" : "dense_y_pass_kernel (evaluation)");
-  if (mode == 0) DN_OK(dense_launch_reduce(D.d_gpart, D.n_blocks, E->d * (int64_t)E->stride, D.d_G, nullptr, P.stop, E->stream));
-  DN_OK(dense_launch_reduce(D.d_objpart, D.n_blocks, E->n, D.d_colobj, nullptr, P.stop, E->stream));
-  DN_DBG("dense_reduce_kernel");
+  // fixed-order two-level reduction over the row blocks: this rank's groups, the other ranks' groups (all-gather), total
+  const int64_t glen = E->d * (int64_t)E->stride;
+  if (mode == 0) DN_OK(dense_launch_reduce_groups(D.d_gpart, D.bg, D.g0, D.g1, glen, D.d_gsum_G, nullptr, P.stop, E->stream));
+  DN_OK(dense_launch_reduce_groups(D.d_objpart, D.bg, D.g0, D.g1, E->n, D.d_gsum_o, nullptr, P.stop, E->stream));
+  if (mode == 0 && (rc = dense_gather_groups(E, D.d_gsum_G, glen))) return rc;
+  if ((rc = dense_gather_groups(E, D.d_gsum_o, E->n))) return rc;
+  if (mode == 0) DN_OK(dense_launch_reduce_total(D.d_gsum_G, glen, D.d_G, nullptr, P.stop, E->stream));
+  DN_OK(dense_launch_reduce_total(D.d_gsum_o, E->n, D.d_colobj, nullptr, P.stop, E->stream));
+  DN_DBG("dense_reduce kernels");
   DenseYState Q = dense_ystate(E, flags, min_stepsize, honour_stop);
   DN_OK(dense_launch_begin(E->tile_g, E->tile_r, Q, E->stream));
   DN_DBG("dense_y_begin_kernel");
-  *launches += mode == 0 ? 4 : 3;
+  *launches += mode == 0 ? 6 : 4;
   return 0;
 }
 
@@ -694,20 +778,24 @@ static int dense_sweep_y(glrmb200_engine* E, double min_stepsize, bool honour_st
     if (round >= 4095) return fail(GLRMB200_E_STATE, "dense Y line search did not terminate");
     DN_OK(dense_launch_step(E->tile_g, E->tile_r, Q, E->stream));
     DN_DBG("dense_y_step_kernel");
-    DN_OK(dense_launch_y_pass(D.kt, loss, 1, P, D.n_blocks, D.max_chunks, E->stream));
+    if (D.mma) DN_OK(dense_mma_launch_y(D.nt, loss, 1, P, (D.g1 - D.g0) * D.bg, D.max_chunks, E->stream));
+    else DN_OK(dense_launch_y_pass(D.kt, loss, 1, P, (D.g1 - D.g0) * D.bg, D.max_chunks, E->stream));
     DN_DBG("dense_y_pass_kernel (trial)");
-    DN_OK(dense_launch_reduce(D.d_objpart, D.n_blocks, E->n, D.d_colobj, D.d_nactive, P.stop, E->stream));
+    DN_OK(dense_launch_reduce_groups(D.d_objpart, D.bg, D.g0, D.g1, E->n, D.d_gsum_o, D.d_nactive, P.stop, E->stream));
+    if ((rc = dense_gather_groups(E, D.d_gsum_o, E->n))) return rc;
+    DN_OK(dense_launch_reduce_total(D.d_gsum_o, E->n, D.d_colobj, D.d_nactive, P.stop, E->stream));
     DN_OK(dense_launch_decide(Q, E->stream));
     DN_DBG("dense_y_decide_kernel");
     Q.seq = key(round + 1);
     DN_OK(dense_launch_plan(Q, E->stream));
-    *launches += 5;
+    *launches += 6;
     if (round == 0) continue;
-    // plan(round) or a later one of this sweep has been published?
+    // plan(round) has been published?  (slot round % 4 of the ring; at most the plans of rounds round .. round + 2 are
+    // outstanding, so the slot cannot have been overwritten)
+    volatile int32_t* slot = D.h_nactive + 2 * (round & 3);
     const auto t0 = std::chrono::steady_clock::now();
     for (int spin = 0;; ++spin) {
-      const int32_t k1 = D.h_nactive[1];
-      if ((k1 >> 12) == D.seq && (k1 & 4095) >= round) break;
+      if (slot[1] == key(round)) break;
       if ((spin & 1023) == 1023) {
         const cudaError_t q = cudaStreamQuery(E->stream);
         if (q == cudaSuccess) break;                                       // everything enqueued has run: the plan is there
@@ -717,7 +805,7 @@ static int dense_sweep_y(glrmb200_engine* E, double min_stepsize, bool honour_st
       }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
-    if (D.h_nactive[0] == 0) break;
+    if (slot[0] == 0) break;
   }
   return 0;
 }
@@ -966,6 +1054,14 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P, int flags)
     glrmb200_plan_shards(nullptr, m, E->nranks, R.bounds.data());
     glrmb200_plan_shards(nullptr, n, E->nranks, C.bounds.data());
   }   // (observation lists: checked, sharded and uploaded by load_lists below)
+  if (E->obs_full && want_dense && E->nranks > 1) {
+    // mode B: rank r owns the row-block groups [r * G / N, (r + 1) * G / N); every rank updates all of Y
+    int bg; int64_t rpb;
+    dense_blocks(m, &bg, &rpb);
+    for (int r = 0; r <= E->nranks; ++r) R.bounds[(size_t)r] = std::min<int64_t>(m, (int64_t)(r * DN_GROUPS / E->nranks) * bg * rpb);
+    C.bounds[0] = 0;
+    for (int r = 1; r <= E->nranks; ++r) C.bounds[(size_t)r] = n;
+  }
   R.begin = R.bounds[E->rank]; R.end = R.bounds[E->rank + 1];
   C.begin = C.bounds[E->rank]; C.end = C.bounds[E->rank + 1];
 
@@ -1029,7 +1125,8 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P, int flags)
     unsigned long long* d_bad = nullptr;
     if ((rc = dalloc(&d_bad, 1, E->stream))) return rc;
     CUDA_OK(cudaMemsetAsync(d_bad, 0xff, sizeof(unsigned long long), E->stream));
-    validate_dense_kernel<<<(unsigned)((E->dn.lda * n + 255) / 256), 256, 0, E->stream>>>(E->dn.d_A, E->dn.lda * n, m, E->dn.lda, E->d_loss_code, E->d_loss_param, d_bad);
+    const int64_t mloc = E->dn.row1 - E->dn.row0;   // this rank's rows (all of them on one GPU)
+    if (mloc > 0) validate_dense_kernel<<<(unsigned)((E->dn.lda * n + 255) / 256), 256, 0, E->stream>>>(E->dn.d_A, E->dn.lda * n, mloc, E->dn.lda, E->d_loss_code, E->d_loss_param, d_bad);
     CUDA_OK(cudaGetLastError());
     unsigned long long bad = 0;
     CUDA_OK(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
@@ -1038,7 +1135,7 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P, int flags)
     if (bad != ~0ULL) {
       const int kind = -(int)(bad & 15ULL);
       const int64_t pos = (int64_t)(bad >> 4);
-      const int64_t f = pos / m, e = pos % m;
+      const int64_t f = pos / mloc, e = E->dn.row0 + pos % mloc;
       if (kind == GLRMB200_E_NAN) return fail(kind, "Observed value in entry (%lld, %lld) is NaN.", (long long)e + 1, (long long)f + 1);
       return fail(kind, "entry (%lld, %lld): label %g is outside the domain of loss code %d", (long long)e + 1, (long long)f + 1, P->dense_A[f * m + e], P->loss_code[f]);
     }
@@ -1259,6 +1356,7 @@ extern "C" int glrmb200_ipc_open(glrmb200_handle E, const uint8_t* blobs) {
   if (!E || !blobs) return fail(GLRMB200_E_INVALID, "null argument");
   if (E->nranks == 1) return 0;
   if (E->has_vec) return 0;   // block columns keep the NCCL exchange this round
+  if (E->dn.on) return 0;     // fully observed path: no factor exchange at all (rows sharded, Y replicated)
   CUDA_OK(cudaSetDevice(E->device));
   const size_t nb = (size_t)E->nranks * GLRMB200_IPC_BYTES;
   if (!E->opened.empty() && E->peer_blobs.size() == nb && memcmp(E->peer_blobs.data(), blobs, nb) == 0) {
@@ -1334,6 +1432,14 @@ extern "C" int glrmb200_upload_factors(glrmb200_handle E, const double* X, const
     pack_launch(E, sy + yb * k, E->d_Y, yb, ye - yb, E->d_peer_Y, E->nranks - 1);
     CUDA_OK(cudaGetLastError());
     if ((rc = comm_barrier(E))) return rc;
+  } else if (E->dn.on && E->nranks > 1) {
+    // fully observed path on several GPUs: a rank only ever touches its own rows of X (and the whole of Y)
+    const int64_t rb = E->rows.begin, re = E->rows.end;
+    if (re > rb) CUDA_OK(cudaMemcpyAsync(sx + rb * k, X + rb * k, (size_t)((re - rb) * k) * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+    CUDA_OK(cudaMemcpyAsync(sy, Y, (size_t)(E->d * k) * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+    pack_launch(E, sx + rb * k, E->d_X, rb, re - rb, nullptr, 0);
+    pack_launch(E, sy, E->d_Y, 0, E->d, nullptr, 0);
+    CUDA_OK(cudaGetLastError());
   } else {
     CUDA_OK(cudaMemcpyAsync(sx, X, (size_t)(E->m * k) * sizeof(double), cudaMemcpyHostToDevice, E->stream));
     CUDA_OK(cudaMemcpyAsync(sy, Y, (size_t)(E->d * k) * sizeof(double), cudaMemcpyHostToDevice, E->stream));
@@ -1355,10 +1461,14 @@ extern "C" int glrmb200_download_factors(glrmb200_handle E, double* X, double* Y
   const int64_t k = E->k;
   double* sx = E->d_stage;
   double* sy = E->d_stage + E->m * k;
-  unpack_factor_kernel<<<(unsigned)((E->m * k + 255) / 256), 256, 0, E->stream>>>(E->d_X, sx, E->m, (int)k, E->stride);
+  // fully observed path on several GPUs: this rank holds (and returns) only its own rows of X; the caller's other rows
+  // are left as they are (each process of a multi-process fit gets its shard back)
+  const bool own_rows = E->dn.on && E->nranks > 1;
+  const int64_t rb = own_rows ? E->rows.begin : 0, re = own_rows ? E->rows.end : E->m;
+  if (re > rb) unpack_factor_kernel<<<(unsigned)(((re - rb) * k + 255) / 256), 256, 0, E->stream>>>(E->d_X + rb * E->stride, sx + rb * k, re - rb, (int)k, E->stride);
   unpack_factor_kernel<<<(unsigned)((E->d * k + 255) / 256), 256, 0, E->stream>>>(E->d_Y, sy, E->d, (int)k, E->stride);
   CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaMemcpyAsync(X, sx, (size_t)(E->m * k) * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  if (re > rb) CUDA_OK(cudaMemcpyAsync(X + rb * k, sx + rb * k, (size_t)((re - rb) * k) * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
   CUDA_OK(cudaMemcpyAsync(Y, sy, (size_t)(E->d * k) * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
   CUDA_OK(cudaStreamSynchronize(E->stream));
   return 0;
@@ -1376,6 +1486,18 @@ static int allgather_units(glrmb200_engine* E, double* buf, const Side& S, int64
     const int64_t cnt = (e - b) * elems;
     if (cnt == 0) continue;
     NCCL_OK(g_nccl.Broadcast(buf + b * elems, buf + b * elems, (size_t)cnt, kNcclDouble, r, E->comm, E->stream));
+  }
+  NCCL_OK(g_nccl.GroupEnd());
+  return 0;
+}
+
+static int dense_gather_groups(glrmb200_engine* E, double* gsum, int64_t len) {
+  if (E->nranks == 1 || len <= 0) return 0;
+  if (!E->comm) return fail(GLRMB200_E_STATE, "glrmb200_comm_init was not called");
+  NCCL_OK(g_nccl.GroupStart());
+  for (int r = 0; r < E->nranks; ++r) {
+    const int g0 = r * DN_GROUPS / E->nranks, g1 = (r + 1) * DN_GROUPS / E->nranks;
+    NCCL_OK(g_nccl.Broadcast(gsum + (int64_t)g0 * len, gsum + (int64_t)g0 * len, (size_t)((g1 - g0) * len), kNcclDouble, r, E->comm, E->stream));
   }
   NCCL_OK(g_nccl.GroupEnd());
   return 0;
@@ -1400,6 +1522,25 @@ static int objective_resident(glrmb200_engine* E, bool include_reg, double* out,
     if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "penalty launch: %s", cudaGetErrorString(ce));
     ++*launches;
   }
+  if (E->dn.on) {
+    // fully observed path: Y (and obj_by_col) are replicated, rows are owned by whole groups of row blocks; the row penalties
+    // are summed per group (by the owner), gathered, and totalled in group order — the same tree on 1, 2, 4 or 8 ranks
+    sum_kernel<<<1, 1024, 0, E->stream>>>(E->cols.d_obj, E->n, E->d_scalars);
+    ++*launches;
+    if (include_reg) {
+      DenseHost& D = E->dn;
+      const int64_t grows = (int64_t)D.bg * D.rows_per_block;
+      for (int g = D.g0; g < D.g1; ++g) {
+        const int64_t b = std::min<int64_t>(E->m, g * grows), e = std::min<int64_t>(E->m, (g + 1) * grows);
+        sum_kernel<<<1, 1024, 0, E->stream>>>(E->rows.d_obj + b, e - b, D.d_gsum_x + g);
+        ++*launches;
+      }
+      int rcg = dense_gather_groups(E, D.d_gsum_x, 1);
+      if (rcg) return rcg;
+      sum_kernel<<<1, 1024, 0, E->stream>>>(D.d_gsum_x, DN_GROUPS, E->d_scalars + 1);
+      ++*launches;
+    }
+  } else {
   int rc = E->peer_ready ? comm_barrier(E) : allgather_units(E, E->cols.d_obj, E->cols, 1);
   if (rc) return rc;
   sum_kernel<<<1, 1024, 0, E->stream>>>(E->cols.d_obj, E->n, E->d_scalars);
@@ -1407,6 +1548,7 @@ static int objective_resident(glrmb200_engine* E, bool include_reg, double* out,
   if (include_reg) {
     sum_kernel<<<1, 1024, 0, E->stream>>>(E->rows.d_obj, E->m, E->d_scalars + 1);
     ++*launches;
+  }
   }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(E->h_pinned, E->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
@@ -1487,12 +1629,20 @@ extern "C" int glrmb200_fit_resident(glrmb200_handle E, const glrmb200_params* p
     harvested = upto;
     return 0;
   };
+  const int sync_every = E->nranks == 1 ? 0 : (E->dn.on ? 1 : 8);
   for (int it = 1; it <= max_iter; ++it) {                                // :107
     if (it > 1 && (it - 1) % EVENT_CHUNK == 0) {                           // the event pool wraps: harvest the chunk first
       CUDA_OK(cudaStreamSynchronize(E->stream));
       harvest(it - 1);
     }
-    if (*E->h_stop != 0) break;                                            // the device has stopped: nothing more to enqueue
+    // the device has stopped: nothing more to enqueue.  Several ranks must leave the loop at the SAME iteration (they
+    // enqueue collectives / peer barriers in lockstep), so they only look at the flag after a synchronisation, at
+    // iterations fixed in advance; the iterations enqueued in between return at once on every rank.
+    if (sync_every == 0) { if (*E->h_stop != 0) break; }
+    else if (it > 1 && (it - 1) % sync_every == 0) {
+      CUDA_OK(cudaStreamSynchronize(E->stream));
+      if (*E->h_stop != 0) break;
+    }
     cudaEvent_t* ev = &E->evpool[(size_t)((it - 1) % EVENT_CHUNK) * 5];
     if (prm->inner_iter_X > 1 || prm->inner_iter_Y > 1) {                  // :112-115
       if ((rc = fill(E, E->rows.d_alpha, E->m, prm->stepsize, E->d_stop))) return rc;
@@ -1507,7 +1657,8 @@ extern "C" int glrmb200_fit_resident(glrmb200_handle E, const glrmb200_params* p
       if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "update-X launch: %s", cudaGetErrorString(ce));
     }
     CUDA_OK(cudaEventRecord(ev[1], E->stream));
-    if (E->peer_ready) { if ((rc = comm_barrier(E))) return rc; }          // columns already stored into the peers
+    if (E->dn.on) {}                                                       // fully observed path: X never leaves its owner
+    else if (E->peer_ready) { if ((rc = comm_barrier(E))) return rc; }     // columns already stored into the peers
     else if ((rc = allgather_units(E, E->d_X, E->rows, E->stride))) return rc;
     CUDA_OK(cudaEventRecord(ev[2], E->stream));
     for (int inner = 0; inner < prm->inner_iter_Y; ++inner) {              // :160-203
@@ -1518,7 +1669,8 @@ extern "C" int glrmb200_fit_resident(glrmb200_handle E, const glrmb200_params* p
       if (ce != cudaSuccess) return fail(GLRMB200_E_CUDA, "update-Y launch: %s", cudaGetErrorString(ce));
     }
     CUDA_OK(cudaEventRecord(ev[3], E->stream));
-    if (E->peer_ready) { if ((rc = comm_barrier(E))) return rc; }
+    if (E->dn.on) {}                                                       // ... and every rank holds the whole of Y
+    else if (E->peer_ready) { if ((rc = comm_barrier(E))) return rc; }
     else {
       if ((rc = allgather_units(E, E->d_Y, E->cols, E->stride, E->has_vec ? E->ystart.data() : nullptr))) return rc;
       if ((rc = allgather_units(E, E->cols.d_obj, E->cols, 1))) return rc;

@@ -34,4 +34,4 @@ def test_sharded_fit_is_bit_identical_to_single_gpu(world):
         if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("identical=True") == 4
+    assert r.stdout.count("identical=True") == 6

@@ -399,7 +399,8 @@ def test_errors_through_the_abi():
     epq.keep["row_val"][11] = np.nan
     assert L.glrmb200_create(C.byref(h), C.byref(epq.struct), 0, 0, 1) == -7
     A = np.floor(synth.uniform(1, 1, np.arange(60)).reshape(20, 3) * 3) + 1
-    for g2 in (lrm.GLRM(A, lrm.MultinomialLoss(3), lrm.ZeroReg(), lrm.ZeroReg(), 40),           # block columns need k <= 32
+    part = [(i, j) for i in range(20) for j in range(3) if (i, j) != (7, 1)]                    # not fully observed: gather kernels
+    for g2 in (lrm.GLRM(A, lrm.MultinomialLoss(3), lrm.ZeroReg(), lrm.ZeroReg(), 40, obs=part),  # block columns need k <= 32 there
                lrm.GLRM(A * 3, lrm.MultinomialLoss(9), lrm.ZeroReg(), lrm.ZeroReg(), 2),        # embedding dim > 8
                lrm.GLRM(A, lrm.MultinomialLoss(3), lrm.ZeroReg(), lrm.UnitOneSparseConstraint(), 2)):  # non-separable block reg
         with pytest.raises(_abi.GLRMB200Error) as ei:

@@ -23,8 +23,11 @@ for name, scale, oracle_iters in [(a.split("/")[0], int(a.split("/")[1]), int(a.
     g = problem(name, scale)
     ep = lrm.encode_problem(g, validate=False)
     tgen = time.time() - t
-    for dense in ("1", "0"):
-        os.environ["GLRMB200_DENSE"] = dense
+    for dense in ("1", "fma", "0"):                   # tensor-core kernels, FP64-FMA kernels (glrm_dense.cuh), gather kernels
+        os.environ["GLRMB200_DENSE"] = "0" if dense == "0" else "1"
+        os.environ["GLRMB200_DENSE_MMA"] = "0" if dense == "fma" else "1"
+        if dense in os.environ.get("DENSE_CHECK_SKIP", "").split(","):
+            continue
         if dense == "0" and ep.nnz > 400_000_000:
             continue
         t = time.time()

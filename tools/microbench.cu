@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <vector>
 
@@ -194,6 +195,27 @@ __global__ void __launch_bounds__(256) dfma_peak(double* out, int iters) {
   if (s == 1.2345e300) out[0] = s;
 }
 
+// ---- FP64 tensor-core (DMMA m8n8k4) peak: 8 independent accumulator pairs per warp ---------------------------------------
+__global__ void __launch_bounds__(256) dmma_peak(double* out, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x * 1e-9 + i; c[i][1] = i; }
+  const double a = 1.0000000001, b = 0.25 + 1e-12 * threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  if (s == 1.2345e300) out[0] = s;
+}
+
 __global__ void stream_read(const double2* __restrict__ p, int64_t n, double* out) {
   double acc = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -233,7 +255,8 @@ static uint64_t splitmix(uint64_t& s) {
   return z ^ (z >> 31);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  const bool only_fp64 = argc > 1 && strcmp(argv[1], "fp64") == 0;   // `microbench fp64`: just the FP64 pipe sections
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
@@ -245,7 +268,7 @@ int main() {
   std::vector<int32_t> h_idx((size_t)n_entries);
   int32_t* d_idx;
   CK(cudaMalloc(&d_idx, n_entries * 4));
-  for (int which = 0; which < 2; ++which) {
+  for (int which = 0; which < (only_fp64 ? 0 : 2); ++which) {
     const int64_t ncols = which == 0 ? 26744 : 138493;
     uint64_t seed = 12345 + which;
     for (auto& v : h_idx) v = (int32_t)(splitmix(seed) % (uint64_t)ncols);
@@ -309,7 +332,24 @@ int main() {
     const double flops = 2.0 * 64.0 * iters * 256.0 * sms * 8;
     printf(", \"dfma_peak\": {\"ms\": %.4f, \"TFLOPs\": %.2f}", ms, flops / (ms * 1e-3) / 1e12);
   }
-  {  // HBM streaming
+  {  // FP64 FMA rate with one warp per scheduler (128 threads per SM) and with two
+    const int iters = 4000;
+    float ms = time_ms([&] { dfma_peak<<<sms, 128>>>(d_out, iters); });
+    printf(", \"dfma_4warps_per_sm\": {\"ms\": %.4f, \"TFLOPs\": %.2f}", ms, 2.0 * 64.0 * iters * 128.0 * sms / (ms * 1e-3) / 1e12);
+    ms = time_ms([&] { dfma_peak<<<sms, 256>>>(d_out, iters); });
+    printf(", \"dfma_8warps_per_sm\": {\"ms\": %.4f, \"TFLOPs\": %.2f}", ms, 2.0 * 64.0 * iters * 256.0 * sms / (ms * 1e-3) / 1e12);
+  }
+  {  // FP64 tensor-core rate (mma.sync m8n8k4 = 256 FMA per warp instruction)
+    const int iters = 2000;
+    const double fl = 2.0 * 256.0 * 32.0 * iters;   // per warp
+    float ms = time_ms([&] { dmma_peak<<<sms * 8, 256>>>(d_out, iters); });
+    printf(", \"dmma_peak\": {\"ms\": %.4f, \"TFLOPs\": %.2f}", ms, fl * 8.0 * sms * 8 / (ms * 1e-3) / 1e12);
+    ms = time_ms([&] { dmma_peak<<<sms, 128>>>(d_out, iters); });
+    printf(", \"dmma_4warps_per_sm\": {\"ms\": %.4f, \"TFLOPs\": %.2f}", ms, fl * 4.0 * sms / (ms * 1e-3) / 1e12);
+    ms = time_ms([&] { dmma_peak<<<sms, 256>>>(d_out, iters); });
+    printf(", \"dmma_8warps_per_sm\": {\"ms\": %.4f, \"TFLOPs\": %.2f}", ms, fl * 8.0 * sms / (ms * 1e-3) / 1e12);
+  }
+  if (!only_fp64) {  // HBM streaming
     const int64_t n = (int64_t)4 << 30;        // 4 GiB
     double2 *p, *q;
     CK(cudaMalloc(&p, n)); CK(cudaMalloc(&q, n));
