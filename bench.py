@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 METRIC = "observed-entries/sec/iter (X+Y sweep) at k=50"
 UNIT = "entries/s/iter"
 PARITY_TOL = 1e-4            # north_star: objective trajectories within 1e-4 relative of the reference
-FP64_PEAK_TFLOPS = 36.58     # tools/microbench.cu dfma_peak on this pool's B200 (profiles/r2_microbench.json)
+FP64_PEAK_TFLOPS = 37.06     # tools/microbench.cu dmma_peak (FP64 mma.sync m8n8k4; DFMA: 36.58) on this pool's B200 (profiles/r2_microbench_fp64.json)
 
 
 def log(*a):
@@ -53,6 +53,11 @@ def peaks():
     try:
         mb = json.load(open(os.path.join(ROOT, "profiles", "r2_microbench.json")))
         out["fp64_tflops"] = float(mb["dfma_peak"]["TFLOPs"])
+        try:
+            mb2 = json.load(open(os.path.join(ROOT, "profiles", "r2_microbench_fp64.json")))
+            out["fp64_tflops"] = max(out["fp64_tflops"], float(mb2["dmma_peak"]["TFLOPs"]))
+        except Exception:
+            pass
         out["l2_gather_gbs"] = {"y": float(mb["ldg_d4_y13MB"]["GBps"]), "x": float(mb["ldg_d4_x71MB"]["GBps"])}
     except Exception:
         pass
@@ -320,7 +325,7 @@ def dense_roofline(m, n, d, k, x_ms, y_ms, T_x, T_y, pk):
         out[side] = {"ms": ms, "mean_trials": T, "algorithmic_flops": flops, "algorithmic_bytes": byts,
                      "fp64_tflops": flops / (ms * 1e-3) / 1e12, "fp64_frac": flops / (ms * 1e-3) / 1e12 / pk["fp64_tflops"],
                      "hbm_gbs": byts / (ms * 1e-3) / 1e9, "hbm_frac": byts / (ms * 1e-3) / 1e9 / pk["hbm_gbs"]}
-    out["peaks"] = {"fp64_tflops": pk["fp64_tflops"], "fp64_source": "tools/microbench.cu dfma_peak (profiles/r2_microbench.json)",
+    out["peaks"] = {"fp64_tflops": pk["fp64_tflops"], "fp64_source": "tools/microbench.cu dmma_peak / dfma_peak, the larger (profiles/r2_microbench_fp64.json)",
                     "hbm_gbs": pk["hbm_gbs"], "hbm_source": pk["hbm_source"]}
     return out
 
@@ -423,7 +428,7 @@ class Job:
                 self.comm_ready = True
             else:
                 eng.comm_init(None)         # the per-process NCCL communicator is cached inside the library
-            if not os.environ.get("GLRMB200_NO_PEER"):
+            if not os.environ.get("GLRMB200_NO_PEER") and not ep.struct.obs_full:
                 eng.peer_init(self.dist)    # fused exchange: peer stores from the update kernels (CUDA IPC over NVLink)
         return eng
 
@@ -472,8 +477,10 @@ def value_leg(job, g, ep, pk, sample_clocks):
     T_y = prof["y_trials"] / max(1, (ce - cb) * args.steps)
     # ---- roofline of the dominant kernel (update-X), SURVEY.md section 8d ------------------------------
     if dense:
-        dr = dense_roofline(m, n, int(ep.struct.d), k, prof["update_x_ms"] / args.steps, prof["update_y_ms"] / args.steps, T_x, T_y, pk)
-        roofline = {"bound": "fp64 pipe (FMA, not tensor: DESIGN.md section 4.4)", "kernel": "dense_x_kernel (one X sweep)",
+        # (several GPUs: rows are sharded, every rank passes over its own rows in both sweeps; Y's trials are counted on rank 0)
+        dr = dense_roofline(rows_local, n, int(ep.struct.d), k, prof["update_x_ms"] / args.steps, prof["update_y_ms"] / args.steps,
+                            T_x, prof["y_trials"] / max(1, n * args.steps), pk)
+        roofline = {"bound": "tensor (FP64 DMMA pipe; the same 37 TFLOP/s as the FP64 FMA pipe on B200)", "kernel": "dense_mma_x_kernel (one X sweep)",
                     "achieved": dr["update_x"]["fp64_tflops"], "peak": pk["fp64_tflops"], "unit": "TFLOP/s",
                     "frac": dr["update_x"]["fp64_frac"], "traffic": None, "both": dr}
     else:
@@ -512,8 +519,6 @@ def run_ours(args):
     nnz = ep.nnz
     m, n = g.shape
     dense = bool(ep.struct.obs_full)
-    if dense and world > 1:
-        raise SystemExit("the fully observed configurations run on one GPU in this build")
     log(f"[rank {rank}] problem ready in {time.time() - t_gen:.1f}s: {m}x{n}, nnz={nnz}, k={g.k}")
     if not dense:
         ep = pin_encoded(ep)
@@ -529,7 +534,7 @@ def run_ours(args):
     e1 = time.time()
     if world > 1:
         eng2.comm_init(None)
-        if not os.environ.get("GLRMB200_NO_PEER"):
+        if not os.environ.get("GLRMB200_NO_PEER") and not dense:
             eng2.peer_init(job.dist)
     e2 = time.time()
     obj2, _ = eng2.fit(pt, Xh, Yh)
@@ -601,7 +606,10 @@ def run_ours(args):
         "dtype": "f64", "data": "synthetic",
         "config": config_static(args.config) if args.scale == 1 else
         {"workload": config_static(args.config)["workload"] + f" - /{args.scale} twin ({m}x{n}, {nnz} obs)", "l2": "twin: not a bench configuration"},
-        "detail": {"parallelism": (f"rows/columns sharded over {world} GPU(s); " + ("single GPU" if world == 1 else
+        "detail": {"parallelism": (f"fully observed: rows of A and X sharded over {world} GPU(s) by whole row-block groups, Y replicated; "
+                                   "partial G_Y / per-feature objectives all-gathered per line-search round (NCCL) and summed in group order"
+                                   if dense and world > 1 else
+                                   f"rows/columns sharded over {world} GPU(s); " + ("single GPU" if world == 1 else
                                    "NCCL all-gather per half-iteration" if os.environ.get("GLRMB200_NO_PEER") else
                                    "accepted columns stored into every peer from the update kernels (CUDA IPC over NVLink), "
                                    "peer-memory flag barrier per half-iteration")),

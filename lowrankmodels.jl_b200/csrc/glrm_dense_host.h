@@ -78,6 +78,8 @@ struct DenseArgs {
   const int32_t* ucol_y;
   int32_t nst;
   double uparam[3];
+  unsigned long long* phase;  // [8] or nullptr: clocks of thread 0 per phase of the X sweep (GLRMB200_PHASE_TIMERS=1): waiting for
+                              // the tile, gradient pass, search set-up, trial points, trial losses, accept / compact; rounds; tiles
 };
 
 struct DenseYState {

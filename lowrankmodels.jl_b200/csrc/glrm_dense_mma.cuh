@@ -40,7 +40,7 @@ struct MmSmem {
   int* smeta;       // [nst][MI]  per stage: [0..31] feature of local column c; generic: [32..33] features per unit,
                     //            [34..65] feature lists, [66..99] first local column of each feature (+ end)
   int* rstate;      // X sweep: s_state[128], s_perm[128];  Y sweep: feature / Y column of own column c, unit lists
-  int* cnt;         // [0..7] compaction counts
+  int* cnt;         // [0..7] compaction counts, [9..10] some trial point of the round needs a pass over Y (by round parity)
 };
 template <int NT, bool GEN>
 __device__ __forceinline__ MmSmem mm_carve(unsigned char* base, int nst) {
@@ -158,6 +158,92 @@ __device__ __forceinline__ void mm_elem_uniform(const double* __restrict__ up, d
   }
 }
 
+// ---- element-wise phase, heterogeneous problem, stage (X sweep) / unit (Y sweep) made of ONE scalar loss type: on the fragments ----
+// Features keep their own parameters (scale, threshold ...).  YSIDE = false: the feature belongs to the other-side index
+// (column 8 nt + 2 t + e of the stage, colfeat[]); YSIDE = true: to the own row (fown[mt]).  The per-row / per-feature sums
+// follow the butterfly order of the scratch path (offsets 16, 8, 4, 2, 1 over the stage index), so a feature's loss is
+// the same number whichever path its unit takes (the Y sweep's trial passes regroup the features).
+template <int L, bool GRAD, int MT, bool YSIDE>
+__device__ __forceinline__ void mm_elem_cols_body(const DenseArgs& P, const int* __restrict__ colfeat, const int (&fown)[2], int t,
+                                                  double (&acc)[2][4][2], const double (&aP)[16], unsigned mown, unsigned moth,
+                                                  double (&lsum)[2]) {
+  double lv[2][4][2];
+  double so[2][3];
+  if (YSIDE) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const double* lp = P.loss_param + (int64_t)(fown[mt] >= 0 ? fown[mt] : 0) * GLRMB200_LOSS_NPARAM;
+      so[mt][0] = lp[0]; so[mt][1] = lp[1]; so[mt][2] = lp[2];
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double s = 1.0, p1 = 0.0, p2 = 0.0;
+      if (!YSIDE) {
+        const int f = colfeat[8 * nt + 2 * t + e];
+        const double* lp = P.loss_param + (int64_t)(f >= 0 ? f : 0) * GLRMB200_LOSS_NPARAM;
+        s = lp[0]; p1 = lp[1]; p2 = lp[2];
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const bool valid = ((mown >> mt) & 1u) && ((moth >> (2 * nt + e)) & 1u);
+        double l, c;
+        if (YSIDE) loss_eval<L, GRAD>(L, so[mt][0], so[mt][1], so[mt][2], acc[mt][nt][e], aP[mt * 8 + nt * 2 + e], l, c);
+        else loss_eval<L, GRAD>(L, s, p1, p2, acc[mt][nt][e], aP[mt * 8 + nt * 2 + e], l, c);
+        if (GRAD) acc[mt][nt][e] = valid ? c : 0.0;
+        lv[mt][nt][e] = valid ? l : 0.0;
+      }
+    }
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    double v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      v[e] = (lv[mt][0][e] + lv[mt][2][e]) + (lv[mt][1][e] + lv[mt][3][e]);
+      v[e] += __shfl_xor_sync(FULLMASK, v[e], 2);
+      v[e] += __shfl_xor_sync(FULLMASK, v[e], 1);
+    }
+    lsum[mt] = v[0] + v[1];
+  }
+}
+template <bool GRAD, int MT, bool YSIDE>
+__device__ __forceinline__ void mm_elem_cols(int code, const DenseArgs& P, const int* __restrict__ colfeat, const int (&fown)[2], int t,
+                                             double (&acc)[2][4][2], const double (&aP)[16], unsigned mown, unsigned moth,
+                                             double (&lsum)[2]) {
+  switch (code) {
+#define MM_CASE(L) case L: mm_elem_cols_body<L, GRAD, MT, YSIDE>(P, colfeat, fown, t, acc, aP, mown, moth, lsum); break;
+    MM_CASE(GLRMB200_LOSS_QUAD) MM_CASE(GLRMB200_LOSS_L1) MM_CASE(GLRMB200_LOSS_HUBER) MM_CASE(GLRMB200_LOSS_QUANTILE)
+    MM_CASE(GLRMB200_LOSS_PERIODIC) MM_CASE(GLRMB200_LOSS_POISSON) MM_CASE(GLRMB200_LOSS_ORDINAL_HINGE)
+    MM_CASE(GLRMB200_LOSS_LOGISTIC) MM_CASE(GLRMB200_LOSS_WEIGHTED_HINGE)
+#undef MM_CASE
+    default: lsum[0] = lsum[1] = NAN; break;
+  }
+}
+// entries of A in fragment layout for rows arow[mt] (X sweep: the stage's columns; -1 = no row / no feature)
+template <bool STREAM>
+__device__ __forceinline__ void mm_prefetch_a_fx(const DenseArgs& P, const int* __restrict__ colfeat, const int64_t (&arow)[2], int t,
+                                                 double (&aP)[16], unsigned& moth) {
+  moth = 0;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int f = colfeat[8 * nt + 2 * t + e];
+      if (f >= 0) moth |= 1u << (2 * nt + e);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        double v = 0.0;
+        if (f >= 0 && arow[mt] >= 0) {
+          const double* src = P.A + (int64_t)f * P.lda + arow[mt];
+          v = STREAM ? __ldcs(src) : __ldg(src);
+        }
+        aP[mt * 8 + nt * 2 + e] = v;
+      }
+    }
+}
+
 // ---- element-wise phase, per-feature losses (scalar or vector-valued): through the warp's scratch tile ------------------------
 // The entries of A were prefetched into registers a stage ahead (aG); they are parked in the warp's staging area so that
 // the feature loops below can stay rolled (one copy of the loss code per kernel).
@@ -180,35 +266,47 @@ __device__ __forceinline__ double mm_elem_generic_x(const DenseArgs& P, double* 
   __syncwarp();
   const int r = lane & 15, h = lane >> 4;
   double lsum = 0.0;
+  // the (row, feature) pairs of this lane, flattened over the two units: j = 0 .. n0 + n1 - 1.  The operands of pair j + 1
+  // (ids, loss descriptor, entry of A) are fetched while pair j is evaluated.
+  const int nf0 = meta[32], nf1 = meta[33];
+  const int n0 = nf0 > h ? (nf0 - h + 1) >> 1 : 0, n1 = nf1 > h ? (nf1 - h + 1) >> 1 : 0;
+  struct Ev { int off, D, code; const double* lp; double s, p1, p2, a; };
+  auto fetch = [&](int j) {
+    const int uu = j >= n0 ? 1 : 0, q = uu ? j - n0 : j, p = h + 2 * q;
+    const int f = meta[34 + 16 * uu + p];
+    const int o = meta[66 + 17 * uu + p];
+    Ev ev;
+    ev.off = 16 * uu + o;
+    ev.D = meta[66 + 17 * uu + p + 1] - o;
+    ev.code = P.loss_code[f];
+    ev.lp = P.loss_param + (int64_t)f * GLRMB200_LOSS_NPARAM;
+    ev.s = ev.lp[0]; ev.p1 = ev.lp[1]; ev.p2 = ev.lp[2];
+    ev.a = Aw[(8 * uu + q) * 32 + lane];
+    return ev;
+  };
+  Ev nx;
+  if (n0 + n1 > 0) nx = fetch(0);
 #pragma unroll 1
-  for (int uu = 0; uu < 2; ++uu) {
-    const int nf = meta[32 + uu];
-#pragma unroll 1
-    for (int p = h; p < nf; p += 2) {
-      const int f = meta[34 + 16 * uu + p];
-      const int off = meta[66 + 17 * uu + p];
-      const int D = meta[66 + 17 * uu + p + 1] - off;
-      double* up = Sw + r * MM_SW + 16 * uu + off;
-      const int code = P.loss_code[f];
-      const double* lp = P.loss_param + (int64_t)f * GLRMB200_LOSS_NPARAM;
-      const double a = Aw[(8 * uu + (p >> 1)) * 32 + lane];
-      double l;
-      if (code < GLRMB200_LOSS_MULTINOMIAL) {
-        double c;
-        loss_eval<0, GRAD>(code, lp[0], lp[1], lp[2], up[0], a, l, c);
-        if (GRAD) up[0] = rowvalid ? c : 0.0;
-      } else {
-        double u[VEC_DMAX], gc[VEC_DMAX];
+  for (int j = 0; j < n0 + n1; ++j) {
+    const Ev ev = nx;
+    if (j + 1 < n0 + n1) nx = fetch(j + 1);
+    double* up = Sw + r * MM_SW + ev.off;
+    double l;
+    if (ev.code < GLRMB200_LOSS_MULTINOMIAL) {
+      double c;
+      loss_eval<0, GRAD>(ev.code, ev.s, ev.p1, ev.p2, up[0], ev.a, l, c);
+      if (GRAD) up[0] = rowvalid ? c : 0.0;
+    } else {
+      double u[VEC_DMAX], gc[VEC_DMAX];
 #pragma unroll
-        for (int cc = 0; cc < VEC_DMAX; ++cc) { u[cc] = cc < D ? up[cc] : 0.0; gc[cc] = 0.0; }
-        l = vec_loss<GRAD>(code, lp, u, D, rowvalid ? a : 1.0, gc);
-        if (GRAD) {
+      for (int cc = 0; cc < VEC_DMAX; ++cc) { u[cc] = cc < ev.D ? up[cc] : 0.0; gc[cc] = 0.0; }
+      l = vec_loss<GRAD>(ev.code, ev.lp, u, ev.D, rowvalid ? ev.a : 1.0, gc);
+      if (GRAD) {
 #pragma unroll
-          for (int cc = 0; cc < VEC_DMAX; ++cc) if (cc < D) up[cc] = rowvalid ? gc[cc] : 0.0;
-        }
+        for (int cc = 0; cc < VEC_DMAX; ++cc) if (cc < ev.D) up[cc] = rowvalid ? gc[cc] : 0.0;
       }
-      lsum += rowvalid ? l : 0.0;
     }
+    lsum += rowvalid ? l : 0.0;
   }
   __syncwarp();
   if (GRAD) {
@@ -263,28 +361,38 @@ __device__ __forceinline__ void mm_elem_generic_y(const DenseArgs& P, double* __
   for (int q = 0; q < 16; ++q) Aw[q * 32 + lane] = aG[q];
   __syncwarp();
   const int nf = um[0];
+  struct Ev { int off, D, code; const double* lp; double s, p1, p2, a; };
+  auto fetch = [&](int p) {
+    const int f = um[1 + p];
+    Ev ev;
+    ev.off = um[17 + p];
+    ev.D = um[17 + p + 1] - ev.off;
+    ev.code = P.loss_code[f];
+    ev.lp = P.loss_param + (int64_t)f * GLRMB200_LOSS_NPARAM;
+    ev.s = ev.lp[0]; ev.p1 = ev.lp[1]; ev.p2 = ev.lp[2];
+    ev.a = Aw[p * 32 + lane];
+    return ev;
+  };
+  Ev nx;
+  if (nf > 0) nx = fetch(0);
 #pragma unroll 1
   for (int p = 0; p < nf; ++p) {
-    const int f = um[1 + p];
-    const int off = um[17 + p];
-    const int D = um[17 + p + 1] - off;
-    double* up = Sw + off * MM_SW + lane;
-    const int code = P.loss_code[f];
-    const double* lp = P.loss_param + (int64_t)f * GLRMB200_LOSS_NPARAM;
-    const double a = Aw[p * 32 + lane];
+    const Ev ev = nx;
+    if (p + 1 < nf) nx = fetch(p + 1);
+    double* up = Sw + ev.off * MM_SW + lane;
     double l;
-    if (code < GLRMB200_LOSS_MULTINOMIAL) {
+    if (ev.code < GLRMB200_LOSS_MULTINOMIAL) {
       double c;
-      loss_eval<0, GRAD>(code, lp[0], lp[1], lp[2], up[0], a, l, c);
+      loss_eval<0, GRAD>(ev.code, ev.s, ev.p1, ev.p2, up[0], ev.a, l, c);
       if (GRAD) up[0] = rowvalid ? c : 0.0;
     } else {
       double u[VEC_DMAX], gc[VEC_DMAX];
 #pragma unroll
-      for (int cc = 0; cc < VEC_DMAX; ++cc) { u[cc] = cc < D ? up[cc * MM_SW] : 0.0; gc[cc] = 0.0; }
-      l = vec_loss<GRAD>(code, lp, u, D, rowvalid ? a : 1.0, gc);
+      for (int cc = 0; cc < VEC_DMAX; ++cc) { u[cc] = cc < ev.D ? up[cc * MM_SW] : 0.0; gc[cc] = 0.0; }
+      l = vec_loss<GRAD>(ev.code, ev.lp, u, ev.D, rowvalid ? ev.a : 1.0, gc);
       if (GRAD) {
 #pragma unroll
-        for (int cc = 0; cc < VEC_DMAX; ++cc) if (cc < D) up[cc * MM_SW] = rowvalid ? gc[cc] : 0.0;
+        for (int cc = 0; cc < VEC_DMAX; ++cc) if (cc < ev.D) up[cc * MM_SW] = rowvalid ? gc[cc] : 0.0;
       }
     }
     l = rowvalid ? l : 0.0;
@@ -325,6 +433,13 @@ __device__ __forceinline__ void mm_fill_y_stage(const DenseArgs& P, const MmSmem
       if (cc == nf - 1) meta[66 + 17 * (lane >> 4) + nf] = P.feat_off[p0 + cc] + (int)(P.ystart[fl + 1] - P.ystart[fl]);
     }
     if (nf == 0 && cc == 0) meta[66 + 17 * (lane >> 4)] = 0;
+    // one scalar loss type in the whole stage?  (then the element-wise phase stays on the fragments)
+    const int code = f >= 0 ? P.loss_code[f] : -1;
+    const bool scalar1 = f < 0 || (code < GLRMB200_LOSS_MULTINOMIAL && P.ystart[f + 1] - P.ystart[f] == 1);
+    const unsigned havef = __ballot_sync(FULLMASK, f >= 0);
+    const int c0 = __shfl_sync(FULLMASK, code, havef ? __ffs(havef) - 1 : 0);
+    const bool same = __all_sync(FULLMASK, scalar1 && (f < 0 || code == c0));
+    if (lane == 0) meta[101] = (same && havef) ? c0 : 0;
   }
   double* dst = S.stage + ((size_t)slot * MM_SC + lane) * PT;
   if (ycol < 0) {
@@ -420,8 +535,10 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_x_kernel(const DenseA
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t e0 = P.row0 + tile * MM_TM;
     const int nrows = (int)((P.row1 - e0) < MM_TM ? (P.row1 - e0) : MM_TM);
-    double* Gg = P.gscratch + (int64_t)blockIdx.x * MM_TM * P.stride;
+    double* Gg = P.gscratch + (int64_t)blockIdx.x * MM_TM * P.stride;                 // gradient of the tile's rows
+    double* Tg = P.gscratch + (int64_t)(gridDim.x + blockIdx.x) * MM_TM * P.stride;   // last evaluated trial point of each row
     mm_bar_sync(1, MM_THREADS);                        // everybody has left the previous tile
+    if (tid == 0) { S.cnt[9] = 0; S.cnt[10] = 0; }
     if (warp == 0) {
       // the own tile: rows of X (zero rows past the end)
       for (int r = lane + (nrows & ~31); r < MM_TM; r += 32) {
@@ -436,8 +553,11 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_x_kernel(const DenseA
       for (int r = lane; r < nrows; r += 32) mm_bulk_copy(S.own + (size_t)r * PT, P.X + (e0 + r) * P.stride, 64 * NT, xfull);
     }
     pass_prologue();
+    long long pc0 = 0, pc_form = 0, pc_eval = 0, pc_acc = 0;
+    if (P.phase != nullptr && tid == 0) pc0 = clock64();
     mm_wait(xfull, xph, P.diag, 1);
     xph ^= 1u;
+    if (P.phase != nullptr && tid == 0) { const long long c = clock64(); atomicAdd(P.phase + 0, (unsigned long long)(c - pc0)); pc0 = c; }
     // ---- gradient pass (proxgrad.jl:119-135) ----
     {
       const uint32_t base = cons;
@@ -462,7 +582,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_x_kernel(const DenseA
       double rlg = 0.0;
       auto prefetch = [&](const int* meta) {
         if constexpr (GEN) {
-          mm_prefetch_a_gx<true>(P, meta, grow, lane, aG);
+          if (meta[101]) mm_prefetch_a_fx<true>(P, meta, arow, t, aG, moth);    // one scalar loss type: fragment layout
+          else mm_prefetch_a_gx<true>(P, meta, grow, lane, aG);
         } else {
           moth = 0;
 #pragma unroll
@@ -486,7 +607,17 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_x_kernel(const DenseA
         double acc[2][4][2];
         mm_gemm1<NT, 2>(S.own + (size_t)(ow + g) * PT + t, oth + g * PT + t, ks, acc);
         if constexpr (GEN) {
-          rlg += mm_elem_generic_x<true, 2>(P, Sw, Aw, S.smeta + slot * MI, acc, aG, grow >= 0, lane);
+          const int* meta = S.smeta + slot * MI;
+          if (meta[101]) {
+            const int nofeat[2] = {-1, -1};
+            double ls[2];
+            mm_elem_cols<true, 2, false>(meta[101], P, meta, nofeat, t, acc, aG, mown, moth, ls);
+            // stage sums of rows 8 mt + g (quad lanes) -> the lane = row layout of the scratch path
+            const double v0 = __shfl_sync(FULLMASK, ls[0], 4 * (lane & 7)), v1 = __shfl_sync(FULLMASK, ls[1], 4 * (lane & 7));
+            rlg += (lane & 8) ? v1 : v0;
+          } else {
+            rlg += mm_elem_generic_x<true, 2>(P, Sw, Aw, meta, acc, aG, grow >= 0, lane);
+          }
         } else {
           double ls[2];
           mm_elem_uniform<LOSS, true, 2>(up, acc, areg, mown, moth, ls);
@@ -513,6 +644,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_x_kernel(const DenseA
       else if (t == 0) { part[ow + g] = rl[0]; part[ow + 8 + g] = rl[1]; }
     }
     mm_bar_sync(1, MM_THREADS);
+    if (P.phase != nullptr && tid == 0) { const long long c = clock64(); atomicAdd(P.phase + 1, (unsigned long long)(c - pc0)); pc0 = c; }
     // regularizer of the current rows + line-search state: a lane group per row
     for (int step = 0; step < 16 / NGW; ++step) {
       const int r = warp * 16 + step * NGW + gq;
@@ -550,13 +682,20 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_x_kernel(const DenseA
       mm_bar_sync(1, MM_THREADS);
     }
     int ntrials = 0, rounds = 0;
+    if (P.phase != nullptr && tid == 0) { const long long c = clock64(); atomicAdd(P.phase + 2, (unsigned long long)(c - pc0)); pc0 = c; }
     // ---- line search (proxgrad.jl:136-155): all searching rows of the tile try their step together ----
     while (na > 0) {
       if (++rounds > 4096) { dn_give_up(P.diag, 2, na, (int)tile, rounds); break; }
       // trial points x_new = prox(x - (alpha/l) g) of the active slots -> own[slot][.] (the tile's rows of X are not needed
-      // any more: x comes from global memory, where it stays untouched until a trial is accepted); a lane group per slot
+      // any more: x comes from global memory, where it stays untouched until a trial is accepted); a lane group per slot.
+      // A trial point that equals the row's previous (rejected) one bit for bit has the same objective and is rejected
+      // again — the reference evaluates it and finds an exact tie (proxgrad.jl:143) — so such trials are decided here,
+      // without a pass over Y: the step keeps shrinking (:149-153) until the point moves or the step is exhausted.
+      // (k-means rows whose assignment is optimal spend all their ~13 trials this way.)
       {
-        double2 x0n[TR], gn[TR];
+        const bool have_prev = rounds > 1;
+        if (tid == 0) S.cnt[9 + ((rounds + 1) & 1)] = 0;
+        double2 x0n[TR], gn[TR], pvn[TR];
         auto fetch_slot = [&](int base) {
           const int s = base + warp * NGW + gq;
           const int r = s_perm[s < na ? s : 0];
@@ -565,6 +704,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_x_kernel(const DenseA
             const int i0 = 2 * (lg + TG * rr);
             x0n[rr] = *reinterpret_cast<const double2*>(P.X + (e0 + r) * P.stride + i0);          // padding past k is zero
             gn[rr] = *reinterpret_cast<const double2*>(Gg + (int64_t)r * P.stride + i0);
+            pvn[rr] = have_prev ? *reinterpret_cast<const double2*>(Tg + (int64_t)r * P.stride + i0) : make_double2(0.0, 0.0);
           }
         };
         fetch_slot(0);
@@ -575,31 +715,104 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_x_kernel(const DenseA
           const int64_t e = e0 + r;
           const int rcode = P.reg_code[P.reg_uniform ? 0 : e];
           const double* rp = P.reg_param + (P.reg_uniform ? 0 : e) * GLRMB200_REG_NPARAM;
-          const double stepsize = alpha[r] / l1;                            // :137
-          double2 xn[TR];
+          double2 x0[TR], gg[TR], pv[TR];
 #pragma unroll
-          for (int rr = 0; rr < TR; ++rr) {
-            xn[rr].x = fma(-stepsize, gn[rr].x, x0n[rr].x); xn[rr].y = fma(-stepsize, gn[rr].y, x0n[rr].y);   // :140
-          }
+          for (int rr = 0; rr < TR; ++rr) { x0[rr] = x0n[rr]; gg[rr] = gn[rr]; pv[rr] = pvn[rr]; }
           if (base + MM_WARPS * NGW < na) fetch_slot(base + MM_WARPS * NGW);
-          reg_prox<TG, TR>(rcode, rp, xn, lg, k, stepsize);                  // :142
-          const double rv = reg_eval<TG, TR>(rcode, rp, xn, lg, k);
-          if (ok) {
+          auto make = [&](double a_, double2 (&out)[TR]) {
+            const double stepsize = a_ / l1;                                // :137
+#pragma unroll
+            for (int rr = 0; rr < TR; ++rr) {
+              out[rr].x = fma(-stepsize, gg[rr].x, x0[rr].x); out[rr].y = fma(-stepsize, gg[rr].y, x0[rr].y);   // :140
+            }
+            reg_prox<TG, TR>(rcode, rp, out, lg, k, stepsize);               // :142
 #pragma unroll
             for (int rr = 0; rr < TR; ++rr) {
               const int i0 = 2 * (lg + TG * rr);
-              if (i0 < 8 * NT)
-                *reinterpret_cast<double2*>(S.own + (size_t)s * PT + i0) = make_double2(i0 < k ? xn[rr].x : 0.0, i0 + 1 < k ? xn[rr].y : 0.0);
+              if (i0 >= k) out[rr].x = 0.0;
+              if (i0 + 1 >= k) out[rr].y = 0.0;
             }
-            if (lg == 0) regnew[r] = rv;
+          };
+          double a = alpha[r];
+          double2 xn[TR];
+          make(a, xn);
+          int extra = 0;
+          bool stopped = false;
+          {
+            // repeats: the trial point is the row itself (objective == obj_old, computed by the same reduction tree in the
+            // gradient pass) or the row's previous, rejected, trial point
+            const unsigned gmask = (TG == 32 ? 0xffffffffu : ((1u << TG) - 1u)) << (gq * TG);
+            if (rcode == GLRMB200_REG_UNIT_ONE_SPARSE) {
+              // k-means rows (UnitOneSparseConstraint, regularizers.jl:297): the trial point is the one-hot vector at
+              // argmax_i (x_i - s g_i), every component linear in the step s.  If it equals the row itself, the row's index
+              // wins at s and at 0, hence at every step in between: all remaining trials are exact ties.  The step is
+              // shrunk to exhaustion right here (:149-153), one trial counted per shrink.
+              bool eq0 = true;
+#pragma unroll
+              for (int rr = 0; rr < TR; ++rr)
+                eq0 = eq0 && __double_as_longlong(xn[rr].x) == __double_as_longlong(x0[rr].x) &&
+                      __double_as_longlong(xn[rr].y) == __double_as_longlong(x0[rr].y);
+              const unsigned bal0 = __ballot_sync(FULLMASK, eq0);
+              if (ok && (bal0 & gmask) == gmask) {
+                while (!stopped) {
+                  ++extra;
+                  a *= .7;
+                  if (a < P.min_stepsize) { a = P.min_stepsize * 1.1; stopped = true; }
+                  else if (!(a > P.min_stepsize)) stopped = true;            // (the while condition of :136 fails)
+                }
+              }
+            }
+            for (;;) {
+              bool eq0 = true, eqp = have_prev;
+#pragma unroll
+              for (int rr = 0; rr < TR; ++rr) {
+                eq0 = eq0 && __double_as_longlong(xn[rr].x) == __double_as_longlong(x0[rr].x) &&
+                      __double_as_longlong(xn[rr].y) == __double_as_longlong(x0[rr].y);
+                eqp = eqp && __double_as_longlong(xn[rr].x) == __double_as_longlong(pv[rr].x) &&
+                      __double_as_longlong(xn[rr].y) == __double_as_longlong(pv[rr].y);
+              }
+              const unsigned bal0 = __ballot_sync(FULLMASK, eq0), balp = __ballot_sync(FULLMASK, eqp);
+              const bool same = ok && !stopped && ((bal0 & gmask) == gmask || (balp & gmask) == gmask);
+              if (!__any_sync(FULLMASK, same)) break;
+              if (same) {
+                ++extra;
+                a *= .7;                                                     // :149
+                if (a < P.min_stepsize) { a = P.min_stepsize * 1.1; stopped = true; }   // :150-153
+                else if (!(a > P.min_stepsize)) stopped = true;              // (the while condition of :136 fails)
+              }
+              double2 xt[TR];
+              make(a, xt);                                                   // (warp-wide: the prox shuffles)
+              if (same && !stopped) {
+#pragma unroll
+                for (int rr = 0; rr < TR; ++rr) xn[rr] = xt[rr];
+              }
+            }
+          }
+          const double rv = reg_eval<TG, TR>(rcode, rp, xn, lg, k);
+          __syncwarp();                                  // every lane of the group has read alpha[r]
+          if (ok) {
+            if (lg == 0) { alpha[r] = a; ntrials += extra; }
+            if (stopped) {
+              if (lg == 0) s_state[r] = 1;
+            } else {
+#pragma unroll
+              for (int rr = 0; rr < TR; ++rr) {
+                const int i0 = 2 * (lg + TG * rr);
+                if (i0 < 8 * NT) *reinterpret_cast<double2*>(S.own + (size_t)s * PT + i0) = xn[rr];
+                *reinterpret_cast<double2*>(Tg + (int64_t)r * P.stride + i0) = xn[rr];
+              }
+              if (lg == 0) { regnew[r] = rv; S.cnt[9 + (rounds & 1)] = 1; }
+            }
           }
         }
       }
       mm_bar_sync(1, MM_THREADS);
-      pass_prologue();
+      if (P.phase != nullptr && tid == 0) { const long long c = clock64(); pc_form += c - pc0; pc0 = c; }
+      const bool any_eval = S.cnt[9 + (rounds & 1)] != 0;                  // (false: every trial of this round was a repeat)
+      if (any_eval) pass_prologue();
       // losses of the trial points: (16 slots, stage) items.  Y resident: the items are dealt round-robin over the warps and
       // every item leaves its 16 stage sums in psum[stage]; streamed: warp w serves slots 16 w .. 16 w + 15 through all stages.
-      {
+      if (any_eval) {
         const int nmp = (na + 15) >> 4;
         auto item = [&](int mp, const double* oth, const int* meta, double (&ls)[2], double& lsg) {
           const double* ownp = S.own + (size_t)(16 * mp + g) * PT + t;
@@ -608,9 +821,27 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_x_kernel(const DenseA
             const int sg = 16 * mp + (lane & 15);
             const int64_t grow = sg < na ? e0 + s_perm[sg] : -1;
             double aG[16];
-            mm_prefetch_a_gx<false>(P, meta, grow, lane, aG);
-            mm_gemm1<NT, 2>(ownp, oth + g * PT + t, ks, acc);
-            lsg = mm_elem_generic_x<false, 2>(P, Sw, Aw, meta, acc, aG, grow >= 0, lane);
+            if (meta[101]) {
+              int64_t arow[2];
+              unsigned mown = 0, moth = 0;
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt) {
+                const int s = 16 * mp + 8 * mt + g;
+                arow[mt] = s < na ? e0 + s_perm[s] : -1;
+                if (s < na) mown |= 1u << mt;
+              }
+              mm_prefetch_a_fx<false>(P, meta, arow, t, aG, moth);
+              mm_gemm1<NT, 2>(ownp, oth + g * PT + t, ks, acc);
+              const int nofeat[2] = {-1, -1};
+              double l2[2];
+              mm_elem_cols<false, 2, false>(meta[101], P, meta, nofeat, t, acc, aG, mown, moth, l2);
+              const double v0 = __shfl_sync(FULLMASK, l2[0], 4 * (lane & 7)), v1 = __shfl_sync(FULLMASK, l2[1], 4 * (lane & 7));
+              lsg = (lane & 8) ? v1 : v0;
+            } else {
+              mm_prefetch_a_gx<false>(P, meta, grow, lane, aG);
+              mm_gemm1<NT, 2>(ownp, oth + g * PT + t, ks, acc);
+              lsg = mm_elem_generic_x<false, 2>(P, Sw, Aw, meta, acc, aG, grow >= 0, lane);
+            }
           } else {
             int64_t arow[2];
             unsigned mown = 0;
@@ -671,7 +902,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_x_kernel(const DenseA
         }
       }
       mm_bar_sync(1, MM_THREADS);
-      if (tid < na) {
+      if (P.phase != nullptr && tid == 0) { const long long c = clock64(); pc_eval += c - pc0; pc0 = c; }
+      if (tid < na && s_state[s_perm[tid]] == 0) {
         const int myrow = s_perm[tid];
         double tot = S.psum[tid];
         if (resident) for (int st = 1; st < nst; ++st) tot += S.psum[st * MM_TM + tid];
@@ -684,6 +916,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_x_kernel(const DenseA
         } else {
           alpha[myrow] *= .7;                                                // :149
           if (alpha[myrow] < P.min_stepsize) { alpha[myrow] = P.min_stepsize * 1.1; s_state[myrow] = 1; }   // :150-153
+          else if (!(alpha[myrow] > P.min_stepsize)) s_state[myrow] = 1;     // (the while condition of :136 fails)
         }
       }
       mm_bar_sync(1, MM_THREADS);
@@ -709,6 +942,11 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_x_kernel(const DenseA
         for (int w = 0; w < MM_WARPS; ++w) na += S.cnt[w];
         mm_bar_sync(1, MM_THREADS);
       }
+      if (P.phase != nullptr && tid == 0) { const long long c = clock64(); pc_acc += c - pc0; pc0 = c; }
+    }
+    if (P.phase != nullptr && tid == 0) {
+      atomicAdd(P.phase + 3, (unsigned long long)pc_form); atomicAdd(P.phase + 4, (unsigned long long)pc_eval);
+      atomicAdd(P.phase + 5, (unsigned long long)pc_acc); atomicAdd(P.phase + 6, (unsigned long long)rounds); atomicAdd(P.phase + 7, 1ull);
     }
     if (tid < nrows) {
       if (!(P.flags & FLAG_EVAL_ONLY)) P.alpha[e0 + tid] = alpha[tid];
@@ -816,13 +1054,38 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_y_kernel(const DenseA
   double areg[2][4][2];
   double aG[16];
   unsigned moth = 0;
+  // heterogeneous problem: a unit made of one scalar loss type keeps its element-wise phase on the fragments
+  int ocode = 0;
+  if (GEN && active) {
+    const int nf = um[0];
+    const int code = lane < nf ? P.loss_code[um[1 + lane]] : -1;
+    const int c0 = __shfl_sync(FULLMASK, code, 0);
+    const bool same = __all_sync(FULLMASK, lane >= nf || code == c0);
+    ocode = (same && nf > 0 && um[17 + nf] == nf && c0 < GLRMB200_LOSS_MULTINOMIAL) ? c0 : 0;
+  }
   auto prefetch = [&](int s) {
     const int64_t r0 = rb0 + (int64_t)s * MM_SC;
     if constexpr (GEN) {
-      const int nf = um[0];
-      const int64_t row = r0 + lane;
+      if (ocode) {
+        moth = 0;
 #pragma unroll
-      for (int p = 0; p < 16; ++p) aG[p] = (p < nf && row < rb1) ? __ldcs(P.A + (int64_t)um[1 + p] * P.lda + row) : 0.0;
+        for (int nt = 0; nt < 4; ++nt) {
+          const int64_t row = r0 + 8 * nt + 2 * t;
+          if (row < rb1) moth |= 1u << (2 * nt);
+          if (row + 1 < rb1) moth |= 1u << (2 * nt + 1);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            double2 v = make_double2(0.0, 0.0);
+            if (fown[mt] >= 0 && row < rb1) v = __ldcs(reinterpret_cast<const double2*>(P.A + (int64_t)fown[mt] * P.lda + row));
+            aG[mt * 8 + nt * 2] = v.x; aG[mt * 8 + nt * 2 + 1] = v.y;
+          }
+        }
+      } else {
+        const int nf = um[0];
+        const int64_t row = r0 + lane;
+#pragma unroll
+        for (int p = 0; p < 16; ++p) aG[p] = (p < nf && row < rb1) ? __ldcs(P.A + (int64_t)um[1 + p] * P.lda + row) : 0.0;
+      }
     } else {
       moth = 0;
 #pragma unroll
@@ -853,7 +1116,13 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_y_kernel(const DenseA
       double acc[2][4][2];
       mm_gemm1<NT, 2>(S.own + (size_t)(ow + g) * PT + t, oth + g * PT + t, ks, acc);
       if constexpr (GEN) {
-        mm_elem_generic_y<MODE == 0>(P, Sw, Aw, um, acc, aG, rb0 + (int64_t)s * MM_SC + lane < rb1, lane, featloss);
+        if (ocode) {
+          double ls[2];
+          mm_elem_cols<MODE == 0, 2, true>(ocode, P, nullptr, fown, t, acc, aG, mown, moth, ls);
+          cl[0] += ls[0]; cl[1] += ls[1];
+        } else {
+          mm_elem_generic_y<MODE == 0>(P, Sw, Aw, um, acc, aG, rb0 + (int64_t)s * MM_SC + lane < rb1, lane, featloss);
+        }
       } else {
         double ls[2];
         mm_elem_uniform<LOSS, MODE == 0, 2>(up, acc, areg, mown, moth, ls);
@@ -867,7 +1136,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_y_kernel(const DenseA
   }
   if (!active) return;
   // partial loss sums of the block's rows per feature, partial G_Y
-  if (GEN) {
+  if (GEN && !ocode) {
     if (lane < um[0]) P.objpart[(int64_t)b * P.n + um[1 + lane]] = featloss;
   } else if (t == 0) {
 #pragma unroll

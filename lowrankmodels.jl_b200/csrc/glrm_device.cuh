@@ -183,9 +183,10 @@ __device__ __forceinline__ void loss_eval(int code, double s, double p1, double 
 // regularizer sees (k, or k-1 under the offset wrappers lastentry1 / lastentry_unpenalized :163-189).
 struct ArgMax { double v; int i; };
 __device__ __forceinline__ bool am_better(double av, int ai, double bv, int bi) {   // Julia argmax: first max, NaN wins
-  const bool an = av != av, bn = bv != bv;
-  if (an || bn) return an && (!bn || ai < bi);
-  return av > bv || (av == bv && ai < bi);
+  // branch-free (predicate logic only): this sits on the critical path of every one-hot / k-sparse / simplex prox
+  const bool an = av != av, bn = bv != bv, lower = ai < bi;
+  const bool ordered = (av > bv) | ((av == bv) & lower);
+  return an ? (!bn | lower) : (!bn & ordered);
 }
 template <int G>
 __device__ __forceinline__ ArgMax group_argmax(ArgMax m) {

@@ -140,6 +140,7 @@ struct DenseHost {
   int nt = 0, nst = 0;
   int unit_cols = DN_TN;
   int32_t *d_ucol_feat = nullptr, *d_ucol_y = nullptr, *d_ucol_feat2 = nullptr, *d_ucol_y2 = nullptr;
+  unsigned long long* d_phase = nullptr;    // GLRMB200_PHASE_TIMERS=1: phase clocks of the X sweep (printed when the handle goes)
   volatile int32_t* h_nactive = nullptr;    // mapped pinned [2]: (features still searching, sweep sequence number)
   int32_t seq = 0;
 };
@@ -473,6 +474,15 @@ static SweepArgs make_args(const glrmb200_engine* E, bool x_side, int flags, dou
 // fully observed path (csrc/glrm_dense.cuh)
 static void dense_free(glrmb200_engine* E) {
   DenseHost& D = E->dn;
+  if (D.d_phase) {
+    unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyAsync(ph, D.d_phase, sizeof(ph), cudaMemcpyDeviceToHost, E->stream) == cudaSuccess && cudaStreamSynchronize(E->stream) == cudaSuccess && ph[7])
+      fprintf(stderr, "[glrmb200] X sweep phases, clocks per tile (thread 0): wait %.0f, gradient pass %.0f, search set-up %.0f, trial points %.0f, "
+                      "trial losses %.0f, accept/compact %.0f; rounds per tile %.2f; tiles %llu\n",
+              (double)ph[0] / ph[7], (double)ph[1] / ph[7], (double)ph[2] / ph[7], (double)ph[3] / ph[7], (double)ph[4] / ph[7], (double)ph[5] / ph[7],
+              (double)ph[6] / ph[7], ph[7]);
+    dfree(D.d_phase, E->stream);
+  }
   dfree(D.d_A, E->stream);
   dfree(D.d_chunk_ptr, E->stream); dfree(D.d_feat_list, E->stream); dfree(D.d_feat_off, E->stream); dfree(D.d_nchunks, E->stream);
   dfree(D.d_chunk_ptr2, E->stream); dfree(D.d_feat_list2, E->stream); dfree(D.d_feat_off2, E->stream); dfree(D.d_nchunks2, E->stream);
@@ -502,10 +512,12 @@ static bool dense_eligible(const glrmb200_engine* E, const glrmb200_problem* P) 
 // row blocks of the Y sweep: DN_GROUPS groups of up to 37 blocks (two CTA waves of 148), fixed by m alone so that neither
 // the reduction order nor the multi-GPU row shards depend on the launch
 static void dense_blocks(int64_t m, int* bg, int64_t* rows_per_block) {
+  // t 64-row tiles per block so that 8 x 37 blocks cover m; then just as many blocks per group as those tiles need (a
+  // mid-size m would otherwise leave the last groups — and, sharded, the last GPUs — without rows)
   const int64_t tiles = (m + DN_TM - 1) / DN_TM;
-  *bg = (int)std::min<int64_t>(37, std::max<int64_t>(1, (tiles + DN_GROUPS - 1) / DN_GROUPS));
-  const int64_t nb = (int64_t)DN_GROUPS * *bg;
-  *rows_per_block = ((m + nb - 1) / nb + DN_TM - 1) / DN_TM * DN_TM;
+  const int64_t t = std::max<int64_t>(1, (tiles + DN_GROUPS * 37 - 1) / (DN_GROUPS * 37));
+  *bg = (int)std::max<int64_t>(1, (tiles + DN_GROUPS * t - 1) / (DN_GROUPS * t));
+  *rows_per_block = t * DN_TM;
 }
 
 static int dense_setup(glrmb200_engine* E, const glrmb200_problem* P) {
@@ -608,8 +620,9 @@ static int dense_setup(glrmb200_engine* E, const glrmb200_problem* P) {
   const int tile_rows = D.mma ? MM_TM : DN_TM;
   const int64_t tiles = std::max<int64_t>(1, (mloc + tile_rows - 1) / tile_rows);
   D.x_grid = (int)std::min<int64_t>(tiles, D.mma ? (int64_t)sms : (int64_t)sms * D.ctas_per_sm);
-  if ((rc = dalloc(&D.d_gscratch, (size_t)D.x_grid * tile_rows * E->stride, E->stream))) return rc;
-  CUDA_OK(cudaMemsetAsync(D.d_gscratch, 0, (size_t)D.x_grid * tile_rows * E->stride * sizeof(double), E->stream));   // lanes past the register tiles stay zero
+  const size_t gs_doubles = (size_t)D.x_grid * tile_rows * E->stride * (D.mma ? 2 : 1);   // (tensor-core kernels: + the rows' last trial points)
+  if ((rc = dalloc(&D.d_gscratch, gs_doubles, E->stream))) return rc;
+  CUDA_OK(cudaMemsetAsync(D.d_gscratch, 0, gs_doubles * sizeof(double), E->stream));   // lanes past the register tiles stay zero
   if ((rc = dalloc(&D.d_gpart, (size_t)D.n_blocks * (size_t)d * E->stride, E->stream))) return rc;
   CUDA_OK(cudaMemsetAsync(D.d_gpart, 0, (size_t)D.n_blocks * (size_t)d * E->stride * sizeof(double), E->stream));   // (the same)
   if ((rc = dalloc(&D.d_objpart, (size_t)D.n_blocks * (size_t)n, E->stream))) return rc;
@@ -623,6 +636,10 @@ static int dense_setup(glrmb200_engine* E, const glrmb200_problem* P) {
   CUDA_OK(cudaMemsetAsync(D.d_gsum_G, 0, (size_t)DN_GROUPS * (size_t)d * E->stride * sizeof(double), E->stream));
   CUDA_OK(cudaMemsetAsync(D.d_gsum_o, 0, (size_t)DN_GROUPS * (size_t)n * sizeof(double), E->stream));
   CUDA_OK(cudaMemsetAsync(D.d_gsum_x, 0, DN_GROUPS * sizeof(double), E->stream));
+  if (D.mma && getenv("GLRMB200_PHASE_TIMERS") && atoi(getenv("GLRMB200_PHASE_TIMERS"))) {
+    if ((rc = dalloc(&D.d_phase, 8, E->stream))) return rc;
+    CUDA_OK(cudaMemsetAsync(D.d_phase, 0, 8 * sizeof(unsigned long long), E->stream));
+  }
   if ((rc = dalloc(&D.d_colobj, (size_t)n, E->stream))) return rc;
   if ((rc = dalloc(&D.d_objold, (size_t)n, E->stream))) return rc;
   if ((rc = dalloc(&D.d_regnew, (size_t)n, E->stream))) return rc;
@@ -658,6 +675,7 @@ static DenseArgs dense_args(const glrmb200_engine* E, bool static_plan, const do
   P.ucol_feat = static_plan ? D.d_ucol_feat : D.d_ucol_feat2;
   P.ucol_y = static_plan ? D.d_ucol_y : D.d_ucol_y2;
   P.nst = D.nst;
+  P.phase = D.d_phase;
   P.uparam[0] = E->uparam[0]; P.uparam[1] = E->uparam[1]; P.uparam[2] = E->uparam[2];
   return P;
 }

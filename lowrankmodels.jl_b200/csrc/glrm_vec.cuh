@@ -25,6 +25,28 @@ __device__ __forceinline__ void bin_eval(int bcode, double bs, double bp1, doubl
   loss_eval<0, true>(bcode, bs, bp1, bp2, u, label ? 1.0 : 0.0, l, c);
 }
 
+// MultinomialLoss with DD levels (losses.jl:369-398); one exponential per level serves the value and the gradient
+// (u_j - u_a - M and u_j - max(u) are the same number up to rounding)
+template <int DD, bool WANT_GRAD>
+__device__ __forceinline__ double multinomial_fixed(double s, int a, const double (&u)[VEC_DMAX], double (&gc)[VEC_DMAX]) {
+  double mx = u[0], ua = 0.0;
+#pragma unroll
+  for (int j = 0; j < DD; ++j) { mx = jl_maxd(mx, u[j]); ua = (j == a - 1) ? u[j] : ua; }
+  const double M = mx - ua;
+  double e[DD];
+#pragma unroll
+  for (int j = 0; j < DD; ++j) e[j] = exp(u[j] - ua - M);
+  double sumexp = 0.0;
+#pragma unroll
+  for (int j = 0; j < DD; ++j) sumexp += e[j];
+  if (WANT_GRAD) {
+    const double inv = 1.0 / sumexp;
+#pragma unroll
+    for (int j = 0; j < DD; ++j) gc[j] = s * (e[j] * inv - (j == a - 1 ? 1.0 : 0.0));
+  }
+  return s * (log(sumexp) + M);
+}
+
 template <bool WANT_GRAD>
 __device__ __forceinline__ double vec_loss(int code, const double* __restrict__ lp, double (&u)[VEC_DMAX], int D,
                                            double alab, double (&gc)[VEC_DMAX]) {
@@ -33,18 +55,13 @@ __device__ __forceinline__ double vec_loss(int code, const double* __restrict__ 
   double loss = 0.0;
   switch (code) {
     case GLRMB200_LOSS_MULTINOMIAL: {  // losses.jl:369-398.  evaluate: log-sum-exp shifted by max(u); the reference's
-      // O(D^2) gradient loop equals softmax(u) - e_a term by term (exp(-M_j)/sumexp_j == exp(u_j-max)/sum exp(u-max))
-      double mx = u[0], ua = 0.0;
-#pragma unroll
-      for (int j = 0; j < VEC_DMAX; ++j) if (j < D) { mx = jl_maxd(mx, u[j]); if (j == a - 1) ua = u[j]; }
-      const double M = mx - ua;
-      double sumexp = 0.0, sumsm = 0.0;
-#pragma unroll
-      for (int j = 0; j < VEC_DMAX; ++j) if (j < D) { sumexp += exp(u[j] - ua - M); const double e = exp(u[j] - mx); gc[j] = e; sumsm += e; }
-      loss = s * (log(sumexp) + M);
-      if (WANT_GRAD) {
-#pragma unroll
-        for (int j = 0; j < VEC_DMAX; ++j) if (j < D) gc[j] = s * (gc[j] / sumsm - (j == a - 1 ? 1.0 : 0.0));
+      // O(D^2) gradient loop equals softmax(u) - e_a term by term (exp(-M_j)/sumexp_j == exp(u_j-max)/sum exp(u-max)).
+      // The level count is fixed at compile time per case: straight-line code, so the D exponentials overlap.
+      switch (D) {
+#define GLRM_MNL(DD) case DD: loss = multinomial_fixed<DD, WANT_GRAD>(s, a, u, gc); break;
+        GLRM_MNL(1) GLRM_MNL(2) GLRM_MNL(3) GLRM_MNL(4) GLRM_MNL(5) GLRM_MNL(6) GLRM_MNL(7) GLRM_MNL(8)
+#undef GLRM_MNL
+        default: loss = NAN; break;
       }
     } break;
     case GLRMB200_LOSS_OVA:            // :424-438   (scale applied on top of the bin loss's own scale, as in the reference)

@@ -52,7 +52,8 @@ def main():
             ok = ok and bool(fused_same)
         if rank == 0:
             X1, Y1 = g.X.copy(order="F"), g.Y.copy(order="F")
-            with lrm.Engine(ep, device=local) as e1:
+            # (C1 is too small to shard by row groups: the N-GPU fit goes through the gather kernels, and so does its twin)
+            with lrm.Engine(ep, device=local, gather_only=(name == "C1")) as e1:
                 obj1, _ = e1.fit(p, X1, Y1)
                 ar1, ac1 = e1.stepsizes()
             same = (obj == obj1).all() and (X == X1).all() and (Y == Y1).all() and (ar == ar1).all() and (ac == ac1).all()

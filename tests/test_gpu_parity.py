@@ -610,13 +610,13 @@ def test_payload_regularizers_objective_and_reg_scale(orc):
     A, obs, X0 = small_sparse(m=40, n=25, k=k, seed=10)
     Y0 = synth.normal_matrix(74, 1, k, 25)
     rx = [lrm.RemQuadReg(0.3, X0[:, i] + 0.1) if i % 2 else lrm.QuadReg(0.2) for i in range(40)]
-    ry = [lrm.fixed_latent_features(lrm.OneReg(0.1), Y0[:2, j].copy()) if j % 3 else lrm.NonNegOneReg(0.1) for j in range(25)]
-    g = lrm.GLRM(A, lrm.QuadLoss(), rx, ry, k, obs=obs, X=X0.copy(), Y=np.abs(Y0))
+    ry = [lrm.fixed_latent_features(lrm.OneReg(0.1), np.abs(Y0[:2, j])) if j % 3 else lrm.NonNegOneReg(0.1) for j in range(25)]
+    g = lrm.GLRM(A, lrm.QuadLoss(), rx, ry, k, obs=obs, X=X0.copy(), Y=np.abs(Y0))   # (Y starts on the pinned values: finite penalty)
     ep = lrm.encode_problem(g)
     with lrm.Engine(g) as eng:
         want = orc.objective(ep, g.X, g.Y, include_reg=True)
         got = eng.objective(g.X, g.Y, include_regularization=True)
-        assert abs(got - want) <= 1e-12 * abs(want)
+        assert np.isfinite(want) and abs(got - want) <= 1e-12 * abs(want)
         eng.set_reg_scale(0.7)
         lrm.scale_regularizer(g, 0.7)
         ep2 = lrm.encode_problem(g)
