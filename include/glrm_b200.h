@@ -261,7 +261,15 @@ int glrmb200_ipc_open(glrmb200_handle h, const uint8_t* all_blobs /* nranks * GL
 int glrmb200_comm_barrier(glrmb200_handle h);
 
 /* Row range [row_begin,row_end) and column range [col_begin,col_end) this handle updates
- * (nnz-balanced contiguous shards; whole range when nranks==1). */
+ * (cost-balanced contiguous shards; whole range when nranks==1).
+ *
+ * Fully observed problems on several GPUs (nranks in {2, 4, 8}, m >= 512 * nranks; SURVEY.md section 8e, second mode):
+ * only the ROWS of A and X are sharded — by whole groups of row blocks, [row_begin, row_end) — and every rank updates
+ * all of Y (the partial gradients / per-feature objectives of the 8 row-block groups are all-gathered per line-search
+ * round and summed in group order, so every rank holds identical Y, step sizes and objective, bit-identical to the
+ * one-GPU fit).  Such a handle reads and returns ONLY ITS OWN ROWS of X (glrmb200_fit, glrmb200_upload_factors,
+ * glrmb200_download_factors leave the caller's other columns of X[k x m] untouched); Y is complete on every rank.
+ * [col_begin, col_end) is [0, n) on rank 0 and empty elsewhere (bookkeeping only). */
 int glrmb200_shard(glrmb200_handle h, int64_t* row_begin, int64_t* row_end,
                    int64_t* col_begin, int64_t* col_end);
 

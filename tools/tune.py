@@ -16,8 +16,9 @@ variants = sys.argv[3:] or ["", "GLRMB200_HEAVY=512", "GLRMB200_HEAVY=512 GLRMB2
 g, cfg = build_problem(config, scale)
 ep = lrm.encode_problem(g, validate=False)
 nnz = ep.nnz
-pw = lrm.ProxGradParams(max_iter=3, abs_tol=0, rel_tol=0)
-pk = lrm.ProxGradParams(max_iter=10, abs_tol=0, rel_tol=0)
+STEPS, WARM = int(os.environ.get("TUNE_STEPS", "10")), int(os.environ.get("TUNE_WARM", "3"))
+pw = lrm.ProxGradParams(max_iter=WARM, abs_tol=0, rel_tol=0)
+pk = lrm.ProxGradParams(max_iter=STEPS, abs_tol=0, rel_tol=0)
 ref = None
 for v in variants:
     keys = []
@@ -46,7 +47,7 @@ for v in variants:
     if ref is None:
         ref = obj
     dev = float(np.max(np.abs(obj - ref) / np.abs(ref)))
-    print(json.dumps({"variant": v or "default", "ms_per_step": p["loop_ms"] / 10, "x_ms": p["update_x_ms"] / 10,
-                      "y_ms": p["update_y_ms"] / 10, "Gentries_s": nnz / (p["loop_ms"] / 10 * 1e-3) / 1e9,
+    print(json.dumps({"variant": v or "default", "ms_per_step": p["loop_ms"] / STEPS, "x_ms": p["update_x_ms"] / STEPS,
+                      "y_ms": p["update_y_ms"] / STEPS, "Gentries_s": nnz / (p["loop_ms"] / STEPS * 1e-3) / 1e9,
                       "x_trials": p["x_trials"], "y_trials": p["y_trials"], "obj_last": float(obj[-1]),
                       "max_rel_dev_vs_first": dev}), flush=True)
