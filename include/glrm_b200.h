@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GLRMB200_VERSION 101          /* major*100 + minor */
+#define GLRMB200_VERSION 102          /* major*100 + minor */
 #define GLRMB200_LOSS_NPARAM 8        /* doubles per loss descriptor */
 #define GLRMB200_REG_NPARAM 4         /* doubles per regularizer descriptor */
 
@@ -325,6 +325,23 @@ int glrmb200_fit_resident(glrmb200_handle h, const glrmb200_params* params,
                           double* ch_objective, double* ch_seconds, int32_t cap,
                           int32_t* n_recorded, glrmb200_profile* profile);
 int glrmb200_download_factors(glrmb200_handle h, double* X, double* Y);
+
+/* Evaluation of a fitted model on the device (callers of the path: cross-validation scores a fold with them,
+ * src/cross_validate.jl:34-44).  Domains (src/domains.jl) say how a feature is imputed and scored; domain_code[n] holds
+ * GLRMB200_DOMAIN_* and domain_param[2n] the pairs (min, max) for ORDINAL / CATEGORICAL, (T, -) for PERIODIC,
+ * (max_count, -) for COUNT.  The host side passes each loss's own domain (l.domain) unless the caller overrides it.
+ *   glrmb200_impute        impute(glrm) = impute(losses, X'Y) (src/evaluate_fit.jl:150, src/impute_and_err.jl:147-168):
+ *                          A_imputed[m*n] column-major, a_u = argmin_a loss(u, a) over the domain (impute_and_err.jl:40-120);
+ *                          NaN where the reference has no method for the (domain, loss) pair or raises
+ *   glrmb200_error_metric  error_metric(glrm, X, Y, domains; standardize) (src/evaluate_fit.jl:106-143) over the observed
+ *                          entries: squared error or misclassification of the imputed value, per the domain
+ * One rank only (GLRMB200_E_UNSUPPORTED on a sharded handle). */
+enum { GLRMB200_DOMAIN_REAL = 1, GLRMB200_DOMAIN_BOOL = 2, GLRMB200_DOMAIN_ORDINAL = 3, GLRMB200_DOMAIN_CATEGORICAL = 4,
+       GLRMB200_DOMAIN_PERIODIC = 5, GLRMB200_DOMAIN_COUNT = 6 };
+int glrmb200_impute(glrmb200_handle h, const double* X, const double* Y, const int32_t* domain_code,
+                    const double* domain_param, double* A_imputed);
+int glrmb200_error_metric(glrmb200_handle h, const double* X, const double* Y, const int32_t* domain_code,
+                          const double* domain_param, int32_t standardize, double* out);
 
 /* Step-size state (alpharow / alphacol, proxgrad.jl:69-70) for tests: n_row = m, n_col = n. */
 int glrmb200_get_stepsizes(glrmb200_handle h, double* alpharow, double* alphacol);

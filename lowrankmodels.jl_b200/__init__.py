@@ -19,6 +19,8 @@ from .regularizers import (KSparseConstraint, MNLOrdinalReg, NonNegConstraint, N
                            FixedLastLatentFeaturesConstraint, lastentry1,
                            lastentry_unpenalized)
 from .encode import encode_params, encode_problem, encode_sparse_params
+from .domains import (BoolDomain, CategoricalDomain, CountDomain, Domain, OrdinalDomain, PeriodicDomain, RealDomain,
+                      error_metric, impute, impute_missing, loss_domain)
 from . import _abi, distributed, synth
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -80,6 +80,8 @@ SYMBOLS = [
     ("glrmb200_fit_resident", C.c_int, [Handle, C.POINTER(Params), c_double_p, c_double_p, C.c_int32,
                                          c_int32_p, C.POINTER(Profile)]),
     ("glrmb200_download_factors", C.c_int, [Handle, c_double_p, c_double_p]),
+    ("glrmb200_impute", C.c_int, [Handle, c_double_p, c_double_p, c_int32_p, c_double_p, c_double_p]),
+    ("glrmb200_error_metric", C.c_int, [Handle, c_double_p, c_double_p, c_int32_p, c_double_p, C.c_int32, c_double_p]),
     ("glrmb200_get_stepsizes", C.c_int, [Handle, c_double_p, c_double_p]),
     ("glrmb200_destroy", C.c_int, [Handle]),
     ("glrmb200_plan_shards", C.c_int, [c_int64_p, C.c_int64, C.c_int32, c_int64_p]),

@@ -23,6 +23,7 @@
 #include "glrm_small.cuh"
 #include "glrm_vec.cuh"
 #include "glrm_dense_host.h"
+#include "glrm_eval.cuh"
 
 using namespace glrm;
 
@@ -1843,6 +1844,72 @@ extern "C" int glrmb200_set_reg_scale(glrmb200_handle E, double newscale) {
   }
   CUDA_OK(cudaStreamSynchronize(E->stream));
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// evaluation of a fitted model (csrc/glrm_eval.cuh): impute / error_metric
+static int eval_args(glrmb200_engine* E, const double* X, const double* Y, const int32_t* dom_code, const double* dom_param,
+                     EvalArgs* P, int32_t** d_dc, double** d_dp) {
+  if (!E || !X || !Y || !dom_code || !dom_param) return fail(GLRMB200_E_INVALID, "null argument");
+  if (E->nranks != 1) return fail(GLRMB200_E_UNSUPPORTED, "impute / error_metric run on one rank");
+  int rc = glrmb200_upload_factors(E, X, Y);
+  if (rc) return rc;
+  for (int64_t f = 0; f < E->n; ++f)
+    if (dom_code[f] < GLRMB200_DOMAIN_REAL || dom_code[f] > GLRMB200_DOMAIN_COUNT) return fail(GLRMB200_E_INVALID, "domain code %d (column %lld) is unknown", dom_code[f], (long long)f);
+  if ((rc = upload(d_dc, dom_code, (size_t)E->n, E->stream))) return rc;
+  if ((rc = upload(d_dp, dom_param, (size_t)(2 * E->n), E->stream))) return rc;
+  memset(P, 0, sizeof(*P));
+  P->X = E->d_X; P->Y = E->d_Y; P->stride = E->stride; P->k = (int32_t)E->k; P->m = E->m; P->n = E->n;
+  P->ystart = E->d_ystart;                                   // nullptr: every feature has one column
+  P->loss_code = E->d_loss_code; P->loss_param = E->d_loss_param;
+  P->dom_code = *d_dc; P->dom_param = *d_dp;
+  if (E->dn.on) { P->dense_A = E->dn.d_A; P->lda = E->dn.lda; }
+  else if (E->obs_full) { P->dense_A = E->cols.d_val; P->lda = E->m; }
+  else { P->col_ptr = E->cols.d_ptr; P->col_idx = E->cols.d_idx; P->col_val = E->cols.d_val; }
+  return 0;
+}
+
+extern "C" int glrmb200_impute(glrmb200_handle E, const double* X, const double* Y, const int32_t* dom_code,
+                               const double* dom_param, double* A_imputed) {
+  if (!A_imputed) return fail(GLRMB200_E_INVALID, "null argument");
+  EvalArgs P;
+  int32_t* d_dc = nullptr;
+  double *d_dp = nullptr, *d_out = nullptr;
+  int rc = eval_args(E, X, Y, dom_code, dom_param, &P, &d_dc, &d_dp);
+  if (!rc) rc = dalloc(&d_out, (size_t)(E->m * E->n), E->stream);
+  if (!rc) {
+    P.out_imputed = d_out;
+    const dim3 grid((unsigned)E->n, (unsigned)std::min<int64_t>(64, (E->m + 255) / 256), 1);
+    eval_kernel<0><<<grid, 256, (size_t)VEC_DMAX * E->k * sizeof(double), E->stream>>>(P);
+    cudaError_t ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(A_imputed, d_out, (size_t)(E->m * E->n) * sizeof(double), cudaMemcpyDeviceToHost, E->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(E->stream);
+    if (ce != cudaSuccess) rc = fail(GLRMB200_E_CUDA, "impute: %s", cudaGetErrorString(ce));
+  }
+  if (E) { dfree(d_dc, E->stream); dfree(d_dp, E->stream); dfree(d_out, E->stream); }
+  return rc;
+}
+
+extern "C" int glrmb200_error_metric(glrmb200_handle E, const double* X, const double* Y, const int32_t* dom_code,
+                                     const double* dom_param, int32_t standardize, double* out) {
+  if (!out) return fail(GLRMB200_E_INVALID, "null argument");
+  EvalArgs P;
+  int32_t* d_dc = nullptr;
+  double *d_dp = nullptr, *d_col = nullptr;
+  int rc = eval_args(E, X, Y, dom_code, dom_param, &P, &d_dc, &d_dp);
+  if (!rc) rc = dalloc(&d_col, (size_t)(3 * E->n), E->stream);
+  if (!rc) {
+    P.col_err = d_col; P.col_sq = d_col + E->n; P.col_cnt = d_col + 2 * E->n;
+    eval_kernel<1><<<(unsigned)E->n, 256, (size_t)VEC_DMAX * E->k * sizeof(double), E->stream>>>(P);
+    eval_total_kernel<<<1, 32, 0, E->stream>>>(P.col_err, P.col_sq, P.col_cnt, E->n, standardize, E->d_scalars);
+    cudaError_t ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(E->h_pinned, E->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, E->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(E->stream);
+    if (ce != cudaSuccess) rc = fail(GLRMB200_E_CUDA, "error_metric: %s", cudaGetErrorString(ce));
+    else *out = E->h_pinned[0];
+  }
+  if (E) { dfree(d_dc, E->stream); dfree(d_dp, E->stream); dfree(d_col, E->stream); }
+  return rc;
 }
 
 extern "C" int glrmb200_get_stepsizes(glrmb200_handle E, double* alpharow, double* alphacol) {

@@ -27,7 +27,7 @@ import LowRankModels: fit!, AbstractParams, GLRM, ConvergenceHistory, update_ch!
                       lastentry1, lastentry_unpenalized, OrdinalReg, MNLOrdinalReg,
                       fixed_latent_features, fixed_last_latent_features, RemQuadReg
 
-export B200ProxGradParams, B200SparseProxGradParams, B200Handle, set_obs!, set_reg_scale!, objective_resident
+export B200ProxGradParams, B200SparseProxGradParams, B200Handle, set_obs!, set_reg_scale!, objective_resident, error_metric_resident, impute_resident
 
 const LIB = get(ENV, "GLRMB200_LIB", joinpath(@__DIR__, "..", "csrc", "libglrm_b200.so"))
 
@@ -255,6 +255,34 @@ function objective_resident(hd::B200Handle, X::Matrix{Float64}, Y::Matrix{Float6
     check(ccall((:glrmb200_objective, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Int32, Ref{Cdouble}),
                 hd.h, X, Y, include_regularization ? 1 : 0, out))
     out[]
+end
+# error_metric(glrm, domains; standardize) (evaluate_fit.jl:106-148) and impute(glrm) (evaluate_fit.jl:150) on the device:
+# domains default to each loss's own (l.domain); (code, (p0, p1)) rows as include/glrm_b200.h GLRMB200_DOMAIN_*
+domrow(d::RealDomain) = (Int32(1), 0.0, 0.0)
+domrow(d::BoolDomain) = (Int32(2), 0.0, 0.0)
+domrow(d::OrdinalDomain) = (Int32(3), Float64(d.min), Float64(d.max))
+domrow(d::CategoricalDomain) = (Int32(4), Float64(d.min), Float64(d.max))
+domrow(d::PeriodicDomain) = (Int32(5), Float64(d.T), 0.0)
+domrow(d::CountDomain) = (Int32(6), Float64(d.max_count), 0.0)
+function domtable(domains)
+    rows = [domrow(d) for d in domains]
+    Int32[r[1] for r in rows], collect(Iterators.flatten((r[2], r[3]) for r in rows))
+end
+function error_metric_resident(hd::B200Handle, glrm::GLRM, domains::Array{Domain,1}=Domain[l.domain for l in glrm.losses];
+                               standardize::Bool=false)
+    code, par = domtable(domains)
+    out = Ref{Cdouble}(0.0)
+    check(ccall((:glrmb200_error_metric, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int32}, Ptr{Cdouble}, Int32, Ref{Cdouble}),
+                hd.h, glrm.X, glrm.Y, code, par, standardize ? 1 : 0, out))
+    out[]
+end
+function impute_resident(hd::B200Handle, glrm::GLRM, domains::Array{Domain,1}=Domain[l.domain for l in glrm.losses])
+    code, par = domtable(domains)
+    m, n = size(glrm.A)
+    Ahat = Array{Float64}(undef, m, n)
+    check(ccall((:glrmb200_impute, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int32}, Ptr{Cdouble}, Ptr{Cdouble}),
+                hd.h, glrm.X, glrm.Y, code, par, Ahat))
+    Ahat
 end
 # multi-process plumbing (one Julia worker per GPU): rank 0 makes the id, everybody joins; see INTEGRATION.md
 comm_unique_id() = (id = zeros(UInt8, 128); check(ccall((:glrmb200_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id)); id)

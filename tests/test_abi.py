@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/glrm_b200.h but not exported"
     assert sorted(n for n, _, _ in _abi.SYMBOLS) == declared      # the ctypes table mirrors the header
-    assert L.glrmb200_version() == 101
+    assert L.glrmb200_version() == 102
 
 
 def test_struct_layouts_match_header():
