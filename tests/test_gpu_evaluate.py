@@ -106,3 +106,20 @@ def test_error_metric_on_a_fitted_fully_observed_handle():
         got = lrm.error_metric(g, engine=eng)
     want = impute_ref.error_metric(g, [lrm.loss_domain(l) for l in g.losses], _ystart(g))
     assert abs(got - want) <= 1e-10 * abs(want)
+
+
+def test_imputed_data_has_zero_error_metric_on_the_device():
+    """The reference's own consistency test (test/err_test.jl:35,48-51) through the C ABI: a table made by glrmb200_impute
+    scores exactly 0 under glrmb200_error_metric with the same factors and domains."""
+    losses = [lrm.QuadLoss(), lrm.L1Loss(), lrm.HuberLoss(), lrm.PeriodicLoss(1.0), lrm.OrdinalHingeLoss(1, 10), lrm.LogisticLoss(),
+              lrm.WeightedHingeLoss(), lrm.MultinomialLoss(4), lrm.OrdisticLoss(5)]
+    m, n, k = 100, len(losses), 5
+    d = sum(l.embedding_dim() for l in losses)
+    X, Y = synth.normal_matrix(4, 1, k, m), synth.normal_matrix(4, 2, k, d)
+    seed_A = np.ones((m, n))                       # any table inside every label domain: only its shape matters for impute
+    g0 = lrm.GLRM(seed_A, losses, lrm.ZeroReg(), lrm.ZeroReg(), k, X=X, Y=Y)
+    A = lrm.impute(g0)
+    assert np.isfinite(A).all()
+    g = lrm.GLRM(A, losses, lrm.ZeroReg(), lrm.ZeroReg(), k, X=X, Y=Y)
+    assert lrm.error_metric(g, standardize=True) == 0.0
+    assert lrm.error_metric(g, standardize=False) == 0.0

@@ -431,7 +431,7 @@ def test_full_size_config2_properties():
     assert (obj2 == obj).all() and (X2 == X).all() and (Y2 == Y).all()           # deterministic reduction trees
 
 
-# ---- the fully observed (dense) path: csrc/glrm_dense.cuh ----------------------------------------------------------------
+# ---- the fully observed (dense) path: csrc/glrm_dense_mma.cuh (tensor cores); GLRMB200_DENSE_MMA=0: csrc/glrm_dense.cuh ----------------------------------------------------------------
 def dense_problem(m=150, n=90, k=7, seed=40, losses=None, rx=None, ry=None, labels=None):
     P = synth.normal_matrix(seed, 1, m, 3)
     Q = synth.normal_matrix(seed, 2, 3, n)
@@ -450,10 +450,11 @@ def dense_problem(m=150, n=90, k=7, seed=40, losses=None, rx=None, ry=None, labe
                     X=0.4 * synth.normal_matrix(seed, 4, k, m), Y=0.4 * synth.normal_matrix(seed, 5, k, d))
 
 
-@pytest.mark.parametrize("k", [1, 3, 8, 13, 20, 33, 50, 64, 70, 96, 100, 104, 130])
+@pytest.mark.parametrize("k", [1, 3, 8, 13, 20, 28, 33, 50, 64, 70, 96, 100, 104, 130])
 def test_dense_path_every_rank_tile(orc, k):
-    """Fully observed problems run the streaming kernels for k <= 104 (8 register-tile shapes) and the gather kernels above;
-    rows not a multiple of the 64-row tile, columns spanning two 64-column chunks."""
+    """Fully observed problems run the tensor-core kernels for k <= 104 (one instantiation per factor width NT = 1, 2, 3, 4,
+    6, 8, 10, 12, 13 n-tiles of 8 indices: every one is hit here) and the gather kernels above; rows not a multiple of the
+    128-row tile, 90 columns = three 32-column stages (resident in shared memory)."""
     check(orc, dense_problem(k=k), lrm.ProxGradParams(max_iter=5))
 
 
@@ -468,6 +469,30 @@ def test_dense_path_equals_gather_path(orc, monkeypatch):
     np.testing.assert_allclose(a["alpharow"], b["alpharow"], rtol=1e-9)
     np.testing.assert_allclose(a["X"], b["X"], rtol=1e-6, atol=1e-9)
     assert a["profile"]["x_trials"] == b["profile"]["x_trials"] and a["profile"]["y_trials"] == b["profile"]["y_trials"]
+
+
+def test_dense_tensor_core_and_fma_kernels_agree(orc, monkeypatch):
+    """The two kernel families of the fully observed path (DMMA tensor-core kernels, and the FP64-FMA kernels that serve the
+    shapes whose tensor-core tiles do not fit shared memory) on the same uniform and heterogeneous fits."""
+    lv = 4
+    m, n = 300, 40
+    base = synth.normal_matrix(51, 1, m, 3) @ synth.normal_matrix(51, 2, 3, n)
+    A = np.asfortranarray(base.copy())
+    A[:, 20:30] = np.where(base[:, 20:30] >= 0, 1.0, -1.0)
+    A[:, 30:] = np.clip(np.floor(np.abs(base[:, 30:]) * 2) + 1, 1, lv)
+    mixed = [lrm.QuadLoss()] * 20 + [lrm.HingeLoss()] * 10 + [lrm.MultinomialLoss(lv)] * 10
+    for g in (dense_problem(m=333, n=70, k=20, seed=50),
+              lrm.GLRM(A, mixed, lrm.QuadReg(0.1), lrm.QuadReg(0.1), 12, X=0.3 * synth.normal_matrix(51, 4, 12, m),
+                       Y=0.3 * synth.normal_matrix(51, 5, 12, 20 + 10 + 10 * lv))):
+        p = lrm.ProxGradParams(max_iter=6)
+        monkeypatch.setenv("GLRMB200_DENSE_MMA", "1")
+        a = engine_fit(g, p)
+        monkeypatch.setenv("GLRMB200_DENSE_MMA", "0")
+        b = engine_fit(g, p)
+        assert_traj_close(a["objective"], b["objective"], 1e-9, "tensor-core vs FMA dense kernels")
+        np.testing.assert_allclose(a["alphacol"], b["alphacol"], rtol=1e-9)
+        assert a["profile"]["x_trials"] == b["profile"]["x_trials"] and a["profile"]["y_trials"] == b["profile"]["y_trials"]
+        assert_traj_close(a["objective"], run_oracle(orc, g, p, mode=1)["objective"], 1e-7, "tensor-core kernels vs oracle")
 
 
 @pytest.mark.parametrize("reg", REG_CASES + [lrm.UnitOneSparseConstraint(), lrm.NonNegConstraint(), lrm.ZeroReg()],
