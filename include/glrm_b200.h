@@ -249,6 +249,10 @@ int glrmb200_comm_init(glrmb200_handle h, const uint8_t id[128]);
 /* Host-only shard planner (no device needed): contiguous ranges balanced by observation count.
  * ptr = row_ptr / col_ptr ([count+1]) or NULL (balance by unit count); bounds receives nranks+1 entries. */
 int glrmb200_plan_shards(const int64_t* ptr, int64_t count, int32_t nranks, int64_t* bounds);
+/* ... and the row ranges of a FULLY OBSERVED problem on nranks GPUs (whole groups of row blocks, multiples of 64 rows; see
+ * glrmb200_shard): bounds receives nranks+1 entries.  GLRMB200_E_UNSUPPORTED when such a problem would not be row-sharded
+ * (nranks not in {1, 2, 4, 8} or fewer than 512 rows per rank). */
+int glrmb200_plan_dense_rows(int64_t m, int32_t nranks, int64_t* bounds);
 
 /* Fused exchange over NVLink peer memory (optional, after glrmb200_comm_init).  Every rank exports CUDA IPC
  * handles of its factor replicas (glrmb200_ipc_export, GLRMB200_IPC_BYTES bytes), the host all-gathers the blobs

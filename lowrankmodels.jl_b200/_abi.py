@@ -85,6 +85,7 @@ SYMBOLS = [
     ("glrmb200_get_stepsizes", C.c_int, [Handle, c_double_p, c_double_p]),
     ("glrmb200_destroy", C.c_int, [Handle]),
     ("glrmb200_plan_shards", C.c_int, [c_int64_p, C.c_int64, C.c_int32, c_int64_p]),
+    ("glrmb200_plan_dense_rows", C.c_int, [C.c_int64, C.c_int32, c_int64_p]),
 ]
 
 _lib = None

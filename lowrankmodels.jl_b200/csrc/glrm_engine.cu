@@ -521,6 +521,23 @@ static void dense_blocks(int64_t m, int* bg, int64_t* rows_per_block) {
   *rows_per_block = t * DN_TM;
 }
 
+// rows of a fully observed problem on `nranks` GPUs: rank r owns the row-block groups [r G / N, (r + 1) G / N)
+static void dense_row_bounds(int64_t m, int nranks, int64_t* bounds) {
+  int bg;
+  int64_t rpb;
+  dense_blocks(m, &bg, &rpb);
+  for (int r = 0; r <= nranks; ++r) bounds[r] = std::min<int64_t>(m, (int64_t)(r * DN_GROUPS / nranks) * bg * rpb);
+}
+extern "C" int glrmb200_plan_dense_rows(int64_t m, int32_t nranks, int64_t* bounds) {
+  if (!bounds || m <= 0) return fail(GLRMB200_E_INVALID, "bad argument");
+  if (nranks == 1) { bounds[0] = 0; bounds[1] = m; return 0; }
+  if (!((nranks == 2 || nranks == 4 || nranks == 8) && m >= 512 * (int64_t)nranks))
+    return fail(GLRMB200_E_UNSUPPORTED, "row sharding of a fully observed problem needs 2, 4 or 8 ranks and m >= 512 per rank "
+                                        "(otherwise the handle shards observation lists: glrmb200_plan_shards)");
+  dense_row_bounds(m, nranks, bounds);
+  return 0;
+}
+
 static int dense_setup(glrmb200_engine* E, const glrmb200_problem* P) {
   DenseHost& D = E->dn;
   const int64_t m = E->m, n = E->n, d = E->d;
@@ -1075,9 +1092,7 @@ static int create_impl(glrmb200_engine* E, const glrmb200_problem* P, int flags)
   }   // (observation lists: checked, sharded and uploaded by load_lists below)
   if (E->obs_full && want_dense && E->nranks > 1) {
     // mode B: rank r owns the row-block groups [r * G / N, (r + 1) * G / N); every rank updates all of Y
-    int bg; int64_t rpb;
-    dense_blocks(m, &bg, &rpb);
-    for (int r = 0; r <= E->nranks; ++r) R.bounds[(size_t)r] = std::min<int64_t>(m, (int64_t)(r * DN_GROUPS / E->nranks) * bg * rpb);
+    dense_row_bounds(m, E->nranks, R.bounds.data());
     C.bounds[0] = 0;
     for (int r = 1; r <= E->nranks; ++r) C.bounds[(size_t)r] = n;
   }

@@ -21,6 +21,14 @@ def plan_shards(ptr, count, nranks):
     return b
 
 
+def plan_dense_rows(m, nranks):
+    """Row ranges of a fully observed problem on nranks GPUs (C ABI glrmb200_plan_dense_rows; host-only): whole groups of row
+    blocks, so that the Y sweep's fixed-order sums over the 8 groups do not depend on the number of GPUs."""
+    b = np.zeros(nranks + 1, dtype=np.int64)
+    _abi.check(_abi.lib().glrmb200_plan_dense_rows(int(m), int(nranks), _abi.i64ptr(b)))
+    return b
+
+
 def shard_bounds(ep, nranks):
     """(row_bounds, col_bounds) for an EncodedProblem, exactly as glrmb200_create computes them."""
     s = ep.struct

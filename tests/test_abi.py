@@ -99,3 +99,21 @@ def test_host_mirror_constructor_checks():
     with pytest.raises(ValueError):                                              # nested wrappers: no device implementation
         lrm.encode_problem(lrm.GLRM(A, lrm.QuadLoss(), lrm.fixed_latent_features(lrm.lastentry1(lrm.QuadReg()), [1.0]),
                                     lrm.ZeroReg(), 2))
+
+
+def test_plan_dense_rows_is_nested_and_aligned():
+    """Host-only planner of the row-sharded fully observed mode: shards tile [0, m), start on 64-row tiles, and the shards of
+    2 and 4 ranks are unions of the 8 groups (the reduction tree of the Y sweep does not depend on the number of GPUs)."""
+    from lowrankmodels_b200 import distributed as D
+    for m in (4096, 19531, 62500, 1_000_000, 10_000_000):
+        b8 = D.plan_dense_rows(m, 8)
+        assert b8[0] == 0 and b8[-1] == m and (np.diff(b8) > 0).all() and (b8[:-1] % 64 == 0).all()
+        assert np.diff(b8).max() <= 1.35 * m / 8 + 64                       # the last groups are not left (nearly) empty
+        for nranks in (1, 2, 4):
+            b = D.plan_dense_rows(m, nranks)
+            assert b[0] == 0 and b[-1] == m and set(b.tolist()) <= set(b8.tolist())
+    with pytest.raises(_abi.GLRMB200Error) as ei:
+        D.plan_dense_rows(100, 2)                                            # too small to shard by rows: observation-list mode
+    assert ei.value.code == -2
+    with pytest.raises(_abi.GLRMB200Error):
+        D.plan_dense_rows(100000, 3)

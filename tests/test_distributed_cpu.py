@@ -89,6 +89,34 @@ def _worker(rank, world, port, q):
         want = oracle_py.fit(ep, ps, Xo, Yo, mode=1, nthreads=1)
         assert (X == Xo).all() and (Y == Yo).all()
         np.testing.assert_allclose(traj, want["objective"][1:], rtol=1e-13)
+
+        # fully observed problems (mode B): rows are sharded by whole groups of row blocks (host-only planner), every rank sums
+        # its groups, the 8 group sums are gathered and totalled in group order -> the same bits as one process
+        m_dense = 19531
+        b2, b8 = D.plan_dense_rows(m_dense, world), D.plan_dense_rows(m_dense, 8)
+        assert b2[0] == 0 and b2[-1] == m_dense and set(b2.tolist()) <= set(b8.tolist())      # shards are unions of groups
+        vals = synth.normal_matrix(7, 9, 5, m_dense)                                         # a (5, m) array summed over rows
+        gsum = np.zeros((8, 5))
+        for gidx in range(8):
+            lo, hi = int(b8[gidx]), int(b8[gidx + 1])
+            if int(b2[rank]) <= lo and hi <= int(b2[rank + 1]):                               # a group this rank owns
+                for e in range(lo, hi):
+                    gsum[gidx] += vals[:, e]
+        owner = [next(r for r in range(world) if int(b2[r]) <= int(b8[gi]) and int(b8[gi + 1]) <= int(b2[r + 1])) for gi in range(8)]
+        for gidx in range(8):
+            tg = torch.from_numpy(gsum[gidx].copy())
+            dist.broadcast(tg, src=owner[gidx])
+            gsum[gidx] = tg.numpy()
+        total = np.zeros(5)
+        for gidx in range(8):
+            total += gsum[gidx]
+        alone = np.zeros(5)
+        for gidx in range(8):
+            part = np.zeros(5)
+            for e in range(int(b8[gidx]), int(b8[gidx + 1])):
+                part += vals[:, e]
+            alone += part
+        assert (total == alone).all()
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
